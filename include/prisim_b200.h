@@ -1,0 +1,199 @@
+/* prisim_b200 -- C-ABI of the B200-native visibility engine (libprisim_b200.so).
+ *
+ * PRISim (nithyanandan/PRISim v2.2.1) has no FFI: its seam is the Python method surface of
+ * prisim/interferometry.py.  Every entry point below names the reference code it replaces
+ * (file:line relative to the reference root).  The Python shim in prisim_b200/ binds these with
+ * ctypes (prisim_b200/_lib.py); INTEGRATION.md shows the stub a PRISim maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; all `d_` pointers are DEVICE pointers owned by the caller; `h_` pointers
+ *     are HOST pointers read during the call.
+ *   - every function returns 0 on success or a negative PB200_E* code; pb200_last_error(ctx)
+ *     gives the message.  Nothing throws or aborts.
+ *   - work is enqueued on the CUDA stream passed as `stream` (a cudaStream_t cast to void*;
+ *     NULL = legacy default stream); functions do not synchronise unless stated.
+ *   - one pb200_ctx per device per host thread; a ctx is not re-entrant.
+ *   - visibilities are [nbl, nchan] row-major (channel fastest), complex128 = interleaved
+ *     (re, im) doubles.
+ */
+#ifndef PRISIM_B200_H
+#define PRISIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_VERSION 100
+
+#define PB200_OK            0
+#define PB200_EINVAL       -1   /* bad argument */
+#define PB200_ECUDA        -2   /* CUDA runtime error (message has the CUDA string) */
+#define PB200_ENOMEM       -3
+#define PB200_EUNSUPPORTED -4
+
+typedef struct pb200_ctx pb200_ctx;
+
+int pb200_version(void);
+int pb200_ctx_create(pb200_ctx** out, int device);
+void pb200_ctx_destroy(pb200_ctx* ctx);
+const char* pb200_last_error(const pb200_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's "gpu_launches") */
+long long pb200_launch_count(const pb200_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sky coordinates -> direction cosines, horizon / ROI cull, order-preserving compaction.
+ * Replaces interferometry.py:6174-6219 (hadec2altaz :6177, altitude cut :6216, selection :6219)
+ * and the alt>=0 pre-selection of scripts/run_prisim.py:1872-1876.
+ *
+ *   coords: PB200_SKY_ALTAZ  d_skypos = [nsrc0,2] (alt, az) degrees
+ *           PB200_SKY_HADEC  d_skypos = [nsrc0,2] (HA, Dec) degrees, needs latitude_deg
+ *           PB200_SKY_DIRCOS d_skypos = [nsrc0,3] (l, m, n) East-North-Up direction cosines
+ *   keep source s  iff  alt_s >= 90 - roi_radius_deg   (roi_center='zenith', reference default
+ *   roi_radius = 90), or, when h_roi_center (host, [3] ENU direction cosines) is not NULL, iff the
+ *   source lies within roi_radius_deg of that direction (roi_center='pointing_center', :6213)
+ *   outputs (capacity nsrc0): d_dircos [nsrc,3] fp64, d_index [nsrc] int32 (ascending, = the
+ *   reference's m2 / obs_catalog_indices), *h_nsrc (host; the call synchronises the stream).
+ */
+#define PB200_SKY_ALTAZ  0
+#define PB200_SKY_HADEC  1
+#define PB200_SKY_DIRCOS 2
+int pb200_sky_cull(pb200_ctx* ctx, const double* d_skypos, int nsrc0, int coords, double latitude_deg,
+                   double roi_radius_deg, const double* h_roi_center, double* d_dircos, int32_t* d_index,
+                   int* h_nsrc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Source spectrum x primary beam -> amplitude table.
+ * Replaces interferometry.py:6249 (skymodel.generate_spectrum), :6251-6254 (beam, pbfluxes) and
+ * the beam-table step of ROI_parameters.append_settings (:4583-4615); beam maths from
+ * primary_beams.py:9-441 (wrapper), :517-625 (Airy), :629-730 (Gaussian), :975-1235 (dipole),
+ * :812-971 (ground plane), :1239-1478 (analytic n1 x n2 array), :1482-1754 (phased array).
+ */
+#define PB200_BEAM_DELTA    0   /* primary_beams.py:355-359 */
+#define PB200_BEAM_AIRY     1   /* 'hera'/'hirax' presets (:239-247) and shape 'dish' (:369-373) */
+#define PB200_BEAM_GAUSSIAN 2   /* shape 'gaussian' (:374-377) */
+#define PB200_BEAM_DIPOLE   3   /* 'mwa_dipole'/'paper' presets (:320-349), shape 'dipole' (:360-368) */
+#define PB200_BEAM_TABLE    4   /* caller-supplied pbeam[nsrc,nchan] (roi_info['pbeam'], interferometry.py:6189-6202) */
+
+#define PB200_ARRAY_NONE     0
+#define PB200_ARRAY_ANALYTIC 1  /* isotropic_radiators_array_field_pattern, 'mwa' preset without pointing_info (:273-285) */
+#define PB200_ARRAY_ELEMENTS 2  /* array_field_pattern with element positions, delays and gains (:287-316, :385-416) */
+
+#define PB200_DIPOLE_GENERAL  0 /* primary_beams.py:1224-1225 (wrapper default, :11-12) */
+#define PB200_DIPOLE_SHORT    1 /* :1216-1218 */
+#define PB200_DIPOLE_HALFWAVE 2 /* :1220-1222 */
+
+typedef struct pb200_beam_desc {
+  int32_t element;            /* PB200_BEAM_* */
+  int32_t array_mode;         /* PB200_ARRAY_* : multiplies the element FIELD pattern */
+  int32_t dipole_mode;        /* PB200_DIPOLE_* */
+  int32_t achromatic;         /* !=0: evaluate at ref_freq_hz and broadcast (interferometry.py:4583-4588) */
+  double  size;               /* dish diameter / Gaussian FWHM aperture / dipole length [m] */
+  double  pointing[3];        /* element pointing centre, ENU direction cosines (Airy/Gaussian) */
+  double  orientation[3];     /* dipole axis, ENU direction cosines (:1201 default east) */
+  double  groundplane;        /* height [m] above ground plane; <= 0: none (:418-439) */
+  double  ground_scale;       /* modifier['scale'], 0 = no modifier (:955-958) */
+  double  ground_max;         /* modifier['max'], <= 0 = no clip (:959-960) */
+  double  ref_freq_hz;        /* used when achromatic */
+  /* analytic array (:1430-1478) */
+  int32_t nax1, nax2;
+  double  sep1, sep2, east2ax1_deg;
+  double  array_pointing[3];  /* ENU direction cosines of the array pointing centre */
+  /* element array (:1595-1754): all arrays are DEVICE pointers of n_elements entries;
+     d_delays/d_gains are [n_elements, nrand] (delay jitter / gain jitter realisations already
+     applied by the caller, :1655/:1666); pattern = mean over nrand of |E * F|^2 (:317, :416) */
+  int32_t n_elements, nrand;
+  const double* d_element_locs;   /* [n_elements,3] metres ENU */
+  const double* d_delays;         /* seconds */
+  const double* d_gains;
+} pb200_beam_desc;
+
+/* power-law spectrum (astroutils SkyModel 'func'/'power-law', parameters as built at
+ * scripts/run_prisim.py:1629-1636): S = offset + scale (f/f_ref)^index.  Arrays are indexed by
+ * the ORIGINAL catalogue index (gathered through d_index).  d_flux_offset may be NULL.
+ * d_spectrum != NULL selects a tabulated spectrum [nsrc0, nchan] (fp64) instead.             */
+typedef struct pb200_spectrum_desc {
+  const double* d_flux_scale;
+  const double* d_index;
+  const double* d_freq_ref;
+  const double* d_flux_offset;
+  const double* d_spectrum;
+} pb200_spectrum_desc;
+
+/* Amplitude-table layout (consumed by pb200_skyvis): fp32, channel slabs of PB200_SLAB channels,
+ * each slab a dense [nsrc_pad, PB200_SLAB] matrix; nsrc_pad = nsrc rounded up to PB200_SRC_TILE,
+ * padding rows/channels are zero.  pb200_amp_bytes gives the buffer size.                     */
+#define PB200_SLAB     128
+#define PB200_SRC_TILE 32
+size_t pb200_amp_bytes(int nsrc, int nchan);
+int pb200_nsrc_pad(int nsrc);
+
+/* d_dircos/d_index from pb200_sky_cull (nsrc entries); h_freqs [nchan] Hz (host);
+ * d_pbeam: only for PB200_BEAM_TABLE, fp64 [nsrc, nchan] rows aligned with d_index order.
+ * Output: d_amp (layout above).                                                               */
+int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_index, int nsrc,
+                    const pb200_spectrum_desc* spec, const pb200_beam_desc* beam, const double* d_pbeam,
+                    const double* h_freqs, int nchan, float* d_amp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The phase sum.  Replaces interferometry.py:6155-6165 (phase-centre delays), :6255 +
+ * baseline_delay_horizon.py:240 (geometric delays), :6258-6283 (extended-source taper) and
+ * :6332-6340 / :6348-6376 (phase matrix, exp, sum over sources):
+ *     V[b,f] = sum_s amp[s,f] w[s,b,f] exp(-2 pi i f ((s_s - s_pc) . b) / c)
+ *   d_dircos   [nsrc,3] fp64 source direction cosines (ENU)
+ *   d_amp      amplitude table from pb200_amp_table
+ *   d_bl       [nbl,3] fp64 baselines, local ENU metres
+ *   h_pc       [3] phase-centre direction cosines (host)
+ *   h_freqs    [nchan] Hz (host).  Uniformly spaced channels take the recurrence kernel;
+ *              anything else takes the direct (sincospi per term) kernel.
+ *   d_src_fwhm_deg  NULL, or [nsrc] sqrt(major*minor) FWHM in degrees (:6267) -> taper on
+ *   d_vis      [nbl,nchan] complex128, overwritten
+ *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT
+ */
+#define PB200_SKYVIS_AUTO       0
+#define PB200_SKYVIS_RECURRENCE 1
+#define PB200_SKYVIS_DIRECT     2
+int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float* d_amp, int nsrc,
+                 const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
+                 const double* d_src_fwhm_deg, void* d_vis, int method, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Thermal noise + gains.  Replaces interferometry.py:6676-6693 (generate_noise) and :6707-6722
+ * (add_noise):  rms = 2 k Tsys / (A_eff eff_Q sqrt(df t_acc)) / Jy  (flux_unit_k != 0: the K
+ * form :6689);  noise = rms/sqrt2 (N + iN);  vis = gains*skyvis + noise.
+ * Arrays are [nbl,nchan] for one snapshot.  Normal deviates come from Philox4x32-10 keyed by
+ * (seed, global element index = (snapshot*nbl_total + bl_offset + b)*nchan + f), so a result does
+ * not depend on how baselines are sharded across GPUs.  d_gains may be NULL (unity), d_aeff /
+ * d_effq are [nbl,nchan].  Any of d_rms / d_noise / d_vis may be NULL to skip that output.
+ */
+int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d_tsys, const double* d_aeff,
+                const double* d_effq, const void* d_gains, int nbl, int nchan, double df, double t_acc,
+                int flux_unit_k, uint64_t seed, int snapshot, int bl_offset, int nbl_total,
+                double* d_rms, void* d_noise, void* d_vis, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Windowed delay transform.  Replaces interferometry.py:8114-8134 and delay_spectrum.py:1305-1327:
+ *   X = fftshift(ifft(pad_right(x * bp * wts, npad))) * (nchan+npad) * df, then linear-interp
+ *   decimation by (1+pad) when `downsample`.
+ *   d_x [nrows,nchan] complex128 (NULL: transform bp*wts only -> lag_kernel), d_bp / d_wts
+ *   [nrows,nchan] fp64 or NULL (=1); wts_row_stride/bp_row_stride = 0 broadcasts one row.
+ *   d_out [nrows, nout] complex128 with nout = pb200_delay_nout(nchan, pad, downsample).
+ */
+int pb200_delay_nout(int nchan, double pad, int downsample);
+int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, long long bp_row_stride,
+                          const double* d_wts, long long wts_row_stride, int nrows, int nchan, double df,
+                          double pad, int downsample, void* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Issue-rate microbenchmark (FP32 FMA lanes / clk / SM etc.) used for the measured roofline
+ * denominator.  Fills out[0..n) with: [0] FFMA lane-ops/s, [1] FFMA
+ * lane-ops/clk/SM, [2] MUFU lane-ops/s, [3] DFMA lane-ops/s, [4] SM clock (Hz) seen.  Synchronises.
+ */
+int pb200_microbench(pb200_ctx* ctx, double* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRISIM_B200_H */

@@ -1,0 +1,41 @@
+// Context management for libprisim_b200.so.
+#include "common.cuh"
+#include <new>
+
+extern "C" {
+
+int pb200_version(void) { return PB200_VERSION; }
+
+int pb200_ctx_create(pb200_ctx** out, int device) {
+  if (!out) return PB200_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return PB200_ECUDA;   // no CPU fallback: fail loudly
+  if (device < 0 || device >= n) return PB200_EINVAL;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PB200_ECUDA;
+  if (prop.major != 10) return PB200_EUNSUPPORTED;                           // sm_100a cubins only
+  pb200_ctx* ctx = new (std::nothrow) pb200_ctx();
+  if (!ctx) return PB200_ENOMEM;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PB200_ECUDA; }
+  *out = ctx;
+  return PB200_OK;
+}
+
+void pb200_ctx_destroy(pb200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->twiddle) cudaFree(ctx->twiddle);
+  delete ctx;
+}
+
+const char* pb200_last_error(const pb200_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+long long pb200_launch_count(const pb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// Shared declarations for libprisim_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/prisim_b200.h"
+
+struct pb200_ctx {
+  int device;
+  int sm_count;
+  char err[512];
+  long long launches;
+  // scratch owned by the ctx (grown on demand, freed in pb200_ctx_destroy)
+  void* scratch[4];
+  size_t scratch_bytes[4];
+  // cached twiddle table for the delay transform
+  void* twiddle;
+  int twiddle_n;
+};
+
+#define PB_SPEED_OF_LIGHT 299792458.0   // scipy.constants.c
+#define PB_BOLTZMANN 1.380649e-23       // scipy.constants.k
+#define PB_JY 1.0e-26
+
+inline int pb_fail(pb200_ctx* ctx, int code, const char* fmt, const char* a = "", const char* b = "") {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+  return code;
+}
+
+#define PB_CUDA(ctx, call)                                                                    \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return pb_fail((ctx), PB200_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define PB_CHECK_LAUNCH(ctx, name)                                                            \
+  do {                                                                                        \
+    (ctx)->launches++;                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) return pb_fail((ctx), PB200_ECUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+// grow-only scratch slot
+inline int pb_scratch(pb200_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    size_t want = bytes + (bytes >> 2) + 256;
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+    if (e != cudaSuccess) return pb_fail(ctx, PB200_ENOMEM, "cudaMalloc scratch: %s", cudaGetErrorString(e));
+    ctx->scratch_bytes[slot] = want;
+  }
+  *out = ctx->scratch[slot];
+  return PB200_OK;
+}
+
+static inline int pb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,191 @@
+"""Thin typed wrappers over the C-ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Each function corresponds to one entry point of ``include/prisim_b200.h`` and, through it, to the
+reference lines cited there.  No numerical work happens in Python here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as NP
+import torch
+
+from . import _lib
+from ._lib import BeamDesc, SpectrumDesc, _ptr, get_context
+
+
+def _dev(device):
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else 0
+    return int(device)
+
+
+def _f64(x, device):
+    """Host array-like or tensor -> contiguous float64 CUDA tensor on `device`."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda:{0}".format(device), dtype=torch.float64).contiguous()
+    return torch.as_tensor(NP.ascontiguousarray(x, dtype=NP.float64)).to("cuda:{0}".format(device))
+
+
+def _h64(x):
+    return NP.ascontiguousarray(NP.asarray(x, dtype=NP.float64))
+
+
+def sky_cull(skypos, coords, latitude_deg=0.0, roi_radius_deg=90.0, roi_center_dircos=None, device=None):
+    """``pb200_sky_cull``: returns (dircos [nsrc,3] f64, index [nsrc] i32) of the sources kept.
+    Replaces interferometry.py:6174-6219."""
+    device = _dev(device)
+    ctx = get_context(device)
+    skypos = _f64(skypos, device)
+    nsrc0 = skypos.shape[0] if skypos.ndim == 2 else 0
+    code = {"altaz": _lib.SKY_ALTAZ, "hadec": _lib.SKY_HADEC, "dircos": _lib.SKY_DIRCOS}[coords]
+    dircos = torch.empty((max(nsrc0, 1), 3), dtype=torch.float64, device=skypos.device)
+    index = torch.empty((max(nsrc0, 1),), dtype=torch.int32, device=skypos.device)
+    n = C.c_int(0)
+    center = None if roi_center_dircos is None else _h64(roi_center_dircos)
+    ctx.check(ctx.lib.pb200_sky_cull(ctx.handle, _ptr(skypos), nsrc0, code, float(latitude_deg),
+                                     float(roi_radius_deg), _ptr(center), _ptr(dircos), _ptr(index),
+                                     C.byref(n), ctx.stream()))
+    return dircos[: n.value], index[: n.value]
+
+
+def make_beam_desc(**kw):
+    """Fill a ``pb200_beam_desc``; device arrays for the element array are kept alive on the
+    returned object (attribute ``_keep``)."""
+    b = BeamDesc()
+    b.element = kw.get("element", _lib.BEAM_DELTA)
+    b.array_mode = kw.get("array_mode", _lib.ARRAY_NONE)
+    b.dipole_mode = kw.get("dipole_mode", _lib.DIPOLE_GENERAL)
+    b.achromatic = int(kw.get("achromatic", 0))
+    b.size = float(kw.get("size", 0.0))
+    b.pointing = (C.c_double * 3)(*[float(v) for v in kw.get("pointing", (0.0, 0.0, 1.0))])
+    b.orientation = (C.c_double * 3)(*[float(v) for v in kw.get("orientation", (1.0, 0.0, 0.0))])
+    b.groundplane = float(kw.get("groundplane", 0.0) or 0.0)
+    b.ground_scale = float(kw.get("ground_scale", 0.0) or 0.0)
+    b.ground_max = float(kw.get("ground_max", 0.0) or 0.0)
+    b.ref_freq_hz = float(kw.get("ref_freq_hz", 0.0))
+    b.nax1 = int(kw.get("nax1", 0)); b.nax2 = int(kw.get("nax2", 0))
+    b.sep1 = float(kw.get("sep1", 0.0)); b.sep2 = float(kw.get("sep2", 0.0))
+    b.east2ax1_deg = float(kw.get("east2ax1_deg", 0.0))
+    b.array_pointing = (C.c_double * 3)(*[float(v) for v in kw.get("array_pointing", (0.0, 0.0, 1.0))])
+    b.n_elements = int(kw.get("n_elements", 0)); b.nrand = int(kw.get("nrand", 1))
+    keep = []
+    for name in ("d_element_locs", "d_delays", "d_gains"):
+        t = kw.get(name, None)
+        keep.append(t)
+        setattr(b, name, None if t is None else t.data_ptr())
+    b._keep = keep
+    return b
+
+
+def amp_table(dircos, index, nsrc, spectrum, beam, freqs_hz, pbeam=None, device=None):
+    """``pb200_amp_table``: fp32 amplitude table (slab layout) for the culled sources.
+    `spectrum` is a dict of device tensors {flux_scale, index, freq_ref[, flux_offset]} indexed by
+    catalogue index, or {spectrum: [nsrc0,nchan]}.  Replaces interferometry.py:6249-6254."""
+    device = _dev(device)
+    ctx = get_context(device)
+    freqs = _h64(freqs_hz)
+    nchan = freqs.size
+    nbytes = ctx.lib.pb200_amp_bytes(int(nsrc), int(nchan))
+    amp = torch.empty((nbytes // 4,), dtype=torch.float32, device="cuda:{0}".format(device))
+    sd = SpectrumDesc()
+    for key, field in (("flux_scale", "d_flux_scale"), ("index", "d_index"), ("freq_ref", "d_freq_ref"),
+                       ("flux_offset", "d_flux_offset"), ("spectrum", "d_spectrum")):
+        t = spectrum.get(key, None)
+        setattr(sd, field, None if t is None else t.data_ptr())
+    ctx.check(ctx.lib.pb200_amp_table(ctx.handle, _ptr(dircos), _ptr(index), int(nsrc), C.byref(sd), C.byref(beam),
+                                      _ptr(pbeam), _ptr(freqs), int(nchan), _ptr(amp), ctx.stream()))
+    return amp
+
+
+def amp_table_to_dense(amp, nsrc, nchan):
+    """Undo the slab layout: returns a [nsrc, nchan] fp32 tensor (testing / inspection)."""
+    nsrc_pad = ((max(nsrc, 1) + _lib.SRC_TILE - 1) // _lib.SRC_TILE) * _lib.SRC_TILE
+    nslab = (nchan + _lib.SLAB - 1) // _lib.SLAB
+    a = amp.view(nslab, nsrc_pad, _lib.SLAB).permute(1, 0, 2).reshape(nsrc_pad, nslab * _lib.SLAB)
+    return a[:nsrc, :nchan].contiguous()
+
+
+def dense_to_amp_table(dense):
+    """[nsrc, nchan] (any float dtype, CUDA) -> slab layout fp32 table."""
+    nsrc, nchan = dense.shape
+    nsrc_pad = ((max(nsrc, 1) + _lib.SRC_TILE - 1) // _lib.SRC_TILE) * _lib.SRC_TILE
+    nslab = (nchan + _lib.SLAB - 1) // _lib.SLAB
+    full = torch.zeros((nsrc_pad, nslab * _lib.SLAB), dtype=torch.float32, device=dense.device)
+    full[:nsrc, :nchan] = dense.to(torch.float32)
+    return full.view(nsrc_pad, nslab, _lib.SLAB).permute(1, 0, 2).contiguous().view(-1)
+
+
+def skyvis(dircos, amp, nsrc, baselines_enu, pc_dircos, freqs_hz, src_fwhm_deg=None, method="auto", out=None,
+           device=None):
+    """``pb200_skyvis``: V[nbl,nchan] complex128.  Replaces interferometry.py:6155-6165, :6255,
+    :6258-6283, :6332-6340."""
+    device = _dev(device)
+    ctx = get_context(device)
+    bl = _f64(baselines_enu, device)
+    freqs = _h64(freqs_hz)
+    pc = _h64(pc_dircos)
+    nbl, nchan = bl.shape[0], freqs.size
+    if out is None:
+        out = torch.empty((nbl, nchan), dtype=torch.complex128, device=bl.device)
+    code = {"auto": _lib.SKYVIS_AUTO, "recurrence": _lib.SKYVIS_RECURRENCE, "direct": _lib.SKYVIS_DIRECT}[method]
+    ctx.check(ctx.lib.pb200_skyvis(ctx.handle, _ptr(dircos), _ptr(amp), int(nsrc), _ptr(bl), int(nbl), _ptr(pc),
+                                   _ptr(freqs), int(nchan), _ptr(src_fwhm_deg), _ptr(out), code, ctx.stream()))
+    return out
+
+
+def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, snapshot=0, bl_offset=0, nbl_total=None, gains=None,
+          flux_unit_k=False, want=("rms", "noise", "vis")):
+    """``pb200_noise`` for one snapshot.  All tensors [nbl,nchan] on the same CUDA device.
+    Replaces interferometry.py:6676-6693 and :6707-6722."""
+    device = tsys.device.index
+    ctx = get_context(device)
+    nbl, nchan = tsys.shape
+    nbl_total = nbl if nbl_total is None else int(nbl_total)
+    rms = torch.empty((nbl, nchan), dtype=torch.float64, device=tsys.device) if "rms" in want else None
+    nz = torch.empty((nbl, nchan), dtype=torch.complex128, device=tsys.device) if "noise" in want else None
+    vis = torch.empty((nbl, nchan), dtype=torch.complex128, device=tsys.device) if "vis" in want else None
+    ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), _ptr(tsys), _ptr(aeff), _ptr(effq), _ptr(gains),
+                                  int(nbl), int(nchan), float(df), float(t_acc), int(bool(flux_unit_k)),
+                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(snapshot), int(bl_offset), nbl_total,
+                                  _ptr(rms), _ptr(nz), _ptr(vis), ctx.stream()))
+    return rms, nz, vis
+
+
+def delay_nout(nchan, pad=1.0, downsample=True):
+    return int(_lib.load().pb200_delay_nout(int(nchan), float(pad), int(bool(downsample))))
+
+
+def delay_transform(x, bp, wts, df, pad=1.0, downsample=True, nrows=None, nchan=None, device=None):
+    """``pb200_delay_transform``: x [nrows,nchan] complex128 or None; bp / wts [nrows,nchan] or
+    [nchan] (broadcast) float64 or None.  Returns [nrows, nout] complex128.
+    Replaces interferometry.py:8114-8134."""
+    ref = x if x is not None else (bp if bp is not None else wts)
+    device = ref.device.index if device is None else _dev(device)
+    ctx = get_context(device)
+    if x is not None:
+        nrows, nchan = x.shape
+
+    def stride(t):
+        if t is None:
+            return 0
+        return 0 if t.ndim == 1 or t.shape[0] == 1 else nchan
+
+    nout = delay_nout(nchan, pad, downsample)
+    out = torch.empty((nrows, nout), dtype=torch.complex128, device="cuda:{0}".format(device))
+    ctx.check(ctx.lib.pb200_delay_transform(ctx.handle, _ptr(x), _ptr(bp), stride(bp), _ptr(wts), stride(wts),
+                                            int(nrows), int(nchan), float(df), float(pad), int(bool(downsample)),
+                                            _ptr(out), ctx.stream()))
+    return out
+
+
+def microbench(device=None):
+    """``pb200_microbench``: measured FP32-FMA / MUFU / FP64 issue rates on this GPU."""
+    device = _dev(device)
+    ctx = get_context(device)
+    out = (C.c_double * 5)()
+    ctx.check(ctx.lib.pb200_microbench(ctx.handle, out, 5))
+    return {"ffma_per_s": out[0], "ffma_lanes_per_clk_per_sm": out[1], "mufu_per_s": out[2], "dfma_per_s": out[3],
+            "sm_clock_hz": out[4], "fp32_tflops": 2.0 * out[0] / 1e12}
