@@ -163,15 +163,19 @@ int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float* d_amp, int
  * Thermal noise + gains.  Replaces interferometry.py:6676-6693 (generate_noise) and :6707-6722
  * (add_noise):  rms = 2 k Tsys / (A_eff eff_Q sqrt(df t_acc)) / Jy  (flux_unit_k != 0: the K
  * form :6689);  noise = rms/sqrt2 (N + iN);  vis = gains*skyvis + noise.
- * Arrays are [nbl,nchan] for one snapshot.  Normal deviates come from Philox4x32-10 keyed by
- * (seed, global element index = (snapshot*nbl_total + bl_offset + b)*nchan + f), so a result does
- * not depend on how baselines are sharded across GPUs.  d_gains may be NULL (unity), d_aeff /
- * d_effq are [nbl,nchan].  Any of d_rms / d_noise / d_vis may be NULL to skip that output.
+ * One snapshot, logical shape [nbl,nchan].  d_tsys / d_aeff / d_effq are fp64 with element
+ * strides (row, col) given in `strides[6]` = {tsys_row, tsys_col, aeff_row, aeff_col, effq_row,
+ * effq_col}; a zero stride broadcasts (a [nchan] Tsys is {0,1}, a scalar is {0,0}).
+ * Normal deviates come from Philox4x32-10 keyed by (seed, global element index =
+ * (snapshot*nbl_total + bl_offset + b)*nchan + f), so a result does not depend on how baselines
+ * are sharded across GPUs.  d_gains (complex128 [nbl,nchan]) may be NULL (unity).  Any of d_rms /
+ * d_noise / d_vis may be NULL to skip that output.
+ * add_only != 0: d_noise is an INPUT and only d_vis = gains*skyvis + noise is written (:6722).
  */
 int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d_tsys, const double* d_aeff,
-                const double* d_effq, const void* d_gains, int nbl, int nchan, double df, double t_acc,
-                int flux_unit_k, uint64_t seed, int snapshot, int bl_offset, int nbl_total,
-                double* d_rms, void* d_noise, void* d_vis, void* stream);
+                const double* d_effq, const long long* strides, const void* d_gains, int nbl, int nchan,
+                double df, double t_acc, int flux_unit_k, uint64_t seed, int snapshot, int bl_offset,
+                int nbl_total, int add_only, double* d_rms, void* d_noise, void* d_vis, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Windowed delay transform.  Replaces interferometry.py:8114-8134 and delay_spectrum.py:1305-1327:

@@ -39,13 +39,28 @@ struct NoiseParams {
   unsigned long long seed;
   long long elem_offset;   // (snapshot*nbl_total + bl_offset)*nchan
   long long n;
+  long long st[6];         // element strides (row, col) of tsys, aeff, effq
+  int nchan;
+  int add_only;
 };
 
 __global__ void __launch_bounds__(256) k_noise(const NoiseParams P) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
+  if (P.add_only) {                                             // vis = gains*skyvis + noise (:6722)
+    double2 v = P.skyvis[i], nzi = P.noise[i];
+    if (P.gains) {
+      double2 gn = P.gains[i];
+      v = make_double2(gn.x * v.x - gn.y * v.y, gn.x * v.y + gn.y * v.x);
+    }
+    P.vis[i] = make_double2(v.x + nzi.x, v.y + nzi.y);
+    return;
+  }
+  const long long row = i / P.nchan, col = i - row * P.nchan;
+  const double tsys = P.tsys[row * P.st[0] + col * P.st[1]];
+  const double effq = P.effq[row * P.st[4] + col * P.st[5]];
   // interferometry.py:6687 / :6689
-  double rms = P.flux_unit_k ? P.scale * P.tsys[i] / P.effq[i] : P.scale * (P.tsys[i] / P.aeff[i] / P.effq[i]);
+  double rms = P.flux_unit_k ? P.scale * tsys / effq : P.scale * (tsys / P.aeff[row * P.st[2] + col * P.st[3]] / effq);
   unsigned long long g = (unsigned long long)(P.elem_offset + i);
   uint32_t r[4];
   philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0u, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r);
@@ -72,12 +87,16 @@ __global__ void __launch_bounds__(256) k_noise(const NoiseParams P) {
 }  // namespace
 
 extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d_tsys, const double* d_aeff,
-                           const double* d_effq, const void* d_gains, int nbl, int nchan, double df, double t_acc,
-                           int flux_unit_k, uint64_t seed, int snapshot, int bl_offset, int nbl_total,
-                           double* d_rms, void* d_noise, void* d_vis, void* stream_) {
+                           const double* d_effq, const long long* strides, const void* d_gains, int nbl, int nchan,
+                           double df, double t_acc, int flux_unit_k, uint64_t seed, int snapshot, int bl_offset,
+                           int nbl_total, int add_only, double* d_rms, void* d_noise, void* d_vis, void* stream_) {
   if (!ctx) return PB200_EINVAL;
-  if (nbl <= 0 || nchan <= 0 || !d_tsys || !d_effq || (!flux_unit_k && !d_aeff) || df <= 0.0 || t_acc <= 0.0)
+  if (nbl <= 0 || nchan <= 0) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: bad shape");
+  if (add_only) {
+    if (!d_skyvis || !d_noise || !d_vis) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: add_only needs skyvis, noise and vis");
+  } else if (!d_tsys || !d_effq || !strides || (!flux_unit_k && !d_aeff) || df <= 0.0 || t_acc <= 0.0) {
     return pb_fail(ctx, PB200_EINVAL, "pb200_noise: bad arguments");
+  }
   if (d_vis && !d_skyvis) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: d_vis requested without d_skyvis");
   if (nbl_total < bl_offset + nbl) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: shard exceeds nbl_total");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -85,7 +104,9 @@ extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d
   NoiseParams P;
   P.skyvis = (const double2*)d_skyvis; P.tsys = d_tsys; P.aeff = d_aeff; P.effq = d_effq;
   P.gains = (const double2*)d_gains; P.rms = d_rms; P.noise = (double2*)d_noise; P.vis = (double2*)d_vis;
-  P.scale = flux_unit_k ? 1.0 / sqrt(t_acc * df) : 2.0 * PB_BOLTZMANN / sqrt(t_acc * df) / PB_JY;
+  P.scale = add_only ? 0.0 : (flux_unit_k ? 1.0 / sqrt(t_acc * df) : 2.0 * PB_BOLTZMANN / sqrt(t_acc * df) / PB_JY);
+  for (int i = 0; i < 6; ++i) P.st[i] = strides ? strides[i] : 0;
+  P.nchan = nchan; P.add_only = add_only;
   P.flux_unit_k = flux_unit_k;
   P.seed = seed;
   P.elem_offset = ((long long)snapshot * nbl_total + bl_offset) * (long long)nchan;

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
 }
 
 // geometry staging: [nsrc_pad][4] = (l, m, n, taper coefficient), zero rows for padding
-__global__ void k_skyvis_geom(const double* __restrict__ dircos, const double* __restrict__ fwhm_deg, int nsrc,
+__global__ void k_geom_stage(const double* __restrict__ dircos, const double* __restrict__ fwhm_deg, int nsrc,
                               int nsrc_pad, double* __restrict__ geom) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsrc_pad) return;
@@ -276,8 +276,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
     delete[] tmp;
     if (e != cudaSuccess) return pb_fail(ctx, PB200_ECUDA, "freq upload: %s", cudaGetErrorString(e));
   }
-  k_skyvis_geom<<<pb_div_up(nsrc_pad, 256), 256, 0, stream>>>(d_dircos, d_src_fwhm_deg, nsrc, nsrc_pad, (double*)geom);
-  PB_CHECK_LAUNCH(ctx, "k_skyvis_geom");
+  k_geom_stage<<<pb_div_up(nsrc_pad, 256), 256, 0, stream>>>(d_dircos, d_src_fwhm_deg, nsrc, nsrc_pad, (double*)geom);
+  PB_CHECK_LAUNCH(ctx, "k_geom_stage");
 
   SkyvisParams P;
   P.amp = d_amp; P.geom = (const double*)geom; P.bl = d_bl; P.freqs = (const double*)dfreq; P.vis = (double*)d_vis;

@@ -1,0 +1,99 @@
+"""Mirror of ``prisim/delay_spectrum.py`` for ``DelaySpectrum.delay_transform``.
+
+Wraps an ``InterferometerArray`` like the reference (delay_spectrum.py:901, :1178-1188) and runs
+the same GPU kernel as ``InterferometerArray.delay_transform``; the dictionary it returns has the
+reference's keys (delay_spectrum.py:1302-1342).  Delay CLEAN, subband transforms and the power
+spectrum classes are outside the hot-path scope.
+"""
+from __future__ import annotations
+
+import numpy as NP
+
+from . import engine
+from .interferometry import InterferometerArray
+
+
+def windowing(N, shape="rect", pad_width=0, centering=True, area_normalize=False, peak=1.0, power_normalize=False):
+    """Host helper producing the spectral window run_prisim passes as ``freq_wts``
+    (scripts/run_prisim.py:954: nchan * windowing(nchan, 'bhw', area_normalize=True)).  Semantics
+    of the un-vendored ``astroutils.DSP_modules.windowing``: 'rect', 4-term Blackman-Harris 'bhw'
+    or Blackman-Nuttall 'bnw' over n/(N-1)."""
+    n = NP.arange(N)
+    if shape == "rect":
+        win = NP.ones(N)
+    elif shape in ("bhw", "bnw"):
+        a = {"bhw": (0.35875, 0.48829, 0.14128, 0.01168), "bnw": (0.3635819, 0.4891775, 0.1365995, 0.0106411)}[shape]
+        x = 2 * NP.pi * n / (N - 1)
+        win = a[0] - a[1] * NP.cos(x) + a[2] * NP.cos(2 * x) - a[3] * NP.cos(3 * x)
+    else:
+        raise ValueError("Window shape must be 'rect', 'bhw' or 'bnw'")
+    if area_normalize:
+        win = win / NP.sum(win)
+    elif power_normalize:
+        win = win / NP.sqrt(NP.sum(win ** 2))
+    else:
+        win = win * peak / NP.amax(win)
+    if pad_width > 0:
+        win = NP.pad(win, (pad_width, pad_width), mode="constant")
+    return win
+
+
+class DelaySpectrum(object):
+    def __init__(self, interferometer_array=None, init_file=None):
+        if init_file is not None:
+            raise NotImplementedError("saved delay spectra are outside the hot-path scope")
+        if not isinstance(interferometer_array, InterferometerArray):
+            raise TypeError("Input interferometer_array must be an instance of class InterferometerArray")
+        self.ia = interferometer_array                                   # delay_spectrum.py:1178
+        self.f = self.ia.channels
+        self.df = self.ia.freq_resolution
+        self.n_acc = self.ia.n_acc
+        self.horizon_delay_limits = None
+        self.pad = None
+        self.lags = None
+        self.bp_wts = None
+        self.vis_lag = self.skyvis_lag = self.vis_noise_lag = self.lag_kernel = None
+
+    @property
+    def bp(self):
+        return self.ia.bp
+
+    def delay_transform(self, pad=1.0, freq_wts=None, downsample=True, action=None, verbose=True):
+        """delay_spectrum.py:1224-1342."""
+        if not isinstance(pad, (int, float)):
+            raise TypeError("pad fraction must be a scalar value.")
+        if pad < 0.0:
+            pad = 0.0
+        if not isinstance(downsample, bool):
+            raise TypeError("Input downsample must be of boolean type")
+        ia = self.ia
+        nbl, nchan = ia.baselines.shape[0], ia.channels.size
+        getter = ia._bp_wts if freq_wts is None else ia._freq_wts_getter(freq_wts)
+        lags = NP.fft.fftshift(NP.fft.fftfreq(int(nchan * (1 + pad)), d=self.df))           # :1305
+        out = {"vis_lag": [], "skyvis_lag": [], "vis_noise_lag": [], "lag_kernel": []}
+        src = {"vis_lag": ia._vis, "skyvis_lag": ia._skyvis, "vis_noise_lag": ia._noise}
+        for t in range(len(ia._skyvis)):
+            bp = ia._bp[t]
+            wts = None if getter is None else getter(t)
+            for key, lst in src.items():
+                if lst:
+                    out[key].append(engine.delay_transform(lst[t], bp, wts, self.df, pad=pad, downsample=downsample))
+            krows = nbl if (bp.ndim == 2 or (wts is not None and wts.ndim == 2)) else 1
+            kern = engine.delay_transform(None, bp, wts, self.df, pad=pad, downsample=downsample, nrows=krows,
+                                          nchan=nchan, device=ia.device)
+            out["lag_kernel"].append(kern if krows == nbl else kern[0])
+        if downsample and pad > 0.0:                                                          # :1327
+            pos = NP.arange(0, lags.size, 1 + pad)
+            lags = NP.interp(pos, NP.arange(lags.size), lags)
+        result = {"pad": pad, "lags": lags,
+                  "freq_wts": (NP.ones((nbl, nchan, len(ia._skyvis))) if getter is None else
+                               ia._stack([getter(t) for t in range(len(ia._skyvis))], expand=True))}
+        for key, lst in out.items():
+            result[key] = ia._stack(lst, expand=(key == "lag_kernel")) if lst else None
+        if action == "store":                                                                  # :1333-1340
+            self.pad = pad
+            self.lags = result["lags"]
+            self.bp_wts = result["freq_wts"]
+            self.vis_lag, self.skyvis_lag = result["vis_lag"], result["skyvis_lag"]
+            self.vis_noise_lag, self.lag_kernel = result["vis_noise_lag"], result["lag_kernel"]
+        return result

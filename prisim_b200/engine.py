@@ -136,22 +136,57 @@ def skyvis(dircos, amp, nsrc, baselines_enu, pc_dircos, freqs_hz, src_fwhm_deg=N
     return out
 
 
-def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, snapshot=0, bl_offset=0, nbl_total=None, gains=None,
-          flux_unit_k=False, want=("rms", "noise", "vis")):
-    """``pb200_noise`` for one snapshot.  All tensors [nbl,nchan] on the same CUDA device.
+def _bcast_strides(t, nbl, nchan):
+    """(row, col) element strides of a tensor broadcastable to [nbl, nchan]."""
+    if t is None or t.numel() == 1:
+        return 0, 0
+    if t.ndim == 1:
+        if t.numel() == nchan:
+            return 0, 1
+        if t.numel() == nbl:
+            return 1, 0
+        raise ValueError("1-D array is neither [nchan] nor [nbl]")
+    if tuple(t.shape) == (nbl, nchan):
+        return nchan, 1
+    if tuple(t.shape) == (1, nchan):
+        return 0, 1
+    if tuple(t.shape) == (nbl, 1):
+        return 1, 0
+    raise ValueError("array of shape {0} does not broadcast to [{1},{2}]".format(tuple(t.shape), nbl, nchan))
+
+
+def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, bl_offset=0, nbl_total=None, gains=None,
+          flux_unit_k=False, want=("rms", "noise", "vis"), device=None):
+    """``pb200_noise`` for one snapshot.  tsys / aeff / effq are contiguous fp64 CUDA tensors of
+    shape [nbl,nchan], [nchan], [nbl] or scalar (broadcast through strides).
     Replaces interferometry.py:6676-6693 and :6707-6722."""
-    device = tsys.device.index
+    device = tsys.device.index if device is None else _dev(device)
     ctx = get_context(device)
-    nbl, nchan = tsys.shape
     nbl_total = nbl if nbl_total is None else int(nbl_total)
-    rms = torch.empty((nbl, nchan), dtype=torch.float64, device=tsys.device) if "rms" in want else None
-    nz = torch.empty((nbl, nchan), dtype=torch.complex128, device=tsys.device) if "noise" in want else None
-    vis = torch.empty((nbl, nchan), dtype=torch.complex128, device=tsys.device) if "vis" in want else None
-    ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), _ptr(tsys), _ptr(aeff), _ptr(effq), _ptr(gains),
+    dev = "cuda:{0}".format(device)
+    rms = torch.empty((nbl, nchan), dtype=torch.float64, device=dev) if "rms" in want else None
+    nz = torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "noise" in want else None
+    vis = torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "vis" in want else None
+    st = []
+    for t in (tsys, aeff, effq):
+        st.extend(_bcast_strides(t, nbl, nchan))
+    strides = (C.c_longlong * 6)(*st)
+    ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), _ptr(tsys), _ptr(aeff), _ptr(effq), strides, _ptr(gains),
                                   int(nbl), int(nchan), float(df), float(t_acc), int(bool(flux_unit_k)),
-                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(snapshot), int(bl_offset), nbl_total,
+                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(snapshot), int(bl_offset), nbl_total, 0,
                                   _ptr(rms), _ptr(nz), _ptr(vis), ctx.stream()))
     return rms, nz, vis
+
+
+def add_noise(skyvis_t, noise_t, gains=None):
+    """``pb200_noise`` in add-only mode: vis = gains*skyvis + noise (interferometry.py:6722)."""
+    device = skyvis_t.device.index
+    ctx = get_context(device)
+    nbl, nchan = skyvis_t.shape
+    vis = torch.empty_like(skyvis_t)
+    ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), None, None, None, None, _ptr(gains), int(nbl), int(nchan),
+                                  1.0, 1.0, 0, 0, 0, 0, nbl, 1, None, _ptr(noise_t), _ptr(vis), ctx.stream()))
+    return vis
 
 
 def delay_nout(nchan, pad=1.0, downsample=True):

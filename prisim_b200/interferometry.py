@@ -1,0 +1,723 @@
+"""Host-side mirror of the reference's ``prisim/interferometry.py`` for the hot path.
+
+``InterferometerArray`` keeps the reference's constructor and method signatures
+(interferometry.py:5140-5145, :5874-5878, :6414-6417, :6661, :6697, :8052) and the attribute names
+a PRISim user reads afterwards, but every number is produced by the CUDA
+kernels behind ``include/prisim_b200.h``.  Per-snapshot products live on the GPU as
+[nbl, nchan] tensors; the reference-shaped [nbl, nchan, nsnap] numpy arrays are materialised on
+attribute access.
+
+Deliberate deviations from the reference (documented in DESIGN.md):
+  * sky coordinates 'radec' are turned into hour angles with HA = LST - RA (the reference's own
+    legacy path, interferometry.py:4482); astropy's apparent-place pipeline (:6174-6180) is an
+    input producer outside the parity boundary.  'altaz' sky coordinates are accepted (the
+    reference raises NameError, Appendix C #2).
+  * ``geometric_delays`` is never materialised (Appendix C #4); ``memsave`` is ignored (fp64 path
+    is the parity target); ``gradient_mode`` raises NotImplementedError (out of scope).
+  * noise uses a counter-based Philox generator instead of numpy's global state (Appendix C #16).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as NP
+import scipy.constants as FCNST
+import torch
+
+from . import engine
+from . import geometry as GEOM
+from . import primary_beams as PB
+
+
+class SimpleTime(object):
+    """Duck-type of the astropy ``Time`` the reference's ``observe`` consumes: it only calls
+    ``timeobj.sidereal_time('apparent').deg`` (:6113) and ``timeobj.jd`` (:6395)."""
+
+    class _Angle(object):
+        def __init__(self, deg):
+            self.deg = deg
+
+    def __init__(self, jd, lst_deg):
+        self.jd = float(jd)
+        self._lst = float(lst_deg)
+
+    def sidereal_time(self, kind="apparent", longitude=None):
+        return SimpleTime._Angle(self._lst)
+
+
+################################################################################
+# Layout helpers (host-side input producers; O(N_ant^2))
+################################################################################
+
+def hexagon_generator(spacing, n_total=None, n_side=None, orientation=None, center=None):
+    """Hexagonal antenna layout, mirrors interferometry.py:857-989: rows above and below the
+    central row are appended pairwise (:960-966), then the centre row (:968-969); centred on the
+    mean (:979), rotated (:980-984), scaled (:986).  Returns (xy [n,2], labels)."""
+    if n_total is None and n_side is None:
+        raise NameError("n_total or n_side must be provided")
+    if n_side is None:
+        sqroots = NP.roots([3.0, -3.0, 1.0 - n_total])
+        valid = NP.logical_and(sqroots.real >= 1, sqroots.imag == 0.0)
+        if not NP.any(valid):
+            raise ValueError("No valid root found for the quadratic equation with the specified n_total")
+        n_side = int(NP.round(sqroots[valid].real)[0])
+        if 3 * n_side ** 2 - 3 * n_side + 1 != n_total:
+            raise ValueError("n_total is not a valid number for a hexagonal array")
+    else:
+        if not isinstance(n_side, int):
+            raise TypeError("n_side must be an integer")
+        if n_side <= 0:
+            raise ValueError("n_side must be positive")
+        n_total = 3 * n_side ** 2 - 3 * n_side + 1
+    xref = NP.arange(2 * n_side - 1, dtype=float)
+    xloc, yloc = [], []
+    for i in range(1, n_side):
+        x = xref[:-i] + i * NP.cos(NP.pi / 3)
+        y = i * NP.sin(NP.pi / 3) * NP.ones(2 * n_side - 1 - i)
+        xloc += x.tolist() * 2
+        yloc += y.tolist()
+        yloc += (-y).tolist()
+    xloc += xref.tolist()
+    yloc += [0.0] * int(2 * n_side - 1)
+    xy = NP.asarray(list(zip(xloc, yloc)))
+    xy = xy - NP.mean(xy, axis=0, keepdims=True)
+    if orientation is not None:
+        angle = NP.radians(orientation)
+        rot = NP.asarray([[NP.cos(angle), -NP.sin(angle)], [NP.sin(angle), NP.cos(angle)]])
+        xy = NP.dot(xy, rot.T)
+    xy = xy * spacing
+    if center is not None:
+        xy = xy + center
+    return xy, [str(i) for i in range(n_total)]
+
+
+def baseline_generator(antenna_locations, ant_label=None, ant_id=None, auto=False, conjugate=False):
+    """All antenna pairs, mirrors interferometry.py:1184-1370 for numpy input: b = r_j - r_i for
+    j > i with i as the outer loop (:1355-1358).  Returns (baselines [nbl,3], labels, ids)."""
+    ant = NP.asarray(antenna_locations, dtype=NP.float64)
+    if ant.ndim == 1:
+        ant = ant.reshape(-1, 1)
+    if ant.shape[1] < 3:
+        ant = NP.hstack((ant, NP.zeros((ant.shape[0], 3 - ant.shape[1]))))
+    n = ant.shape[0]
+    if ant_label is None:
+        ant_label = NP.asarray([str(i + 1) for i in range(n)])
+    ant_label = NP.asarray(ant_label)
+    if ant_id is None:
+        ant_id = NP.arange(n)
+    ii, jj = NP.triu_indices(n, k=0 if auto else 1)          # i outer, j inner, j > i (or >=)
+    if conjugate:
+        i2, j2 = NP.tril_indices(n, k=-1)                    # j < i, i outer
+        ii, jj = NP.concatenate((ii, i2)), NP.concatenate((jj, j2))
+    bl = ant[jj] - ant[ii]
+    maxlen = max(len(str(a)) for a in ant_label)
+    labels = NP.asarray(list(zip(ant_label[jj], ant_label[ii])), dtype=[("A2", "U{0}".format(maxlen)), ("A1", "U{0}".format(maxlen))])
+    ids = NP.asarray(list(zip(NP.asarray(ant_id)[jj], NP.asarray(ant_id)[ii])), dtype=[("A2", int), ("A1", int)])
+    return bl, labels, ids
+
+
+def orient_and_sort_baselines(bl, labels=None):
+    """run through the reference's conjugation and ordering step (interferometry.py:1868-1883):
+    flip baselines whose orientation falls outside (-67.5, 112.5] degrees, then stable-sort by
+    length."""
+    bl = NP.array(bl, dtype=NP.float64)
+    blo = NP.angle(bl[:, 0] + 1j * bl[:, 1], deg=True)
+    neg = (blo < -67.5) | (blo > 112.5)
+    bl[neg] = -1.0 * bl[neg]
+    if labels is not None:
+        labels = NP.array(labels)
+        lab2 = labels.copy()
+        lab2["A2"][neg], lab2["A1"][neg] = labels["A1"][neg], labels["A2"][neg]
+        labels = lab2
+    order = NP.argsort(NP.sqrt(NP.sum(bl ** 2, axis=1)), kind="mergesort")
+    return bl[order], (None if labels is None else labels[order]), order
+
+
+def uniq_baselines(bl, precision=1e-3):
+    """Unique baselines up to `precision` metres in length/orientation (redundant arrays,
+    cf. interferometry.py:1373-1463); returns (unique baselines, first-occurrence indices, counts)."""
+    bl = NP.asarray(bl, dtype=NP.float64)
+    keys = NP.round(bl / precision).astype(NP.int64)
+    _, first, counts = NP.unique(keys, axis=0, return_index=True, return_counts=True)
+    order = NP.argsort(first)
+    return bl[first[order]], first[order], counts[order]
+
+
+################################################################################
+
+def _validate_2d(name, val, nbl, nchan):
+    val = NP.asarray(val, dtype=NP.float64)
+    if val.size == nbl:
+        return NP.repeat(val.reshape(-1, 1), nchan, axis=1)
+    if val.size == nchan:
+        return NP.repeat(val.reshape(1, -1), nbl, axis=0)
+    if val.size == nbl * nchan:
+        return val.reshape(-1, nchan)
+    raise ValueError("{0} incompatible with the number of interferometers and/or frequency channels.".format(name))
+
+
+class InterferometerArray(object):
+    """Drop-in for ``prisim.interferometry.InterferometerArray`` on the visibility hot path."""
+
+    def __init__(self, labels, baselines, channels, telescope=None, eff_Q=0.89, latitude=34.0790, longitude=0.0,
+                 altitude=0.0, skycoords="radec", A_eff=NP.pi * (25.0 / 2) ** 2, pointing_coords="hadec", layout=None,
+                 blgroupinfo=None, baseline_coords="localenu", freq_scale=None, gaininfo=None, init_file=None,
+                 simparms_file=None, device=None, bl_offset=0, nbl_total=None, noise_seed=0):
+        if init_file is not None:
+            raise NotImplementedError("loading saved simulations is outside the hot-path scope (SURVEY.md section 8f)")
+        if gaininfo is not None:
+            raise NotImplementedError("gain tables are outside the hot-path scope; unity gains are used (interferometry.py:6707)")
+        self.baselines = NP.asarray(baselines, dtype=NP.float64)                       # :5668-5685
+        if self.baselines.ndim == 1:
+            if self.baselines.size == 2:
+                self.baselines = NP.hstack((self.baselines.reshape(1, -1), NP.zeros((1, 1))))
+            elif self.baselines.size == 3:
+                self.baselines = self.baselines.reshape(1, -1)
+            else:
+                raise ValueError("Baseline(s) must be a 2- or 3-column array.")
+        elif self.baselines.ndim == 2:
+            if self.baselines.shape[1] == 2:
+                self.baselines = NP.hstack((self.baselines, NP.zeros(self.baselines.shape[0]).reshape(-1, 1)))
+            elif self.baselines.shape[1] != 3:
+                raise ValueError("Baseline(s) must be a 2- or 3-column array")
+        else:
+            raise ValueError("Baseline(s) array contains more than 2 dimensions.")
+        self.baseline_lengths = NP.sqrt(NP.sum(self.baselines ** 2, axis=1))
+        self.baseline_orientations = NP.angle(self.baselines[:, 0] + 1j * self.baselines[:, 1])
+        self.projected_baselines = None
+        if not isinstance(labels, (list, tuple, NP.ndarray)):                          # :5690-5695
+            raise TypeError("Interferometer array labels must be a list or tuple of unique identifiers")
+        if len(labels) != self.baselines.shape[0]:
+            raise ValueError("Number of labels do not match the number of baselines specified.")
+        self.labels = labels
+        self.simparms_file = simparms_file if isinstance(simparms_file, str) else None
+        if isinstance(telescope, dict):                                                # :5703-5712
+            self.telescope = telescope
+        else:
+            self.telescope = {"id": "vla", "shape": "dish", "size": 25.0, "ocoords": "altaz",
+                              "orientation": NP.asarray([90.0, 270.0]).reshape(1, -1), "groundplane": None}
+        self.layout = dict(layout) if isinstance(layout, dict) else {}
+        self.blgroups = None
+        self.bl_reversemap = None
+        if blgroupinfo is not None:
+            if not isinstance(blgroupinfo, dict):
+                raise TypeError("Input blgroupinfo must be a dictionary")
+            self.blgroups = blgroupinfo["groups"]
+            self.bl_reversemap = blgroupinfo["reversemap"]
+        self.latitude, self.longitude, self.altitude = latitude, longitude, altitude
+        self.gradient_mode = None
+        self.gradient = {}
+        self.gaininfo = None
+        scale = {None: 1.0, "hz": 1.0, "ghz": 1.0e9, "mhz": 1.0e6, "khz": 1.0e3}                # :5772-5786
+        key = freq_scale.lower() if isinstance(freq_scale, str) else freq_scale
+        if key not in scale:
+            raise ValueError('Frequency units must be "GHz", "MHz", "kHz" or "Hz". If not set, it defaults to "Hz"')
+        self.channels = NP.asarray(channels, dtype=NP.float64).ravel() * scale[key]
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        self.Tsysinfo = []
+        self.flux_unit = "JY"
+        self.timestamp = []
+        self.t_acc = []
+        self.t_obs = 0.0
+        self.n_acc = 0
+        self.pointing_center = NP.empty([1, 2])
+        self.phase_center = NP.empty([1, 2])
+        self.lst = []
+        if isinstance(eff_Q, (int, float)):                                            # :5803-5822
+            self.eff_Q = eff_Q * NP.ones((nbl, nchan))
+        elif isinstance(eff_Q, (list, tuple, NP.ndarray)):
+            eff_Q = NP.asarray(eff_Q)
+            if NP.any(eff_Q < 0.0) or NP.any(eff_Q > 1.0):
+                raise ValueError("One or more values of eff_Q found to be outside the range [0,1].")
+            self.eff_Q = _validate_2d("Efficiency values of interferometers", eff_Q, nbl, nchan)
+        else:
+            raise TypeError("Efficiency values of interferometers must be provided as a scalar, list, tuple or numpy array.")
+        if isinstance(A_eff, (int, float)):                                            # :5824-5843
+            if A_eff < 0.0:
+                raise ValueError("Negative value for effective area is invalid.")
+            self.A_eff = A_eff * NP.ones((nbl, nchan))
+        elif isinstance(A_eff, (list, tuple, NP.ndarray)):
+            A_eff = NP.asarray(A_eff)
+            if NP.any(A_eff < 0.0):
+                raise ValueError("One or more values of A_eff found to be negative.")
+            self.A_eff = _validate_2d("Effective area(s) of interferometers", A_eff, nbl, nchan)
+        else:
+            raise TypeError("Effective area(s) of interferometers must be provided as a scalar, list, tuple or numpy array.")
+        self.freq_resolution = self.channels[1] - self.channels[0] if nchan > 1 else 1.0       # :5847
+        self.lags = None
+        self.obs_catalog_indices = []
+        self.geometric_delays = []          # never materialised (Appendix C #4)
+        if pointing_coords not in ("radec", "hadec", "altaz"):                         # :5855-5859
+            raise ValueError('Pointing center of the interferometer must be "radec", "hadec" or "altaz". Check inputs.')
+        self.pointing_coords = pointing_coords
+        self.phase_center_coords = pointing_coords
+        if skycoords not in ("radec", "hadec", "altaz"):                               # :5861-5864
+            raise ValueError('Sky coordinates must be "radec", "hadec" or "altaz". Check inputs.')
+        self.skycoords = skycoords
+        if baseline_coords not in ("equatorial", "localenu"):                          # :5866-5869
+            raise ValueError('Baseline coordinates must be "equatorial" or "local". Check inputs.')
+        self.baseline_coords = baseline_coords
+
+        # ---- device state ----
+        self.device = engine._dev(device)
+        self.bl_offset = int(bl_offset)                  # position of this shard in the full baseline list
+        self.nbl_total = nbl if nbl_total is None else int(nbl_total)
+        self.noise_seed = int(noise_seed)
+        self.cache_sky = True                            # keep catalogue arrays resident between snapshots
+        self._sky_cache = {}
+        self._d_bl = None
+        self._skyvis = []                                # per snapshot [nbl,nchan] complex128 CUDA tensors
+        self._vis = []
+        self._noise = []
+        self._rms = []
+        self._bp = []                                    # per snapshot [nchan] or [nbl,nchan] float64 CUDA
+        self._bp_wts = None                              # callable t -> tensor, set by delay_transform
+        self._Tsys = []
+        self._lag = {}                                   # product name -> list of [nbl,nout] tensors
+        self._d_aeff = None
+        self._d_effq = None
+
+    # ------------------------------------------------------------------ helpers
+    def _dev_str(self):
+        return "cuda:{0}".format(self.device)
+
+    def _compact(self, arr2d):
+        """[nbl,nchan] host array -> device tensor, collapsed to [nchan] when all rows agree."""
+        arr2d = NP.asarray(arr2d, dtype=NP.float64)
+        if arr2d.shape[0] > 1 and NP.all(arr2d == arr2d[0:1]):
+            return engine._f64(arr2d[0], self.device)
+        return engine._f64(arr2d, self.device)
+
+    def _stack(self, lst, expand=False):
+        """list of per-snapshot device tensors -> numpy [nbl, n, nsnap] (reference layout)."""
+        if not lst:
+            return None
+        nbl = self.baselines.shape[0]
+        out = []
+        for t in lst:
+            if expand and t.ndim == 1:
+                t = t.unsqueeze(0).expand(nbl, t.shape[0])
+            out.append(t.cpu().numpy())
+        return NP.stack(out, axis=2)
+
+    # reference-shaped views (host numpy, materialised on access)
+    @property
+    def skyvis_freq(self):
+        return self._stack(self._skyvis)
+
+    @property
+    def vis_freq(self):
+        return self._stack(self._vis)
+
+    @property
+    def vis_noise_freq(self):
+        return self._stack(self._noise)
+
+    @property
+    def vis_rms_freq(self):
+        return self._stack(self._rms)
+
+    @property
+    def bp(self):
+        if not self._bp:
+            return NP.ones((self.baselines.shape[0], self.channels.size))
+        return self._stack(self._bp, expand=True)
+
+    @property
+    def bp_wts(self):
+        if not self._bp:
+            return NP.ones((self.baselines.shape[0], self.channels.size))
+        if self._bp_wts is None:
+            return NP.ones((self.baselines.shape[0], self.channels.size, len(self._bp)))
+        return self._stack([self._bp_wts(t) for t in range(len(self._bp))], expand=True)
+
+    @property
+    def Tsys(self):
+        if not self._Tsys:
+            return NP.zeros((self.baselines.shape[0], self.channels.size))
+        return self._stack(self._Tsys, expand=True)
+
+    @property
+    def skyvis_lag(self):
+        return self._stack(self._lag.get("skyvis", []))
+
+    @property
+    def vis_lag(self):
+        return self._stack(self._lag.get("vis", []))
+
+    @property
+    def vis_noise_lag(self):
+        return self._stack(self._lag.get("noise", []))
+
+    @property
+    def lag_kernel(self):
+        return self._stack(self._lag.get("kernel", []), expand=True)
+
+    def skyvis_freq_device(self, snapshot=-1):
+        """The [nbl,nchan] complex128 CUDA tensor of one snapshot (no copy)."""
+        return self._skyvis[snapshot]
+
+    # ------------------------------------------------------------------ observe
+    def _sky_to_device(self, skymodel):
+        # identity cache; holding the object itself keeps its id() from being recycled
+        if self.cache_sky and self._sky_cache.get("obj", None) is skymodel:
+            return self._sky_cache["dev"]
+        d = {"location": engine._f64(skymodel.location, self.device)}
+        if getattr(skymodel, "spec_type", "func") == "func":
+            sp = skymodel.spec_parms
+            d["spec"] = {"flux_scale": engine._f64(sp["flux-scale"], self.device),
+                         "index": engine._f64(sp["power-law-index"], self.device),
+                         "freq_ref": engine._f64(sp["freq-ref"], self.device)}
+            if "flux-offset" in sp and NP.any(NP.asarray(sp["flux-offset"]) != 0.0):
+                d["spec"]["flux_offset"] = engine._f64(sp["flux-offset"], self.device)
+        else:
+            spectrum = skymodel.generate_spectrum(frequency=self.channels, interp_method="pchip")
+            d["spec"] = {"spectrum": engine._f64(spectrum, self.device)}
+        if getattr(skymodel, "src_shape", None) is not None:
+            shp = NP.asarray(skymodel.src_shape, dtype=NP.float64)
+            d["fwhm"] = engine._f64(NP.sqrt(shp[:, 0] * shp[:, 1]), self.device)            # :6267
+        if self.cache_sky:
+            self._sky_cache = {"obj": skymodel, "dev": d}
+        return d
+
+    def observe(self, timeobj, Tsysinfo, bandpass, pointing_center, skymodel, t_acc, pb_info=None,
+                brightness_units=None, bpcorrect=None, roi_info=None, roi_radius=None, roi_center=None, lst=None,
+                gradient_mode=None, memsave=False, vmemavail=None, store_prev_skymodel_file=None):
+        """One snapshot; same arguments as interferometry.py:5874-5878."""
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        if gradient_mode is not None:
+            raise NotImplementedError("gradient_mode is outside the hot-path scope (SURVEY.md section 2)")
+        bandpass = NP.asarray(bandpass)
+        if bandpass.ndim == 1:                                                         # :5993-5996
+            if bandpass.size != nchan:
+                raise ValueError("Specified bandpass incompatible with the number of frequency channels")
+            bp_t = engine._f64(bandpass, self.device)
+        elif bandpass.ndim in (2, 3):                                                  # :6002-6022
+            if bandpass.shape[1] != nchan:
+                raise ValueError("Specified bandpass incompatible with the number of frequency channels")
+            if bandpass.shape[0] != nbl:
+                raise ValueError("Specified bandpass incompatible with the number of interferometers")
+            if bandpass.ndim == 3:
+                if bandpass.shape[2] != 1:
+                    raise ValueError("Bandpass can have only one layer for this instance of accumulation.")
+                bandpass = bandpass[:, :, 0]
+            bp_t = self._compact(bandpass)
+        else:
+            raise ValueError("Specified bandpass has incompatible dimensions")
+
+        if not isinstance(Tsysinfo, dict):                                             # :6026-6039
+            raise TypeError("Input Tsysinfo must be a dictionary")
+        Tsys = None
+        if Tsysinfo.get("Tnet", None) is not None:
+            Tsys = Tsysinfo["Tnet"]
+        if Tsys is None:
+            try:
+                Tsys = Tsysinfo["Trx"] + Tsysinfo["Tant"]["T0"] * (self.channels / Tsysinfo["Tant"]["f0"]) ** Tsysinfo["Tant"]["spindex"]
+            except KeyError:
+                raise KeyError("One or more keys not found in input Tsysinfo")
+            Tsys = NP.asarray(Tsys, dtype=NP.float64).reshape(1, -1)
+        if bpcorrect is not None:                                                      # :6042-6053
+            if not isinstance(bpcorrect, NP.ndarray):
+                raise TypeError("Input specifying bandpass correction must be a numpy array")
+            if bpcorrect.size == nchan:
+                bpcorrect = bpcorrect.reshape(1, -1)
+            elif bpcorrect.size == nbl:
+                bpcorrect = bpcorrect.reshape(-1, 1)
+            elif bpcorrect.size == nbl * nchan:
+                bpcorrect = bpcorrect.reshape(-1, nchan)
+            else:
+                raise ValueError("Input bpcorrect has dimensions incompatible with the number of baselines and frequencies")
+            Tsys = NP.asarray(Tsys, dtype=NP.float64) * bpcorrect
+        if isinstance(Tsys, (int, float)):                                             # :6055-6063
+            if Tsys < 0.0:
+                raise ValueError("Tsys found to be negative.")
+            Tsys_t = engine._f64(NP.full(nchan, float(Tsys)), self.device)
+        elif isinstance(Tsys, (list, tuple, NP.ndarray)):                              # :6064-6084
+            Tsys = NP.asarray(Tsys, dtype=NP.float64)
+            if NP.any(Tsys < 0.0):
+                raise ValueError("Tsys should be non-negative.")
+            if Tsys.size == nchan:
+                Tsys_t = engine._f64(Tsys.ravel(), self.device)
+            elif Tsys.size == nbl:
+                Tsys_t = self._compact(NP.repeat(Tsys.reshape(-1, 1), nchan, axis=1))
+            elif Tsys.size == nbl * nchan:
+                Tsys_t = self._compact(Tsys.reshape(-1, nchan))
+            else:
+                raise ValueError("Specified Tsys has incompatible dimensions with the number of baselines and/or number of frequency channels.")
+        else:
+            raise TypeError("Tsys should be a scalar, list, tuple, or numpy array")
+
+        if hasattr(timeobj, "sidereal_time"):                                          # :6113
+            lst = timeobj.sidereal_time("apparent").deg
+        if lst is not None:
+            lst = float(NP.asarray(lst).ravel()[0])
+        pointing_center = NP.asarray(pointing_center, dtype=NP.float64).reshape(1, -1)
+        pc = pointing_center[0]
+
+        # pointing centre -> Alt-Az -> direction cosines (:6155-6164)
+        if self.pointing_coords == "hadec":
+            pc_altaz = GEOM.hadec2altaz(pc, self.latitude, units="degrees")[0]
+        elif self.pointing_coords == "radec":
+            if lst is None:
+                raise ValueError("LST must be provided. Sky coordinates are in Alt-Az format while pointing center is in RA-Dec format.")
+            pc_altaz = GEOM.hadec2altaz(NP.asarray([lst - pc[0], pc[1]]), self.latitude, units="degrees")[0]
+        else:
+            pc_altaz = pc
+        pc_dircos = GEOM.altaz2dircos(pc_altaz, "degrees")[0]
+
+        if self._d_bl is None:                                                         # :6151-6153
+            bl_local = self.baselines
+            if self.baseline_coords == "equatorial":
+                bl_local = GEOM.xyz2enu(self.baselines, self.latitude, "degrees")
+            self._d_bl = engine._f64(bl_local, self.device)
+
+        for attr in ("location",):
+            if not hasattr(skymodel, attr):
+                raise TypeError("skymodel should be an instance of class SkyModel.")    # :6171
+        sky = self._sky_to_device(skymodel)
+
+        # sky positions in the frame the cull kernel understands (:6174-6180)
+        if self.skycoords == "radec":
+            if lst is None:
+                raise ValueError("LST must be provided to observe a sky model in RA-Dec coordinates.")
+            skypos = torch.stack((lst - sky["location"][:, 0], sky["location"][:, 1]), dim=1).contiguous()
+            coords = "hadec"
+        else:
+            skypos, coords = sky["location"], self.skycoords
+
+        pbeam = None
+        if roi_info is not None:                                                       # :6189-6202
+            if ("ind" not in roi_info) or ("pbeam" not in roi_info):
+                raise KeyError('Both "ind" and "pbeam" keys must be present in dictionary roi_info')
+        if (roi_info is not None) and (roi_info["ind"] is not None) and (roi_info["pbeam"] is not None):
+            m2 = NP.asarray(roi_info["ind"]).ravel()
+            if m2.size > 0:
+                try:
+                    pb_host = NP.asarray(roi_info["pbeam"], dtype=NP.float64).reshape(-1, nchan)
+                except ValueError:
+                    raise ValueError('Number of columns of primary beam in key "pbeam" of dictionary roi_info must be equal to number of frequency channels.')
+                if m2.size != pb_host.shape[0]:
+                    raise ValueError("Values in keys ind and pbeam in must carry same number of elements.")
+                pbeam = engine._f64(pb_host, self.device)
+                sel = torch.as_tensor(m2.astype(NP.int64), device=self._dev_str())
+                dircos, _ = engine.sky_cull(skypos.index_select(0, sel).contiguous(), coords, latitude_deg=self.latitude,
+                                            roi_radius_deg=180.0, device=self.device)
+                index = sel.to(torch.int32)
+            else:
+                dircos, index = skypos[:0], torch.empty(0, dtype=torch.int32, device=self._dev_str())
+        else:
+            if roi_radius is None:                                                     # :6204-6216
+                roi_radius = 90.0
+            if roi_center is None:
+                roi_center = "zenith"
+            elif roi_center not in ("zenith", "pointing_center"):
+                raise ValueError('Center of region of interest, roi_center, must be set to "zenith" or "pointing_center".')
+            center = pc_dircos if roi_center == "pointing_center" else None
+            dircos, index = engine.sky_cull(skypos, coords, latitude_deg=self.latitude, roi_radius_deg=roi_radius,
+                                            roi_center_dircos=center, device=self.device)
+        nsrc = int(index.shape[0])
+
+        if nsrc > 0:
+            if pbeam is not None:
+                beam = engine.make_beam_desc(element=engine._lib.BEAM_TABLE)
+            else:                                                                      # :6251-6252
+                beam = PB.beam_desc_from_telescope(self.telescope, pointing_info=pb_info, pointing_center=pc_altaz,
+                                                   skyunits="altaz", device=self.device)
+            amp = engine.amp_table(dircos, index, nsrc, sky["spec"], beam, self.channels, pbeam=pbeam, device=self.device)
+            fwhm = None
+            if "fwhm" in sky:                                                          # :6258-6267
+                fwhm = sky["fwhm"].index_select(0, index.to(torch.int64)).contiguous()
+            skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm,
+                                   device=self.device)
+            self.obs_catalog_indices = self.obs_catalog_indices + [index.cpu().numpy().astype(NP.int64)]   # :6377
+        else:                                                                          # :6378-6382
+            warnings.warn("No sources found in the catalog within matching radius. Simply populating the observed visibilities and/or gradients with noise.")
+            skyvis = torch.zeros((nbl, nchan), dtype=torch.complex128, device=self._dev_str())
+
+        # bookkeeping (:6103-6108, :6384-6399)
+        if not self.timestamp:
+            self.pointing_center = pointing_center.copy()
+            self.phase_center = pointing_center.copy()
+        else:
+            self.pointing_center = NP.vstack((self.pointing_center, pointing_center))
+            self.phase_center = NP.vstack((self.phase_center, pointing_center))
+        self._skyvis.append(skyvis)
+        self._bp.append(bp_t)
+        self._Tsys.append(Tsys_t)
+        self.Tsysinfo += [Tsysinfo]
+        self.timestamp = self.timestamp + [timeobj.jd if hasattr(timeobj, "jd") else timeobj]
+        self.t_acc = self.t_acc + [t_acc]
+        self.t_obs += t_acc
+        self.n_acc += 1
+        self.lst = self.lst + [lst]
+
+    # ------------------------------------------------------------------ observing_run
+    def observing_run(self, pointing_init, skymodel, t_acc, duration, channels, bpass, Tsys, lst_init, roi_radius=None,
+                      roi_center=None, mode="track", pointing_coords=None, freq_scale=None, brightness_units=None,
+                      verbose=True, memsave=False, jd_init=2451545.0):
+        """Same call as interferometry.py:6414-6417.  The reference's loop (:6641-6647) passes a
+        string timestamp and an ndarray Tsys to ``observe`` and no longer runs (Appendix C #1); this
+        implements the documented behaviour: an LST ladder (:6607) and a tracking or drifting
+        pointing centre (:6609-6633), one ``observe`` per accumulation."""
+        if verbose:
+            print("Preparing an observing run...")
+        if not isinstance(t_acc, (int, float)) or t_acc <= 0.0:
+            raise ValueError("Accumulation interval must be a positive scalar")
+        if not isinstance(duration, (int, float)) or duration <= 0.0:
+            raise ValueError("Observing duration must be a positive scalar")
+        if duration < t_acc:
+            duration = t_acc
+        n_acc = int(duration / t_acc)
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        bpass = NP.asarray(bpass, dtype=NP.float64)
+        if bpass.size == nchan:                                                        # :6560-6571
+            bpass = bpass.reshape(1, nchan, 1)
+        elif bpass.size == nbl * nchan:
+            bpass = bpass.reshape(nbl, nchan, 1)
+        elif bpass.size == nbl * nchan * n_acc:
+            bpass = bpass.reshape(nbl, nchan, n_acc)
+        else:
+            raise ValueError("Dimensions of bpass incompatible with the number of frequency channels, baselines and number of accumulations.")
+        if not isinstance(Tsys, (int, float, list, tuple, NP.ndarray)):                # :6573-6576
+            raise TypeError("Tsys must be a scalar, list, tuple or numpy array")
+        Tsys = NP.asarray(Tsys, dtype=NP.float64).reshape(-1)
+        if Tsys.size == 1:                                                             # :6578-6599
+            Tsys = Tsys[0] + NP.zeros((1, nchan, 1))
+        elif Tsys.size == nchan:
+            Tsys = Tsys.reshape(1, nchan, 1)
+        elif Tsys.size == nbl:
+            Tsys = NP.repeat(Tsys.reshape(nbl, 1, 1), nchan, axis=1)
+        elif Tsys.size == nbl * nchan:
+            Tsys = Tsys.reshape(nbl, nchan, 1)
+        elif Tsys.size == nbl * nchan * n_acc:
+            Tsys = Tsys.reshape(nbl, nchan, n_acc)
+        else:
+            raise ValueError("Dimensions of Tsys incompatible with the number of frequency channels, baselines and number of accumulations.")
+        if not isinstance(lst_init, (int, float)):
+            raise TypeError("Starting LST should be a scalar")
+        lst = (lst_init + (t_acc / 3.6e3) * NP.arange(n_acc)) * 15.0                   # :6607, degrees
+        pointing_init = NP.asarray(pointing_init, dtype=NP.float64).ravel()
+        lst0_deg = lst_init * 15.0
+        if mode == "track":                                                            # :6611-6621
+            if pointing_coords == "hadec":
+                pointing = NP.asarray([lst0_deg - pointing_init[0], pointing_init[1]])
+            elif (pointing_coords == "radec") or (pointing_coords is None):
+                pointing = pointing_init
+            elif pointing_coords == "altaz":
+                hadec = GEOM.altaz2hadec(pointing_init, self.latitude, units="degrees")[0]
+                pointing = NP.asarray([lst0_deg - hadec[0], hadec[1]])
+            else:
+                raise ValueError('pointing_coords can only be set to "hadec", "radec" or "altaz".')
+            self.pointing_coords = "radec"
+            self.phase_center_coords = "radec"
+        elif mode == "drift":                                                          # :6622-6633
+            if pointing_coords == "radec":
+                pointing = NP.asarray([lst0_deg - pointing_init[0], pointing_init[1]])
+            elif (pointing_coords == "hadec") or (pointing_coords is None):
+                pointing = pointing_init
+            elif pointing_coords == "altaz":
+                pointing = GEOM.altaz2hadec(pointing_init, self.latitude, units="degrees")[0]
+            else:
+                raise ValueError('pointing_coords can only be set to "hadec", "radec" or "altaz".')
+            self.pointing_coords = "hadec"
+            self.phase_center_coords = "hadec"
+        else:
+            raise ValueError('mode must be "track" or "drift"')
+        for i in range(n_acc):                                                         # :6641-6647
+            timeobj = SimpleTime(jd_init + i * t_acc / 86400.0, lst[i] % 360.0)
+            bp_i = bpass[:, :, i % bpass.shape[2]]
+            Ts_i = Tsys[:, :, i % Tsys.shape[2]]
+            self.observe(timeobj, {"Tnet": Ts_i[0] if Ts_i.shape[0] == 1 else Ts_i},
+                         bp_i[0] if bp_i.shape[0] == 1 else bp_i, pointing, skymodel, t_acc,
+                         brightness_units=brightness_units, roi_radius=roi_radius, roi_center=roi_center,
+                         lst=lst[i] % 360.0, memsave=memsave)
+        self.t_obs = duration                                                          # :6654-6655
+        self.n_acc = n_acc
+        if verbose:
+            print("Observing run completed successfully.")
+
+    # ------------------------------------------------------------------ noise
+    def _aeff_effq(self):
+        if self._d_aeff is None:
+            self._d_aeff = self._compact(self.A_eff)
+            self._d_effq = self._compact(self.eff_Q)
+        return self._d_aeff, self._d_effq
+
+    def generate_noise(self):
+        """interferometry.py:6661-6693: thermal rms and a noise realisation for every snapshot."""
+        if self.flux_unit.upper() not in ("JY", "K"):
+            raise ValueError("Flux density units can only be in Jy or K.")
+        aeff, effq = self._aeff_effq()
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        self._rms, self._noise = [], []
+        for t in range(len(self._skyvis)):
+            rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[t],
+                                      self.noise_seed, nbl, nchan, snapshot=t, bl_offset=self.bl_offset,
+                                      nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
+                                      want=("rms", "noise"), device=self.device)
+            self._rms.append(rms)
+            self._noise.append(nz)
+
+    def add_noise(self):
+        """interferometry.py:6697-6722 with unity gains (no gain table on the hot path)."""
+        if not self._noise:
+            raise TypeError("vis_noise_freq has not been generated; call generate_noise() first")
+        warnings.warn("Gain table absent. Proceeding with default unity gains")
+        self._vis = [engine.add_noise(self._skyvis[t], self._noise[t]) for t in range(len(self._skyvis))]
+
+    # ------------------------------------------------------------------ delay transform
+    def _freq_wts_getter(self, freq_wts):
+        """Broadcast rules of interferometry.py:8096-8106, kept compact on the device."""
+        nbl, nchan, n_acc = self.baselines.shape[0], self.channels.size, self.n_acc
+        freq_wts = NP.asarray(freq_wts, dtype=NP.float64)
+        if freq_wts.size == nchan:
+            w = engine._f64(freq_wts.ravel(), self.device)
+            return lambda t: w
+        if freq_wts.size == nchan * n_acc:
+            w = engine._f64(freq_wts.reshape(nchan, -1).T, self.device)      # [n_acc, nchan]
+            return lambda t: w[t]
+        if freq_wts.size == nchan * nbl:
+            w = engine._f64(freq_wts.reshape(-1, nchan), self.device)
+            return lambda t: w
+        if freq_wts.size == nchan * nbl * n_acc:
+            w = engine._f64(NP.ascontiguousarray(NP.moveaxis(freq_wts.reshape(nbl, nchan, n_acc), 2, 0)), self.device)
+            return lambda t: w[t]
+        raise ValueError("window shape dimensions incompatible with number of channels and/or number of tiemstamps.")
+
+    def delay_transform(self, pad=1.0, freq_wts=None, verbose=True):
+        """interferometry.py:8052-8137.  Transforms whichever of skyvis / vis / noise exist
+        (the reference raises TypeError when noise is missing, Appendix C #6)."""
+        if verbose:
+            print("Preparing to compute delay transform...\n\tChecking input parameters for compatibility...")
+        if not isinstance(pad, (int, float)):
+            raise TypeError("pad fraction must be a scalar value.")
+        if pad < 0.0:
+            pad = 0.0
+            if verbose:
+                warnings.warn("\tPad fraction found to be negative. Resetting to 0.0 (no padding will be applied).")
+        if freq_wts is not None:
+            self._bp_wts = self._freq_wts_getter(freq_wts)
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        self.lags = NP.fft.fftshift(NP.fft.fftfreq(nchan, d=self.freq_resolution))    # :8114
+        products = {"skyvis": self._skyvis, "vis": self._vis, "noise": self._noise}
+        self._lag = {"skyvis": [], "vis": [], "noise": [], "kernel": []}
+        for t in range(len(self._skyvis)):
+            bp = self._bp[t]
+            wts = None if self._bp_wts is None else self._bp_wts(t)
+            for name, lst in products.items():
+                if lst:
+                    self._lag[name].append(engine.delay_transform(lst[t], bp, wts, self.freq_resolution, pad=pad,
+                                                                  downsample=True))
+            krows = nbl if (bp.ndim == 2 or (wts is not None and wts.ndim == 2)) else 1
+            kern = engine.delay_transform(None, bp, wts, self.freq_resolution, pad=pad, downsample=True, nrows=krows,
+                                          nchan=nchan, device=self.device)
+            self._lag["kernel"].append(kern if krows == nbl else kern[0])
+        if verbose:
+            print("delay_transform() completed successfully.")
+
+    # ------------------------------------------------------------------ out of scope on this path
+    def phase_centering(self, *args, **kwargs):
+        raise NotImplementedError("phase_centering is a 'next' row (SURVEY.md section 8f-1)")
+
+    def save(self, *args, **kwargs):
+        raise NotImplementedError("on-disk formats are a 'next' row (SURVEY.md section 8f-2)")

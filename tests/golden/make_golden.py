@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Generate golden vectors by executing the REFERENCE'S OWN source files under Python 3.
+
+Run in the build container only (`python tests/golden/make_golden.py`); needs /root/reference.
+Nothing from the reference is copied into the repo: its modules are read from
+/root/reference/prisim/*.py at run time, three Python-2 idioms are patched in memory (one
+``print`` statement, ``.iteritems()``, ``xrange``), and stub modules stand in for the third-party
+packages that are not installed here:
+
+  astroutils (un-vendored, unpinned: setup.py:61)  -> geometry / DSP_modules / catalog / constants
+      stubs restating the semantics listed in SURVEY.md section 8c  [AU-memory]
+  astropy, h5py, progressbar, distutils, healpy     -> inert stand-ins (never on the tested path)
+
+The outputs (tests/golden/*.npz) therefore pin this repo's oracle against the reference's real
+beam, delay, phase-sum, noise-rms and delay-transform code; what remains unpinned is the behaviour
+of the stubbed astroutils helpers themselves.
+"""
+import os
+import re
+import sys
+import types
+
+import numpy as NP
+import scipy.constants as FCNST
+from scipy import interpolate
+
+REF = "/root/reference/prisim"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+# ------------------------------------------------------------------------------------------------
+# astroutils stubs [AU-memory]
+# ------------------------------------------------------------------------------------------------
+def _mod(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def altaz2dircos(altaz, units=None):
+    altaz = NP.asarray(altaz, dtype=float).reshape(-1, 2)
+    if units == "degrees":
+        altaz = NP.radians(altaz)
+    return NP.stack((NP.cos(altaz[:, 0]) * NP.sin(altaz[:, 1]), NP.cos(altaz[:, 0]) * NP.cos(altaz[:, 1]), NP.sin(altaz[:, 0])), axis=1)
+
+
+def dircos2altaz(dircos, units=None):
+    dircos = NP.asarray(dircos, dtype=float).reshape(-1, 3)
+    out = NP.stack((NP.arcsin(NP.clip(dircos[:, 2], -1, 1)), NP.arctan2(dircos[:, 0], dircos[:, 1]) % (2 * NP.pi)), axis=1)
+    return NP.degrees(out) if units == "degrees" else out
+
+
+def hadec2altaz(hadec, latitude, units=None):
+    shape1d = NP.asarray(hadec).ndim == 1
+    hadec = NP.asarray(hadec, dtype=float).reshape(-1, 2)
+    if units == "degrees":
+        ha, dec, lat = NP.radians(hadec[:, 0]), NP.radians(hadec[:, 1]), NP.radians(latitude)
+    else:
+        ha, dec, lat = hadec[:, 0], hadec[:, 1], latitude
+    north = NP.sin(dec) * NP.cos(lat) - NP.cos(dec) * NP.cos(ha) * NP.sin(lat)
+    east = -NP.cos(dec) * NP.sin(ha)
+    up = NP.sin(dec) * NP.sin(lat) + NP.cos(dec) * NP.cos(ha) * NP.cos(lat)
+    out = NP.stack((NP.arcsin(NP.clip(up, -1, 1)), NP.arctan2(east, north) % (2 * NP.pi)), axis=1)
+    out = NP.degrees(out) if units == "degrees" else out
+    return out.ravel() if shape1d else out
+
+
+def altaz2hadec(altaz, latitude, units=None):
+    shape1d = NP.asarray(altaz).ndim == 1
+    altaz = NP.asarray(altaz, dtype=float).reshape(-1, 2)
+    if units == "degrees":
+        alt, az, lat = NP.radians(altaz[:, 0]), NP.radians(altaz[:, 1]), NP.radians(latitude)
+    else:
+        alt, az, lat = altaz[:, 0], altaz[:, 1], latitude
+    e, n, u = NP.cos(alt) * NP.sin(az), NP.cos(alt) * NP.cos(az), NP.sin(alt)
+    z = n * NP.cos(lat) + u * NP.sin(lat)
+    x = -n * NP.sin(lat) + u * NP.cos(lat)
+    out = NP.stack((NP.arctan2(-e, x) % (2 * NP.pi), NP.arcsin(NP.clip(z, -1, 1))), axis=1)
+    out = NP.degrees(out) if units == "degrees" else out
+    return out.ravel() if shape1d else out
+
+
+def sphdist(lon1, lat1, lon2, lat2):
+    lon1, lat1, lon2, lat2 = [NP.radians(NP.asarray(v, dtype=float)) for v in (lon1, lat1, lon2, lat2)]
+    a = NP.sin(0.5 * (lat2 - lat1)) ** 2 + NP.cos(lat1) * NP.cos(lat2) * NP.sin(0.5 * (lon2 - lon1)) ** 2
+    return NP.degrees(2 * NP.arcsin(NP.minimum(1.0, NP.sqrt(a))))
+
+
+def xyz2enu(xyz, latitude, units=None):
+    xyz = NP.asarray(xyz, dtype=float).reshape(-1, 3)
+    lat = NP.radians(latitude) if units == "degrees" else latitude
+    return NP.stack((xyz[:, 1], -NP.sin(lat) * xyz[:, 0] + NP.cos(lat) * xyz[:, 2], NP.cos(lat) * xyz[:, 0] + NP.sin(lat) * xyz[:, 2]), axis=1)
+
+
+def FT1D(inp, ax=-1, use_real=False, shift=False, inverse=False, verbose=True):
+    out = NP.fft.ifft(inp, axis=ax) if inverse else NP.fft.fft(inp, axis=ax)
+    return NP.fft.fftshift(out, axes=ax) if shift else out
+
+
+def spectral_axis(length, delx=1.0, shift=False, use_real=False):
+    ax = NP.fft.fftfreq(length, d=delx)
+    return NP.fft.fftshift(ax) if shift else ax
+
+
+def downsampler(inp, factor, axis=-1, verbose=True, method="interp", kind="linear", fill_value=NP.nan):
+    inp = NP.asarray(inp)
+    n = inp.shape[axis]
+    f = interpolate.interp1d(NP.arange(n), inp, kind=kind, axis=axis, bounds_error=False, fill_value=fill_value)
+    return f(NP.arange(0, n, factor))
+
+
+class SkyModel(object):
+    """catalog.SkyModel stand-in: power-law ('func') spectra only."""
+
+    def __init__(self, location, flux_scale, spindex, freq_ref, src_shape=None, epoch="J2000"):
+        self.location = NP.asarray(location, dtype=float)
+        self.flux_scale, self.spindex, self.freq_ref = map(lambda v: NP.asarray(v, dtype=float), (flux_scale, spindex, freq_ref))
+        self.src_shape = src_shape
+        self.epoch = epoch
+
+    def generate_spectrum(self, ind=None, frequency=None, interp_method="pchip"):
+        ind = NP.arange(self.location.shape[0]) if ind is None else NP.asarray(ind)
+        f = NP.asarray(frequency, dtype=float).reshape(1, -1)
+        return self.flux_scale[ind].reshape(-1, 1) * (f / self.freq_ref[ind].reshape(-1, 1)) ** self.spindex[ind].reshape(-1, 1)
+
+
+def install_stubs():
+    au = _mod("astroutils", __githash__="stub")
+    au.geometry = _mod("astroutils.geometry", altaz2dircos=altaz2dircos, dircos2altaz=dircos2altaz, hadec2altaz=hadec2altaz,
+                       altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu)
+    au.DSP_modules = _mod("astroutils.DSP_modules", FT1D=FT1D, spectral_axis=spectral_axis, downsampler=downsampler)
+    au.catalog = _mod("astroutils.catalog", SkyModel=SkyModel)
+    au.constants = _mod("astroutils.constants", Jy=1.0e-26, sday=0.99726958, rest_freq_HI=1420405751.77)
+    for name in ("gridding_modules", "lookup_operations", "nonmathops", "mathops", "ephemeris_timing", "mpi_modules"):
+        setattr(au, name, _mod("astroutils." + name))
+
+    class _Any(object):
+        def __init__(self, *a, **k):
+            pass
+
+        def transform_to(self, *a, **k):
+            return self
+
+    ap = _mod("astropy")
+    ap.io = _mod("astropy.io", fits=_mod("astropy.io.fits"), ascii=_mod("astropy.io.ascii"))
+    ap.coordinates = _mod("astropy.coordinates", Galactic=_Any, SkyCoord=_Any, ICRS=_Any, FK5=_Any, AltAz=_Any, EarthLocation=_Any)
+    ap.units = _mod("astropy.units", deg=1.0, m=1.0)
+    ap.time = _mod("astropy.time", Time=_Any)
+    _mod("h5py")
+    _mod("progressbar")
+    dv = _mod("distutils")
+    dv.version = _mod("distutils.version", LooseVersion=_Any)
+    _mod("prisim", __githash__="stub", __path__=[REF])
+
+
+def load_reference(name):
+    """exec a reference module from its source text with the Python-2 idioms patched in memory."""
+    path = os.path.join(REF, name + ".py")
+    src = open(path).read()
+    src = re.sub(r"^(\s*)print '([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)      # primary_beams.py:2027
+    src = src.replace(".iteritems()", ".items()")                                       # interferometry.py:6405
+    mod = types.ModuleType(name)
+    mod.__file__ = path
+    mod.__dict__["xrange"] = range
+    sys.modules[name] = mod                       # implicit-relative imports (interferometry.py:27-28)
+    exec(compile(src, path, "exec"), mod.__dict__)
+    return mod
+
+
+class TimeObj(object):
+    def __init__(self, jd, lst_deg):
+        self.jd = jd
+        self._lst = lst_deg
+
+    def sidereal_time(self, kind):
+        return types.SimpleNamespace(deg=self._lst)
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference not present; golden vectors can only be regenerated in the build container")
+    for alias, typ in (("int", int), ("float", float), ("bool", bool), ("complex", complex)):
+        if alias not in NP.__dict__:
+            setattr(NP, alias, typ)             # NP.int / NP.float were removed from numpy
+    install_stubs()
+    DLY = load_reference("baseline_delay_horizon")
+    PB = load_reference("primary_beams")
+    RI = load_reference("interferometry")
+    rng = NP.random.default_rng(20261017)
+    lat = -30.7224
+
+    # ---------------- beams (primary_beams.py executed as is) ----------------
+    nsrc = 60
+    altaz = NP.stack((rng.uniform(0.5, 89.5, nsrc), rng.uniform(0, 360, nsrc)), axis=1)
+    altaz[0] = [90.0, 0.0]
+    freqs_ghz = (150e6 + (NP.arange(16) - 8) * 2e6) / 1e9
+    pc_altaz = NP.asarray([80.0, 30.0])
+    beams = {}
+    tel = {"hera": {"id": "hera", "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz"},
+           "hirax_offzenith": {"id": "hirax", "orientation": NP.asarray([75.0, 120.0]), "ocoords": "altaz"},
+           "mwa_dipole_gp": {"id": "mwa_dipole", "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3},
+           "paper": {"id": "paper", "orientation": NP.asarray([0.0, 90.0]), "ocoords": "altaz"},
+           "mwa_analytic": {"id": "mwa", "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3},
+           "delta": {"shape": "delta"},
+           "dish": {"shape": "dish", "size": 14.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0])},
+           "gaussian": {"shape": "gaussian", "size": 10.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0])},
+           "dipole_gp_mod": {"shape": "dipole", "size": 1.2, "ocoords": "dircos", "orientation": NP.asarray([[0.0, 1.0, 0.0]]),
+                             "groundplane": 0.4, "ground_modify": {"scale": 0.8, "max": 1.5}}}
+    for key, t in tel.items():
+        kw = dict(skyunits="altaz", freq_scale="GHz")
+        if key in ("dish", "gaussian"):
+            kw["pointing_center"] = pc_altaz
+        beams["pb_" + key] = PB.primary_beam_generator(altaz.copy(), freqs_ghz.copy(), dict(t), **kw)
+    # dipole approximations through the wrapper
+    beams["pb_paper_short"] = PB.primary_beam_generator(altaz.copy(), freqs_ghz.copy(), dict(tel["paper"]), skyunits="altaz", short_dipole_approx=True)
+    beams["pb_paper_halfwave"] = PB.primary_beam_generator(altaz.copy(), freqs_ghz.copy(), dict(tel["paper"]), skyunits="altaz", half_wave_dipole_approx=True)
+    # phased tile (array_field_pattern in the reference's float32), explicit delays then pointing-centre delays
+    xl, yl = NP.meshgrid(1.1 * NP.linspace(-1.5, 1.5, 4), 1.1 * NP.linspace(1.5, -1.5, 4))
+    element_locs = NP.hstack((xl.reshape(-1, 1), yl.reshape(-1, 1), NP.zeros((16, 1))))
+    pcd = altaz2dircos(NP.asarray([[52.806, 101.31]]), "degrees")[0]
+    delays = NP.dot(element_locs, pcd) / FCNST.c
+    delays = NP.round((delays - delays.min()) / 435e-12) * 435e-12
+    mwa_el = {"id": "mwa", "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3, "element_locs": element_locs}
+    beams["pb_mwa_tile_delays"] = PB.primary_beam_generator(altaz.copy(), freqs_ghz.copy(), dict(mwa_el), skyunits="altaz",
+                                                          pointing_info={"delays": delays.copy()})
+    beams["pb_mwa_tile_pointing"] = PB.primary_beam_generator(altaz.copy(), freqs_ghz.copy(), dict(mwa_el), skyunits="altaz",
+                                                            pointing_info={"pointing_center": NP.asarray([52.806, 101.31]), "pointing_coords": "altaz"})
+    NP.savez_compressed(os.path.join(OUT, "beams.npz"), altaz=altaz, freqs_ghz=freqs_ghz, pc_altaz=pc_altaz,
+                        element_locs=element_locs, tile_delays=delays, **beams)
+
+    # ---------------- geometric delays (baseline_delay_horizon.py executed as is) ----------------
+    bl = rng.normal(0, 120.0, (9, 3)); bl[:, 2] *= 0.02
+    hadec = NP.stack((rng.uniform(0, 360, 25), rng.uniform(-80, 40, 25)), axis=1)
+    NP.savez_compressed(os.path.join(OUT, "delays.npz"), bl=bl, altaz=altaz, hadec=hadec, latitude=lat,
+                        tau_altaz=DLY.geometric_delay(bl, altaz, altaz=True, hadec=False),
+                        tau_hadec=DLY.geometric_delay(bl, hadec, altaz=False, hadec=True, latitude=lat),
+                        tau_dircos=DLY.geometric_delay(bl, altaz2dircos(altaz, "degrees"), altaz=False, hadec=False, dircos=True),
+                        horizon=DLY.horizon_delay_limits(bl, altaz2dircos(NP.asarray([[90.0, 270.0]]), "degrees")))
+
+    # ---------------- InterferometerArray.observe / generate_noise / add_noise / delay_transform ----------------
+    def run_observe(tag, telescope, src_shape=None, roi_radius=None, pb_info=None, nbl=12, nchan=32, nsrc0=150, nsnap=3,
+                    pointing_coords="hadec", roi_info_from_beam=False):
+        bl = rng.normal(0, 60.0, (nbl, 3)); bl[:, 2] *= 0.02
+        bl[0] = [14.6, 0.0, 0.0]
+        chans = 150e6 + (NP.arange(nchan) - nchan // 2) * 100e3
+        labels = [("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)]
+        ra = rng.uniform(0, 360, nsrc0)
+        dec = NP.degrees(NP.arcsin(rng.uniform(-1, 0.5, nsrc0)))
+        flux = 10 ** rng.uniform(-1, 1.5, nsrc0)
+        spindex = rng.normal(-0.83, 0.2, nsrc0)
+        shp = None
+        if src_shape is not None:
+            fw = rng.uniform(0.05, src_shape, nsrc0)
+            shp = NP.stack((fw, fw * rng.uniform(0.5, 1.0, nsrc0), NP.zeros(nsrc0)), axis=1)
+        ia = RI.InterferometerArray(labels, bl, chans, telescope=dict(telescope), eff_Q=0.96, latitude=lat, longitude=21.4278,
+                                    altitude=0.0, skycoords="hadec", A_eff=154.0 * 0.65, pointing_coords=pointing_coords,
+                                    baseline_coords="localenu", freq_scale="Hz")
+        Tsysinfo = {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None}
+        bandpass = 1.0 + 0.1 * NP.cos(NP.arange(nchan) / 5.0)
+        t_acc = [10.7, 10.7, 21.4][:nsnap]
+        lsts = [0.0, 15.0, 40.0][:nsnap]
+        pointing = NP.asarray([0.0, lat]) if pointing_coords == "hadec" else NP.asarray([60.0, 200.0])
+        rec = {}
+        for j in range(nsnap):
+            hadec_j = NP.stack(((lsts[j] - ra) % 360.0, dec), axis=1)
+            sky = SkyModel(hadec_j, flux, spindex, NP.full(nsrc0, 150e6), src_shape=shp)
+            kw = {}
+            if roi_info_from_beam:      # the run_prisim route: indices + externally computed beam table (:1959-1971)
+                aa = hadec2altaz(hadec_j, lat, "degrees")
+                ind = NP.where(aa[:, 0] >= 0.0)[0]
+                pbt = PB.primary_beam_generator(aa[ind], chans / 1e9, dict(telescope), skyunits="altaz", freq_scale="GHz",
+                                                pointing_center=hadec2altaz(pointing, lat, "degrees") if pointing_coords == "hadec" else pointing)
+                kw["roi_info"] = {"ind": ind, "pbeam": pbt.astype(NP.float32)}
+                rec["roi_ind_{0}".format(j)] = ind
+                rec["roi_pbeam_{0}".format(j)] = pbt.astype(NP.float32)
+            ia.observe(TimeObj(2451545.0 + j * 0.01, lsts[j]), Tsysinfo, bandpass, pointing, sky, t_acc[j], pb_info=pb_info,
+                       roi_radius=roi_radius, **kw)
+            rec["hadec_{0}".format(j)] = hadec_j
+            rec["m2_{0}".format(j)] = NP.asarray(ia.obs_catalog_indices[-1]) if len(ia.obs_catalog_indices) > j else NP.zeros(0, dtype=int)
+        NP.random.seed(1234 + len(tag))
+        ia.generate_noise()
+        ia.add_noise()
+        window = nchan * windowing_bhw(nchan)
+        ia.delay_transform(pad=1.0, freq_wts=window, verbose=False)
+        rec.update(bl=bl, chans=chans, flux=flux, spindex=spindex, src_shape=(NP.zeros(0) if shp is None else shp), latitude=lat,
+                   bandpass=bandpass, t_acc=NP.asarray(t_acc), lsts=NP.asarray(lsts), pointing=pointing, window=window,
+                   noise_seed=1234 + len(tag), skyvis_freq=ia.skyvis_freq, vis_rms_freq=ia.vis_rms_freq, vis_noise_freq=ia.vis_noise_freq,
+                   vis_freq=ia.vis_freq, Tsys=ia.Tsys, bp=ia.bp, lags=ia.lags, skyvis_lag=ia.skyvis_lag, vis_lag=ia.vis_lag,
+                   lag_kernel=ia.lag_kernel, pointing_center=ia.pointing_center, n_acc=ia.n_acc, t_obs=ia.t_obs)
+        # second pass of the transform without padding, and with pad=0.5 (non-integer decimation)
+        ia.delay_transform(pad=0.0, freq_wts=window, verbose=False)
+        rec["skyvis_lag_pad0"] = ia.skyvis_lag
+        ia.delay_transform(pad=0.5, freq_wts=window, verbose=False)
+        rec["skyvis_lag_pad05"] = ia.skyvis_lag
+        NP.savez_compressed(os.path.join(OUT, "observe_{0}.npz".format(tag)), **rec)
+
+    hera = {"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}
+    run_observe("hera", hera)
+    run_observe("hera_taper", hera, src_shape=0.6)
+    run_observe("hera_roi20", hera, roi_radius=20.0)
+    run_observe("hera_roiinfo", hera, roi_info_from_beam=True, nsnap=2)
+    run_observe("gaussian_altazpointing", {"shape": "gaussian", "size": 10.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0]),
+                                           "groundplane": None}, pointing_coords="altaz", nsnap=2)
+    run_observe("mwa_dipole", {"id": "mwa_dipole", "shape": "dipole", "size": 0.74, "orientation": NP.asarray([1.0, 0.0, 0.0]),
+                               "ocoords": "dircos", "groundplane": 0.3}, nsnap=2)
+    print("golden vectors written to", OUT)
+
+
+def windowing_bhw(N):
+    n = NP.arange(N)
+    x = 2 * NP.pi * n / (N - 1)
+    w = 0.35875 - 0.48829 * NP.cos(x) + 0.14128 * NP.cos(2 * x) - 0.01168 * NP.cos(3 * x)
+    return w / w.sum()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+"""Oracle vs golden vectors produced by executing the reference's own source
+(tests/golden/make_golden.py).  Runs on CPU; this is what pins the oracle."""
+import os
+
+import numpy as NP
+import pytest
+
+from oracle import prisim_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+TELESCOPES = {
+    "hera": {"id": "hera", "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz"},
+    "hirax_offzenith": {"id": "hirax", "orientation": NP.asarray([75.0, 120.0]), "ocoords": "altaz"},
+    "mwa_dipole_gp": {"id": "mwa_dipole", "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3},
+    "paper": {"id": "paper", "orientation": NP.asarray([0.0, 90.0]), "ocoords": "altaz"},
+    "mwa_analytic": {"id": "mwa", "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3},
+    "delta": {"shape": "delta"},
+    "dish": {"shape": "dish", "size": 14.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0])},
+    "gaussian": {"shape": "gaussian", "size": 10.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0])},
+    "dipole_gp_mod": {"shape": "dipole", "size": 1.2, "ocoords": "dircos", "orientation": NP.asarray([[0.0, 1.0, 0.0]]),
+                      "groundplane": 0.4, "ground_modify": {"scale": 0.8, "max": 1.5}},
+}
+
+OBSERVE_CASES = {
+    "hera": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
+    "hera_taper": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
+    "hera_roi20": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}, roi_radius=20.0),
+    "hera_roiinfo": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
+    "gaussian_altazpointing": dict(telescope={"shape": "gaussian", "size": 10.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0]), "groundplane": None},
+                                   pointing_coords="altaz"),
+    "mwa_dipole": dict(telescope={"id": "mwa_dipole", "shape": "dipole", "size": 0.74, "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3}),
+}
+
+
+def _load(name):
+    return NP.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+@pytest.mark.parametrize("key", sorted(TELESCOPES))
+def test_beam_presets_match_reference(key):
+    g = _load("beams.npz")
+    kw = dict(skyunits="altaz", freq_scale="GHz")
+    if key in ("dish", "gaussian"):
+        kw["pointing_center"] = g["pc_altaz"]
+    pb = O.primary_beam_generator(g["altaz"], g["freqs_ghz"], dict(TELESCOPES[key]), **kw)
+    ref = g["pb_" + key]
+    assert pb.shape == ref.shape
+    assert NP.allclose(pb, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_dipole_approximations_match_reference():
+    g = _load("beams.npz")
+    t = TELESCOPES["paper"]
+    assert NP.allclose(O.primary_beam_generator(g["altaz"], g["freqs_ghz"], dict(t), skyunits="altaz", short_dipole_approx=True),
+                       g["pb_paper_short"], rtol=1e-9, atol=1e-12)
+    assert NP.allclose(O.primary_beam_generator(g["altaz"], g["freqs_ghz"], dict(t), skyunits="altaz", half_wave_dipole_approx=True),
+                       g["pb_paper_halfwave"], rtol=1e-9, atol=1e-12)
+
+
+def test_phased_tile_matches_reference_in_float32_and_float64():
+    """The reference evaluates the phased-array factor in float32 (primary_beams.py:1730-1746).
+    reference_float32=True reproduces it to float32 rounding; the float64 evaluation (the parity
+    target of the GPU kernel) deviates from it only at the float32 level."""
+    g = _load("beams.npz")
+    tel = {"id": "mwa", "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3,
+           "element_locs": g["element_locs"]}
+    for key, pinfo in (("pb_mwa_tile_delays", {"delays": g["tile_delays"]}),
+                       ("pb_mwa_tile_pointing", {"pointing_center": NP.asarray([52.806, 101.31]), "pointing_coords": "altaz"})):
+        ref = g[key]
+        pb32 = O.primary_beam_generator(g["altaz"], g["freqs_ghz"], dict(tel), skyunits="altaz", pointing_info=dict(pinfo),
+                                        reference_float32=True)
+        pb64 = O.primary_beam_generator(g["altaz"], g["freqs_ghz"], dict(tel), skyunits="altaz", pointing_info=dict(pinfo))
+        assert NP.abs(pb32 - ref).max() <= 2e-6 * NP.abs(ref).max()
+        assert NP.abs(pb64 - ref).max() <= 2e-3 * NP.abs(ref).max()
+
+
+def test_geometric_delay_matches_reference():
+    g = _load("delays.npz")
+    lat = float(g["latitude"])
+    assert NP.allclose(O.geometric_delay(g["bl"], g["altaz"], altaz=True, hadec=False), g["tau_altaz"], rtol=0, atol=1e-20)
+    assert NP.allclose(O.geometric_delay(g["bl"], g["hadec"], altaz=False, hadec=True, latitude=lat), g["tau_hadec"], rtol=0, atol=1e-20)
+    assert NP.allclose(O.geometric_delay(g["bl"], O.altaz2dircos(g["altaz"]), altaz=False, hadec=False, dircos=True), g["tau_dircos"], rtol=0, atol=1e-20)
+    hz = O.horizon_delay_limits(g["bl"], O.altaz2dircos([90.0, 270.0])[0])
+    assert NP.allclose(hz, g["horizon"].reshape(hz.shape), rtol=1e-12, atol=1e-20)
+
+
+def oracle_run(g, case):
+    """Re-run a golden observe() case through the oracle; returns dict of products."""
+    nsnap = int(g["n_acc"])
+    lat = float(g["latitude"])
+    src_shape = g["src_shape"] if g["src_shape"].size else None
+    pointing_coords = case.get("pointing_coords", "hadec")
+    skyvis, m2s = [], []
+    for j in range(nsnap):
+        roi_info = None
+        if "roi_ind_{0}".format(j) in g.files:
+            roi_info = {"ind": g["roi_ind_{0}".format(j)], "pbeam": g["roi_pbeam_{0}".format(j)]}
+        V, m2 = O.observe_snapshot(g["bl"], g["chans"], g["hadec_{0}".format(j)], "hadec", lat, g["pointing"], pointing_coords,
+                                   dict(case["telescope"]), g["flux"], g["spindex"], 150e6, src_shape=src_shape,
+                                   roi_radius=case.get("roi_radius", None), roi_info=roi_info, lst=float(g["lsts"][j]))
+        skyvis.append(V)
+        m2s.append(m2)
+    return NP.stack(skyvis, axis=2), m2s
+
+
+@pytest.mark.parametrize("tag", sorted(OBSERVE_CASES))
+def test_observe_matches_reference(tag):
+    g = _load("observe_{0}.npz".format(tag))
+    case = OBSERVE_CASES[tag]
+    skyvis, m2s = oracle_run(g, case)
+    ref = g["skyvis_freq"]
+    assert skyvis.shape == ref.shape
+    scale = NP.sqrt(NP.mean(NP.abs(ref) ** 2))
+    assert NP.abs(skyvis - ref).max() <= 1e-11 * scale
+    for j, m2 in enumerate(m2s):
+        assert NP.array_equal(m2, g["m2_{0}".format(j)])
+    nbl, nchan, nsnap = ref.shape
+    # Tsys, rms, noise (same legacy-RNG draws), vis
+    Tsysinfo = {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None}
+    Tsys = NP.repeat(O.system_temperature(Tsysinfo, g["chans"], nbl)[:, :, None], nsnap, axis=2)
+    assert NP.allclose(Tsys, g["Tsys"])
+    rms = O.thermal_noise_rms(Tsys, 154.0 * 0.65, 0.96, g["t_acc"], g["chans"][1] - g["chans"][0])
+    assert NP.allclose(rms, g["vis_rms_freq"], rtol=1e-13)
+    NP.random.seed(int(g["noise_seed"]))
+    nre = NP.random.randn(nbl, nchan, nsnap)
+    nim = NP.random.randn(nbl, nchan, nsnap)
+    noise = O.noise_from_normals(rms, nre, nim)
+    assert NP.allclose(noise, g["vis_noise_freq"], rtol=1e-13)
+    assert NP.allclose(O.add_noise(ref, noise), g["vis_freq"], rtol=1e-13)
+    # delay transforms: pad 1.0 (default), 0.0 and 0.5
+    bp = g["bp"]
+    wts = O.broadcast_freq_wts(g["window"], nbl, nchan, nsnap)
+    df = g["chans"][1] - g["chans"][0]
+    for pad, key in ((1.0, "skyvis_lag"), (0.0, "skyvis_lag_pad0"), (0.5, "skyvis_lag_pad05")):
+        lag, lags = O.delay_transform(ref, bp, wts, df, pad=pad)
+        assert lag.shape == g[key].shape
+        assert NP.abs(lag - g[key]).max() <= 1e-12 * NP.abs(g[key]).max()
+    lag, lags = O.delay_transform(g["vis_freq"], bp, wts, df, pad=1.0)
+    assert NP.abs(lag - g["vis_lag"]).max() <= 1e-12 * NP.abs(g["vis_lag"]).max()
+    assert NP.allclose(lags, g["lags"])
+    kern, _ = O.delay_transform(NP.ones_like(ref), bp, wts, df, pad=1.0)
+    assert NP.abs(kern - g["lag_kernel"]).max() <= 1e-12 * NP.abs(g["lag_kernel"]).max()
