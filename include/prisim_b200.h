@@ -150,11 +150,12 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
  *              anything else takes the direct (sincospi per term) kernel.
  *   d_src_fwhm_deg  NULL, or [nsrc] sqrt(major*minor) FWHM in degrees (:6267) -> taper on
  *   d_vis      [nbl,nchan] complex128, overwritten
- *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT
+ *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR
  */
 #define PB200_SKYVIS_AUTO       0
 #define PB200_SKYVIS_RECURRENCE 1
 #define PB200_SKYVIS_DIRECT     2
+#define PB200_SKYVIS_RECURRENCE_SCALAR 3   /* same algorithm with scalar FFMA instead of packed FFMA2 (A/B measurement) */
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float* d_amp, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                  const double* d_src_fwhm_deg, void* d_vis, int method, void* stream);

@@ -3,37 +3,49 @@
 // :6332-6340 / :6348-6376 of the reference, which materialise [nsrc,nbl,nchan] complex128 slabs
 // and call numpy exp/sum on them.
 //
-// Design (see DESIGN.md section "K1"):
-//   * FP32-FMA-issue bound, not HBM and not tensor cores: 6 FMA-pipe issues per term (complex
+// Design (DESIGN.md section "K1"):
+//   * FP32-FMA-issue bound, not HBM and not tensor cores: 6 FMA-pipe lane-issues per term (complex
 //     rotation 2 FMUL + 2 FFMA, accumulate 2 FFMA) is the algorithmic cost.
-//   * one thread owns one baseline x KT consecutive channels, accumulators in registers; a warp's
-//     32 lanes are 32 baselines of the same channel block, so amplitude reads are shared-memory
-//     broadcasts (LDS.128 = 4 channels for the whole warp).
-//   * a CTA = WC channel blocks (one PB200_SLAB-channel slab) x WB baseline groups; it streams
-//     source tiles (PB200_SRC_TILE rows of the slab + fp64 geometry) through a double-buffered
-//     shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier).
-//   * phases: tau = s.b/c - tau_pc in fp64; the anchor phase tau*f_k0 is range-reduced in fp64
-//     and only the fraction goes to fp32; channels advance by an fp32 complex rotation r =
-//     exp(-2 pi i tau df), re-anchored every KA channels (survey section 8d: K <= 32-64 holds 1e-5).
+//   * one thread owns one baseline x KT=32 consecutive channels, accumulators in registers; a
+//     warp's 32 lanes are 32 baselines of the same channel block, so amplitude reads are
+//     shared-memory broadcasts (one LDS.128 = 4 channels for the whole warp).
+//   * a CTA = 4 channel blocks (one PB200_SLAB-channel slab) x 4 baseline groups = 512 threads,
+//     128 baselines; it streams source tiles (32 rows of the slab + fp64 geometry, 17 KB) through
+//     a double-buffered shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier).
+//   * per tile the CTA first computes, cooperatively and once per (source, baseline), the delay
+//     tau = s.b/c - tau_pc in fp64 and the per-channel rotation r = exp(-2 pi i tau df) to full fp32
+//     accuracy (fp64 range reduction + first-order correction of the fp32 argument), and parks
+//     them in shared memory; the four channel-block warps that share a baseline reuse them.
+//   * each thread then anchors its channel block with exp(-2 pi i tau f_k0): the product is formed
+//     and range-reduced in fp64, pre-scaled in fp64 so that the MUFU's own 1/(2 pi) multiply lands
+//     on the reduced turn fraction without a systematic bias, and fed to MUFU.SIN/COS.
+//   * channels advance by the fp32 rotation, two channels per packed FFMA2 (sm_100 f32x2), which
+//     halves the issue slots of the 6-per-term core and leaves room for the anchor/LDS work.
 //   * fp32 accumulators are flushed into the fp64 output every FLUSH_TILES source tiles
-//     (<= 1024 sources), the output buffer itself being the fp64 accumulator (one owner thread per
-//     (b,f), so no atomics and a deterministic sum order).
+//     (<= 1024 sources); the output buffer itself is the fp64 accumulator (one owner thread per
+//     (b,f): no atomics, deterministic order).
 #include "common.cuh"
 
 namespace {
 
 constexpr int KT = 32;                         // channels per thread
-constexpr int WC = PB200_SLAB / KT;            // channel blocks (warps) per slab = 4
+constexpr int WC = PB200_SLAB / KT;            // channel blocks per slab = 4
 constexpr int WB = 4;                          // baseline groups (warps) per CTA
 constexpr int BL_PER_CTA = 32 * WB;            // 128
 constexpr int NTHREADS = 32 * WC * WB;         // 512
 constexpr int T = PB200_SRC_TILE;              // sources per tile
 constexpr int FLUSH_TILES = 32;                // fp32 -> fp64 flush cadence (1024 sources)
 constexpr int NSTAGE = 2;
+constexpr int PRE_PER_THREAD = T * BL_PER_CTA / NTHREADS;   // (source, baseline) pairs per thread per tile = 8
+
+// 1 / fl32(1/(2 pi)): multiplying the fp64 turn fraction by this and rounding to fp32 makes the
+// FMUL by 0.15915494f that sin.approx/cos.approx prepend (SASS: FMUL R, R, 0.15915494; MUFU.SIN)
+// return the fraction itself to fp32 rounding, with no coherent phase-scale bias.
+#define PB_INV_RCP2PI_F32 (1.0 / 0.15915493667125701904296875)
 
 struct SkyvisParams {
   const float* amp;        // [nslab][nsrc_pad][SLAB]
-  const double* geom;      // [nsrc_pad][4]: l, m, n, taper coefficient q
+  const double* geom;      // [nsrc_pad][4]: l, m, n, taper coefficient
   const double* bl;        // [nbl][3] metres
   const double* freqs;     // device [nchan_pad] Hz (padded channels repeat the last frequency)
   double* vis;             // [nbl][nchan] complex128
@@ -42,10 +54,15 @@ struct SkyvisParams {
   int nsrc_pad, nbl, nchan, nslab;
 };
 
-struct __align__(16) Tile {
-  float amp[T][PB200_SLAB];    // 16 KB
-  double geom[T][4];           // 1 KB
+struct __align__(16) TileIn {                  // TMA destination
+  float amp[T][PB200_SLAB];                    // 16 KB
+  double geom[T][4];                           // 1 KB
 };
+struct __align__(16) TilePre {                 // produced by the CTA once per tile
+  double tau[T][BL_PER_CTA];                   // 32 KB
+  float2 rot[T][BL_PER_CTA];                   // 32 KB
+};
+struct __align__(16) TileKap { float kap[T][BL_PER_CTA]; };   // taper exponent coefficient, 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -79,38 +96,88 @@ __device__ __forceinline__ double frac_turns(double x) {
   return x - r;
 }
 
-template <bool TAPER, bool DIRECT>
+// exp(-2 pi i u) for an fp64 phase u in turns: fp64 range reduction, MUFU evaluation
+__device__ __forceinline__ float2 anchor_phasor(double u) {
+  const float x = (float)(frac_turns(u) * PB_INV_RCP2PI_F32);
+  return make_float2(__cosf(x), -__sinf(x));
+}
+
+// exp(-2 pi i d) to full fp32 accuracy: accurate sincospif on the fp32 half-turn argument plus
+// the first-order correction for the part of the fp64 argument the fp32 rounding dropped
+__device__ __forceinline__ float2 rotation_phasor(double d_turns) {
+  const double x = 2.0 * frac_turns(d_turns);          // half-turns in [-1, 1]
+  const float x32 = (float)x;
+  const float e = (float)(x - (double)x32) * 3.14159265358979f;
+  float sn, cs;
+  sincospif(x32, &sn, &cs);
+  return make_float2(fmaf(-e, sn, cs), -fmaf(e, cs, sn));
+}
+
+struct Geometry {
+  double bx, by, bz, tau_pc, blen2;
+};
+
+__device__ __forceinline__ Geometry load_baseline(const SkyvisParams& P, int b, bool valid) {
+  Geometry G = {0, 0, 0, 0, 0};
+  if (valid) {   // baseline in light-seconds
+    G.bx = P.bl[3 * (size_t)b] / PB_SPEED_OF_LIGHT;
+    G.by = P.bl[3 * (size_t)b + 1] / PB_SPEED_OF_LIGHT;
+    G.bz = P.bl[3 * (size_t)b + 2] / PB_SPEED_OF_LIGHT;
+  }
+  G.tau_pc = P.pc[0] * G.bx + P.pc[1] * G.by + P.pc[2] * G.bz;     // interferometry.py:6165
+  G.blen2 = G.bx * G.bx + G.by * G.by + G.bz * G.bz;                // (|b|/c)^2, taper
+  return G;
+}
+
+// add the fp32 partial sums of one thread into its fp64 output cells and clear them
+// (accumulators are kept as channel pairs so the packed FFMA2 path needs no repacking)
+__device__ __forceinline__ void flush_acc(const SkyvisParams& P, int b, bool valid, int kbase, float2 (&acc_re)[KT / 2],
+                                          float2 (&acc_im)[KT / 2]) {
+  if (valid) {
+    double2* row = reinterpret_cast<double2*>(P.vis) + (size_t)b * P.nchan;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const int ch = kbase + k;
+      if (ch < P.nchan) {
+        double2 v = row[ch];
+        v.x += (double)((k & 1) ? acc_re[k >> 1].y : acc_re[k >> 1].x);
+        v.y += (double)((k & 1) ? acc_im[k >> 1].y : acc_im[k >> 1].x);
+        row[ch] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
+}
+
+// =================================================================================================
+// Recurrence kernel (uniform channel grid)
+// =================================================================================================
+template <bool PACKED, bool TAPER>
 __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Tile* tiles = reinterpret_cast<Tile*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * sizeof(Tile));
-  float* sfreq = reinterpret_cast<float*>(smem_raw + NSTAGE * sizeof(Tile) + 64);   // [SLAB] taper: (f/1e8)^2 ; direct: unused
-  double* sfreq64 = reinterpret_cast<double*>(smem_raw + NSTAGE * sizeof(Tile) + 64 + PB200_SLAB * sizeof(float));   // [SLAB]
+  TileIn* tin = reinterpret_cast<TileIn*>(smem_raw);
+  TilePre* tpre = reinterpret_cast<TilePre*>(smem_raw + NSTAGE * sizeof(TileIn));
+  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn) + sizeof(TilePre));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  float* sfreq2 = reinterpret_cast<float*>(tail + 64);                     // [SLAB] (f/1e8)^2, taper only
+  TileKap* tkap = reinterpret_cast<TileKap*>(tail + 64 + PB200_SLAB * sizeof(float));   // [NSTAGE], taper only
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wc = warp % WC, wb = warp / WC;
+  const int wb = warp % WB, wc = warp / WB;           // tid % 128 == wb*32 + lane: producer and consumer baseline coincide
   const int slab = blockIdx.x;
-  const int b = blockIdx.y * BL_PER_CTA + wb * 32 + lane;
+  const int bcol = wb * 32 + lane;
+  const int b = blockIdx.y * BL_PER_CTA + bcol;
   const bool valid = b < P.nbl;
   const int kbase = slab * PB200_SLAB + wc * KT;      // first global channel of this thread
   const int ntiles = P.nsrc_pad / T;
-
-  // baseline in light-seconds (fp64), phase-centre delay
-  double bx = 0, by = 0, bz = 0;
-  if (valid) {
-    bx = P.bl[3 * (size_t)b] / PB_SPEED_OF_LIGHT;
-    by = P.bl[3 * (size_t)b + 1] / PB_SPEED_OF_LIGHT;
-    bz = P.bl[3 * (size_t)b + 2] / PB_SPEED_OF_LIGHT;
-  }
-  const double tau_pc = P.pc[0] * bx + P.pc[1] * by + P.pc[2] * bz;     // interferometry.py:6165
-  const double blen2 = bx * bx + by * by + bz * bz;                      // (|b|/c)^2, taper
+  const Geometry G = load_baseline(P, b, valid);
   const double fk0 = P.f0 + (double)kbase * P.df;
+  const double df = P.df;
 
-  if (tid < PB200_SLAB) {
-    double f = P.freqs[slab * PB200_SLAB + tid];
-    sfreq64[tid] = f;
-    float fs = (float)(f * 1e-8);
-    sfreq[tid] = fs * fs;
+  if (TAPER && tid < PB200_SLAB) {
+    const float fs = (float)(P.freqs[slab * PB200_SLAB + tid] * 1e-8);
+    sfreq2[tid] = fs * fs;
   }
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
@@ -120,78 +187,100 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
 
   const float* amp_slab = P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
   auto issue = [&](int tile, int stage) {
-    mbar_expect_tx(&full[stage], (uint32_t)sizeof(Tile));
-    tma_bulk_g2s(&tiles[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
-    tma_bulk_g2s(&tiles[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
+    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn));
+    tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
+    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
   };
   if (tid == 0) {
     issue(0, 0);
     if (ntiles > 1) issue(1, 1);
   }
 
-  float acc_re[KT], acc_im[KT];
-#pragma unroll
-  for (int k = 0; k < KT; ++k) { acc_re[k] = 0.f; acc_im[k] = 0.f; }
-
-  auto flush = [&]() {
-    if (valid) {
-      double2* row = reinterpret_cast<double2*>(P.vis) + (size_t)b * P.nchan;
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        int ch = kbase + k;
-        if (ch < P.nchan) {
-          double2 v = row[ch];
-          v.x += (double)acc_re[k]; v.y += (double)acc_im[k];
-          row[ch] = v;
-        }
+  // cooperative per-tile stage: tau and the channel rotation for PRE_PER_THREAD sources of this
+  // thread's own baseline (sources s = wc, wc+4, ...)
+  auto precompute = [&](int tile) {
+    const int stage = tile & 1;
+    mbar_wait(&full[stage], (tile >> 1) & 1);
+#pragma unroll 2
+    for (int j = 0; j < PRE_PER_THREAD; ++j) {
+      const int s = wc + WC * j;
+      const double4 g = *reinterpret_cast<const double4*>(&tin[stage].geom[s][0]);
+      const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
+      const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
+      tpre[stage].tau[s][bcol] = tau;
+      tpre[stage].rot[s][bcol] = rotation_phasor(tau * df);
+      if (TAPER) {
+        // w = exp(-1/2 (u_proj/sigma)^2), u_proj^2 = (|b|^2 - (c tau_g)^2) f^2/c^2 (interferometry.py:6262-6283);
+        // g.w = ln2 d^2 1e16 log2(e)  so that  w = exp2(-g.w (|b/c|^2 - tau_g^2) (f/1e8)^2); sqrt argument clamped at 0
+        tkap[stage].kap[s][bcol] = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
       }
     }
-#pragma unroll
-    for (int k = 0; k < KT; ++k) { acc_re[k] = 0.f; acc_im[k] = 0.f; }
   };
+
+  float2 acc_re[KT / 2], acc_im[KT / 2];
+#pragma unroll
+  for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
+
+  precompute(0);
+  __syncthreads();
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int stage = tile & 1;
-    mbar_wait(&full[stage], (tile >> 1) & 1);
-    const Tile& tl = tiles[stage];
+    if (tile + 1 < ntiles) precompute(tile + 1);
+    const TileIn& ti = tin[stage];
+    const TilePre& tp = tpre[stage];
+
+    // software pipeline over sources: the anchor of source s+1 is evaluated while the channel loop of s runs
+    float2 p_next = anchor_phasor(tp.tau[0][bcol] * fk0);
+    float2 r_next = tp.rot[0][bcol];
 #pragma unroll 1
     for (int s = 0; s < T; ++s) {
-      const double4 g = *reinterpret_cast<const double4*>(&tl.geom[s][0]);
-      const double tau_g = g.x * bx + g.y * by + g.z * bz;           // baseline_delay_horizon.py:240
-      const double tau = tau_g - tau_pc;                             // interferometry.py:6332
-      const float4* arow = reinterpret_cast<const float4*>(&tl.amp[s][wc * KT]);
+      const float2 p0 = p_next, r = r_next;
+      const int sn = (s + 1 < T) ? s + 1 : s;
+      p_next = anchor_phasor(tp.tau[sn][bcol] * fk0);
+      r_next = tp.rot[sn][bcol];
+      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[s][wc * KT]);
       float kap = 0.f;
-      if (TAPER) {
-        // w = exp(-1/2 (u_proj/sigma)^2), u_proj^2 = (|b|^2 - (c tau_g)^2) f^2/c^2 (interferometry.py:6262-6283);
-        // g.w = 1/2 * 2 ln2 * d^2 * 1e16 * log2(e)  so that  w = exp2(-g.w * (|b/c|^2 - tau_g^2) * (f/1e8)^2)
-        kap = (float)(g.w * fmax(blen2 - tau_g * tau_g, 0.0));
-      }
-      if (DIRECT) {
+      if (TAPER) kap = tkap[stage].kap[s][bcol];
+
+      if (PACKED) {
+        // two channels per packed register: P = (p_k, p_{k+1}), stepped by r^2
+        const float p1r = fmaf(-p0.y, r.y, p0.x * r.x), p1i = fmaf(p0.y, r.x, p0.x * r.y);
+        const float r2r = fmaf(-r.y, r.y, r.x * r.x), r2i = 2.0f * r.x * r.y;
+        float2 PR = make_float2(p0.x, p1r), PI = make_float2(p0.y, p1i);
+        const float2 RR = make_float2(r2r, r2r), RI = make_float2(r2i, r2i), NRI = make_float2(-r2i, -r2i);
 #pragma unroll
         for (int k4 = 0; k4 < KT / 4; ++k4) {
           const float4 a4 = arow[k4];
-          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = 4 * k4 + j;
-            float x = (float)(2.0 * frac_turns(tau * sfreq64[wc * KT + k]));
-            float sn, cs;
-            sincospif(x, &sn, &cs);
-            float a = av[j];
-            if (TAPER) a *= exp2f(-kap * sfreq[wc * KT + k]);
-            acc_re[k] = fmaf(a, cs, acc_re[k]);
-            acc_im[k] = fmaf(-a, sn, acc_im[k]);
+          float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w);
+          if (TAPER) {
+            const float4 f4 = *reinterpret_cast<const float4*>(&sfreq2[wc * KT + 4 * k4]);
+            A0.x *= exp2f(-kap * f4.x); A0.y *= exp2f(-kap * f4.y);
+            A1.x *= exp2f(-kap * f4.z); A1.y *= exp2f(-kap * f4.w);
+          }
+          // operand order chosen for the register-reuse cache: every packed instruction reads at
+          // most two fresh 64-bit operands (PR / PI / A stay in the same operand slot across
+          // consecutive instructions), which keeps FFMA2 at its 2-cycle pipe rate
+          float2 t1 = __fmul2_rn(PR, RR), t2 = __fmul2_rn(PR, RI);
+          acc_re[2 * k4] = __ffma2_rn(PR, A0, acc_re[2 * k4]);
+          acc_im[2 * k4] = __ffma2_rn(PI, A0, acc_im[2 * k4]);
+          float2 nr = __ffma2_rn(PI, NRI, t1);
+          float2 ni = __ffma2_rn(PI, RR, t2);
+          PR = nr; PI = ni;
+          if (k4 + 1 < KT / 4) {
+            t1 = __fmul2_rn(PR, RR); t2 = __fmul2_rn(PR, RI);
+          }
+          acc_re[2 * k4 + 1] = __ffma2_rn(PR, A1, acc_re[2 * k4 + 1]);
+          acc_im[2 * k4 + 1] = __ffma2_rn(PI, A1, acc_im[2 * k4 + 1]);
+          if (k4 + 1 < KT / 4) {
+            nr = __ffma2_rn(PI, NRI, t1);
+            ni = __ffma2_rn(PI, RR, t2);
+            PR = nr; PI = ni;
           }
         }
       } else {
-        // anchor phasor exp(-2 pi i tau f_k0) and per-channel rotation exp(-2 pi i tau df)
-        float x0 = (float)(2.0 * frac_turns(tau * fk0));
-        float xd = (float)(2.0 * frac_turns(tau * P.df));
-        float sn, cs, rsn, rcs;
-        sincospif(x0, &sn, &cs);
-        sincospif(xd, &rsn, &rcs);
-        float pr = cs, pi = -sn;
-        const float rr = rcs, ri = -rsn;
+        float pr = p0.x, pi = p0.y;
+        const float rr = r.x, ri = r.y;
 #pragma unroll
         for (int k4 = 0; k4 < KT / 4; ++k4) {
           const float4 a4 = arow[k4];
@@ -200,9 +289,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
           for (int j = 0; j < 4; ++j) {
             const int k = 4 * k4 + j;
             float a = av[j];
-            if (TAPER) a *= exp2f(-kap * sfreq[wc * KT + k]);
-            acc_re[k] = fmaf(a, pr, acc_re[k]);
-            acc_im[k] = fmaf(a, pi, acc_im[k]);
+            if (TAPER) a *= exp2f(-kap * sfreq2[wc * KT + k]);
+            if (k & 1) { acc_re[k >> 1].y = fmaf(a, pr, acc_re[k >> 1].y); acc_im[k >> 1].y = fmaf(a, pi, acc_im[k >> 1].y); }
+            else       { acc_re[k >> 1].x = fmaf(a, pr, acc_re[k >> 1].x); acc_im[k >> 1].x = fmaf(a, pi, acc_im[k >> 1].x); }
             const float nr = fmaf(-pi, ri, pr * rr);
             const float ni = fmaf(pi, rr, pr * ri);
             pr = nr; pi = ni;
@@ -210,16 +299,97 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
         }
       }
     }
-    __syncthreads();                                   // everyone is done with this stage
+    __syncthreads();                                   // tile consumed, next tile's tau/rot visible
     if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-    if (((tile + 1) % FLUSH_TILES) == 0) flush();
+    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, b, valid, kbase, acc_re, acc_im);
   }
-  flush();
+  flush_acc(P, b, valid, kbase, acc_re, acc_im);
+}
+
+// =================================================================================================
+// Direct kernel: arbitrary channel frequencies, one accurate sincospi per term (no recurrence)
+// =================================================================================================
+template <bool TAPER>
+__global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileIn* tin = reinterpret_cast<TileIn*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * sizeof(TileIn));
+  float* sfreq2 = reinterpret_cast<float*>(smem_raw + NSTAGE * sizeof(TileIn) + 64);
+  double* sfreq64 = reinterpret_cast<double*>(smem_raw + NSTAGE * sizeof(TileIn) + 64 + PB200_SLAB * sizeof(float));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wb = warp % WB, wc = warp / WB;
+  const int slab = blockIdx.x;
+  const int b = blockIdx.y * BL_PER_CTA + wb * 32 + lane;
+  const bool valid = b < P.nbl;
+  const int kbase = slab * PB200_SLAB + wc * KT;
+  const int ntiles = P.nsrc_pad / T;
+  const Geometry G = load_baseline(P, b, valid);
+
+  if (tid < PB200_SLAB) {
+    const double f = P.freqs[slab * PB200_SLAB + tid];
+    sfreq64[tid] = f;
+    const float fs = (float)(f * 1e-8);
+    sfreq2[tid] = fs * fs;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float* amp_slab = P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
+  auto issue = [&](int tile, int stage) {
+    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn));
+    tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
+    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
+  };
+  if (tid == 0) {
+    issue(0, 0);
+    if (ntiles > 1) issue(1, 1);
+  }
+  float2 acc_re[KT / 2], acc_im[KT / 2];
+#pragma unroll
+  for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int stage = tile & 1;
+    mbar_wait(&full[stage], (tile >> 1) & 1);
+    const TileIn& ti = tin[stage];
+#pragma unroll 1
+    for (int s = 0; s < T; ++s) {
+      const double4 g = *reinterpret_cast<const double4*>(&ti.geom[s][0]);
+      const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;
+      const double tau = tau_g - G.tau_pc;
+      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[s][wc * KT]);
+      float kap = 0.f;
+      if (TAPER) kap = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
+#pragma unroll
+      for (int k4 = 0; k4 < KT / 4; ++k4) {
+        const float4 a4 = arow[k4];
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = 4 * k4 + j;
+          const float x = (float)(2.0 * frac_turns(tau * sfreq64[wc * KT + k]));   // interferometry.py:6332
+          float sn, cs;
+          sincospif(x, &sn, &cs);
+          float a = av[j];
+          if (TAPER) a *= exp2f(-kap * sfreq2[wc * KT + k]);
+          if (k & 1) { acc_re[k >> 1].y = fmaf(a, cs, acc_re[k >> 1].y); acc_im[k >> 1].y = fmaf(-a, sn, acc_im[k >> 1].y); }
+          else       { acc_re[k >> 1].x = fmaf(a, cs, acc_re[k >> 1].x); acc_im[k >> 1].x = fmaf(-a, sn, acc_im[k >> 1].x); }   // :6340
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
+    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, b, valid, kbase, acc_re, acc_im);
+  }
+  flush_acc(P, b, valid, kbase, acc_re, acc_im);
 }
 
 // geometry staging: [nsrc_pad][4] = (l, m, n, taper coefficient), zero rows for padding
 __global__ void k_geom_stage(const double* __restrict__ dircos, const double* __restrict__ fwhm_deg, int nsrc,
-                              int nsrc_pad, double* __restrict__ geom) {
+                             int nsrc_pad, double* __restrict__ geom) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsrc_pad) return;
   double4 g = make_double4(0, 0, 0, 0);
@@ -243,7 +413,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   if (nsrc < 0 || nbl <= 0 || nchan <= 0 || !d_bl || !h_pc || !h_freqs || !d_vis)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: bad arguments");
   if (nsrc > 0 && (!d_dircos || !d_amp)) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: null source arrays");
-  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_DIRECT)
+  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_SCALAR)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -255,8 +425,9 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   bool uniform = true;
   for (int k = 0; k < nchan; ++k)
     if (fabs(h_freqs[k] - (h_freqs[0] + k * df)) > 1e-4) { uniform = false; break; }   // 1e-4 Hz * 1e-5 s = 1e-9 turn
-  bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
-  if (method == PB200_SKYVIS_RECURRENCE && !uniform)
+  const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR);
+  const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
+  if (want_rec && !uniform)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: recurrence kernel needs uniformly spaced channels");
 
   const int nslab = (nchan + PB200_SLAB - 1) / PB200_SLAB;
@@ -284,18 +455,26 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   P.pc[0] = h_pc[0]; P.pc[1] = h_pc[1]; P.pc[2] = h_pc[2];
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
-  const size_t smem = NSTAGE * sizeof(Tile) + 64 + PB200_SLAB * (sizeof(float) + sizeof(double));
   dim3 grid(nslab, pb_div_up(nbl, BL_PER_CTA));
   const bool taper = d_src_fwhm_deg != nullptr;
-#define LAUNCH(TP, DR)                                                                                    \
+  const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR;
+#define LAUNCH(KERNEL, SMEM)                                                                              \
   do {                                                                                                    \
-    PB_CUDA(ctx, cudaFuncSetAttribute(k_skyvis<TP, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_skyvis<TP, DR><<<grid, NTHREADS, smem, stream>>>(P);                                                \
+    PB_CUDA(ctx, cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
+    KERNEL<<<grid, NTHREADS, (SMEM), stream>>>(P);                                                        \
   } while (0)
-  if (taper && direct) LAUNCH(true, true);
-  else if (taper) LAUNCH(true, false);
-  else if (direct) LAUNCH(false, true);
-  else LAUNCH(false, false);
+  if (direct) {
+    const size_t smem = NSTAGE * sizeof(TileIn) + 64 + PB200_SLAB * (sizeof(float) + sizeof(double));
+    if (taper) LAUNCH(k_skyvis_direct<true>, smem);
+    else LAUNCH(k_skyvis_direct<false>, smem);
+  } else {
+    const size_t smem = NSTAGE * (sizeof(TileIn) + sizeof(TilePre)) + 64 + PB200_SLAB * sizeof(float) +
+                        (taper ? NSTAGE * sizeof(TileKap) : 0);
+    if (packed && taper) LAUNCH((k_skyvis<true, true>), smem);
+    else if (packed) LAUNCH((k_skyvis<true, false>), smem);
+    else if (taper) LAUNCH((k_skyvis<false, true>), smem);
+    else LAUNCH((k_skyvis<false, false>), smem);
+  }
 #undef LAUNCH
   PB_CHECK_LAUNCH(ctx, "k_skyvis");
   return PB200_OK;

@@ -130,7 +130,8 @@ def skyvis(dircos, amp, nsrc, baselines_enu, pc_dircos, freqs_hz, src_fwhm_deg=N
     nbl, nchan = bl.shape[0], freqs.size
     if out is None:
         out = torch.empty((nbl, nchan), dtype=torch.complex128, device=bl.device)
-    code = {"auto": _lib.SKYVIS_AUTO, "recurrence": _lib.SKYVIS_RECURRENCE, "direct": _lib.SKYVIS_DIRECT}[method]
+    code = {"auto": _lib.SKYVIS_AUTO, "recurrence": _lib.SKYVIS_RECURRENCE, "direct": _lib.SKYVIS_DIRECT,
+            "recurrence_scalar": _lib.SKYVIS_RECURRENCE_SCALAR}[method]
     ctx.check(ctx.lib.pb200_skyvis(ctx.handle, _ptr(dircos), _ptr(amp), int(nsrc), _ptr(bl), int(nbl), _ptr(pc),
                                    _ptr(freqs), int(nchan), _ptr(src_fwhm_deg), _ptr(out), code, ctx.stream()))
     return out
