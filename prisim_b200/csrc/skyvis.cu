@@ -49,6 +49,7 @@ struct SkyvisParams {
   const double* bl;        // [nbl][3] metres
   const double* freqs;     // device [nchan_pad] Hz (padded channels repeat the last frequency)
   double* vis;             // [nbl][nchan] complex128
+  double2* accum;          // fp64 running sums, warp-tile layout [cta][warp][k][lane] (coalesced flushes)
   double pc[3];            // phase-centre dircos
   double f0, df;           // uniform channels: f_k = f0 + k df
   int nsrc_pad, nbl, nchan, nslab;
@@ -129,25 +130,42 @@ __device__ __forceinline__ Geometry load_baseline(const SkyvisParams& P, int b, 
   return G;
 }
 
-// add the fp32 partial sums of one thread into its fp64 output cells and clear them
-// (accumulators are kept as channel pairs so the packed FFMA2 path needs no repacking)
-__device__ __forceinline__ void flush_acc(const SkyvisParams& P, int b, bool valid, int kbase, float2 (&acc_re)[KT / 2],
-                                          float2 (&acc_im)[KT / 2]) {
-  if (valid) {
-    double2* row = reinterpret_cast<double2*>(P.vis) + (size_t)b * P.nchan;
+// add the fp32 partial sums of one thread into its fp64 running sums and clear them.  The running
+// sums live in a scratch buffer laid out [cta][warp][k][lane] so that every load/store of a warp is
+// one contiguous 512-byte run (the [nbl][nchan] output layout would put the 32 lanes 16 KB apart);
+// k_skyvis_finalize transposes the scratch into the output once at the end.
+__device__ __forceinline__ void flush_acc(const SkyvisParams& P, float2 (&acc_re)[KT / 2], float2 (&acc_im)[KT / 2]) {
+  const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  double2* base = P.accum + ((cta * (NTHREADS / 32) + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-      const int ch = kbase + k;
-      if (ch < P.nchan) {
-        double2 v = row[ch];
-        v.x += (double)((k & 1) ? acc_re[k >> 1].y : acc_re[k >> 1].x);
-        v.y += (double)((k & 1) ? acc_im[k >> 1].y : acc_im[k >> 1].x);
-        row[ch] = v;
-      }
-    }
+  for (int k = 0; k < KT; ++k) {
+    double2 v = base[k * 32];
+    v.x += (double)((k & 1) ? acc_re[k >> 1].y : acc_re[k >> 1].x);
+    v.y += (double)((k & 1) ? acc_im[k >> 1].y : acc_im[k >> 1].x);
+    base[k * 32] = v;
   }
 #pragma unroll
   for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
+}
+
+// scratch [cta][warp][k][lane] -> vis[b][ch]: one CTA per warp tile, transposed through shared memory
+__global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
+  __shared__ double2 tile[KT][33];
+  const size_t t = blockIdx.x;                          // (cta * 16 + warp)
+  const int warp = (int)(t % (NTHREADS / 32));
+  const size_t cta = t / (NTHREADS / 32);
+  const int slab = (int)(cta % P.nslab), blg = (int)(cta / P.nslab);
+  const int wb = warp % WB, wc = warp / WB;
+  const double2* src = P.accum + t * KT * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int k = ty; k < KT; k += 8) tile[k][tx] = src[k * 32 + tx];
+  __syncthreads();
+  const int b0 = blg * BL_PER_CTA + wb * 32, ch = slab * PB200_SLAB + wc * KT + tx;
+  double2* vis = reinterpret_cast<double2*>(P.vis);
+  for (int r = ty; r < 32; r += 8) {
+    const int b = b0 + r;
+    if (b < P.nbl && ch < P.nchan) vis[(size_t)b * P.nchan + ch] = tile[tx][r];
+  }
 }
 
 // =================================================================================================
@@ -301,9 +319,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     }
     __syncthreads();                                   // tile consumed, next tile's tau/rot visible
     if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, b, valid, kbase, acc_re, acc_im);
+    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, acc_re, acc_im);
   }
-  flush_acc(P, b, valid, kbase, acc_re, acc_im);
+  flush_acc(P, acc_re, acc_im);
 }
 
 // =================================================================================================
@@ -382,9 +400,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
     }
     __syncthreads();
     if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, b, valid, kbase, acc_re, acc_im);
+    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, acc_re, acc_im);
   }
-  flush_acc(P, b, valid, kbase, acc_re, acc_im);
+  flush_acc(P, acc_re, acc_im);
 }
 
 // geometry staging: [nsrc_pad][4] = (l, m, n, taper coefficient), zero rows for padding
@@ -417,8 +435,10 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PB_CUDA(ctx, cudaSetDevice(ctx->device));
-  PB_CUDA(ctx, cudaMemsetAsync(d_vis, 0, sizeof(double) * 2 * (size_t)nbl * nchan, stream));
-  if (nsrc == 0) return PB200_OK;                      // empty ROI: zeros (interferometry.py:6378-6382)
+  if (nsrc == 0) {                                     // empty ROI: zeros (interferometry.py:6378-6382)
+    PB_CUDA(ctx, cudaMemsetAsync(d_vis, 0, sizeof(double) * 2 * (size_t)nbl * nchan, stream));
+    return PB200_OK;
+  }
 
   // uniform channel grid?  (reference channels are f0 + k*df, run_prisim.py:900)
   const double df = nchan > 1 ? (h_freqs[nchan - 1] - h_freqs[0]) / (double)(nchan - 1) : 0.0;
@@ -456,6 +476,12 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
   dim3 grid(nslab, pb_div_up(nbl, BL_PER_CTA));
+  const size_t ntile_out = (size_t)grid.x * grid.y * (NTHREADS / 32);
+  void* accum;
+  rc = pb_scratch(ctx, 4, ntile_out * KT * 32 * sizeof(double2), &accum);
+  if (rc) return rc;
+  PB_CUDA(ctx, cudaMemsetAsync(accum, 0, ntile_out * KT * 32 * sizeof(double2), stream));
+  P.accum = (double2*)accum;
   const bool taper = d_src_fwhm_deg != nullptr;
   const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR;
 #define LAUNCH(KERNEL, SMEM)                                                                              \
@@ -477,5 +503,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   }
 #undef LAUNCH
   PB_CHECK_LAUNCH(ctx, "k_skyvis");
+  k_skyvis_finalize<<<(unsigned)ntile_out, 256, 0, stream>>>(P);
+  PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
   return PB200_OK;
 }
