@@ -25,18 +25,26 @@
 //     (<= 1024 sources); the output buffer itself is the fp64 accumulator (one owner thread per
 //     (b,f): no atomics, deterministic order).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
 constexpr int KT = 32;                         // channels per thread
-constexpr int WC = PB200_SLAB / KT;            // channel blocks per slab = 4
-constexpr int WB = 4;                          // baseline groups (warps) per CTA
-constexpr int BL_PER_CTA = 32 * WB;            // 128
-constexpr int NTHREADS = 32 * WC * WB;         // 512
+constexpr int WCS = PB200_SLAB / KT;           // channel blocks per slab = 4
+constexpr int NWARPS = 16;
+constexpr int NTHREADS = 32 * NWARPS;          // 512
 constexpr int T = PB200_SRC_TILE;              // sources per tile
 constexpr int FLUSH_TILES = 32;                // fp32 -> fp64 flush cadence (1024 sources)
 constexpr int NSTAGE = 2;
-constexpr int PRE_PER_THREAD = T * BL_PER_CTA / NTHREADS;   // (source, baseline) pairs per thread per tile = 8
+// CTA shape: SPC slabs (SPC*128 channels) x WB baseline groups, SPC*WCS*WB = 16 warps.  A wider
+// channel extent shares each (source, baseline) delay/rotation among more warps (less per-tile
+// precompute); a wider baseline extent re-reads the amplitude tile less often.
+template <int SPC> struct Shape {
+  static constexpr int WC = SPC * WCS;                  // channel blocks per CTA
+  static constexpr int WB = NWARPS / WC;                // baseline groups per CTA
+  static constexpr int BL = 32 * WB;                    // baselines per CTA
+  static constexpr int PRE = T * BL / NTHREADS;         // (source, baseline) pairs per thread per tile
+};
 
 // 1 / fl32(1/(2 pi)): multiplying the fp64 turn fraction by this and rounding to fp32 makes the
 // FMUL by 0.15915494f that sin.approx/cos.approx prepend (SASS: FMUL R, R, 0.15915494; MUFU.SIN)
@@ -53,17 +61,18 @@ struct SkyvisParams {
   double pc[3];            // phase-centre dircos
   double f0, df;           // uniform channels: f_k = f0 + k df
   int nsrc_pad, nbl, nchan, nslab;
+  int spc;                 // slabs per CTA of the launch that filled `accum` (finalize)
 };
 
-struct __align__(16) TileIn {                  // TMA destination
-  float amp[T][PB200_SLAB];                    // 16 KB
+template <int SPC> struct __align__(16) TileIn {   // TMA destination
+  float amp[SPC][T][PB200_SLAB];               // SPC x 16 KB
   double geom[T][4];                           // 1 KB
 };
-struct __align__(16) TilePre {                 // produced by the CTA once per tile
-  double tau[T][BL_PER_CTA];                   // 32 KB
-  float2 rot[T][BL_PER_CTA];                   // 32 KB
+template <int SPC> struct __align__(16) TilePre {  // produced by the CTA once per tile
+  double tau[T][Shape<SPC>::BL];
+  float2 rot[T][Shape<SPC>::BL];
 };
-struct __align__(16) TileKap { float kap[T][BL_PER_CTA]; };   // taper exponent coefficient, 16 KB
+template <int SPC> struct __align__(16) TileKap { float kap[T][Shape<SPC>::BL]; };   // taper exponent coefficient
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -136,7 +145,7 @@ __device__ __forceinline__ Geometry load_baseline(const SkyvisParams& P, int b, 
 // k_skyvis_finalize transposes the scratch into the output once at the end.
 __device__ __forceinline__ void flush_acc(const SkyvisParams& P, float2 (&acc_re)[KT / 2], float2 (&acc_im)[KT / 2]) {
   const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-  double2* base = P.accum + ((cta * (NTHREADS / 32) + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
+  double2* base = P.accum + ((cta * NWARPS + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
     double2 v = base[k * 32];
@@ -149,18 +158,19 @@ __device__ __forceinline__ void flush_acc(const SkyvisParams& P, float2 (&acc_re
 }
 
 // scratch [cta][warp][k][lane] -> vis[b][ch]: one CTA per warp tile, transposed through shared memory
-__global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
+__global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P, int gridx) {
   __shared__ double2 tile[KT][33];
   const size_t t = blockIdx.x;                          // (cta * 16 + warp)
-  const int warp = (int)(t % (NTHREADS / 32));
-  const size_t cta = t / (NTHREADS / 32);
-  const int slab = (int)(cta % P.nslab), blg = (int)(cta / P.nslab);
+  const int warp = (int)(t % NWARPS);
+  const size_t cta = t / NWARPS;
+  const int gx = (int)(cta % gridx), gy = (int)(cta / gridx);
+  const int WC = P.spc * WCS, WB = NWARPS / WC;
   const int wb = warp % WB, wc = warp / WB;
   const double2* src = P.accum + t * KT * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int k = ty; k < KT; k += 8) tile[k][tx] = src[k * 32 + tx];
   __syncthreads();
-  const int b0 = blg * BL_PER_CTA + wb * 32, ch = slab * PB200_SLAB + wc * KT + tx;
+  const int b0 = gy * 32 * WB + wb * 32, ch = (gx * P.spc + wc / WCS) * PB200_SLAB + (wc % WCS) * KT + tx;
   double2* vis = reinterpret_cast<double2*>(P.vis);
   for (int r = ty; r < 32; r += 8) {
     const int b = b0 + r;
@@ -171,30 +181,34 @@ __global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
 // =================================================================================================
 // Recurrence kernel (uniform channel grid)
 // =================================================================================================
-template <bool PACKED, bool TAPER>
+template <int SPC, bool PACKED, bool TAPER>
 __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
+  using S = Shape<SPC>;
+  constexpr int WB = S::WB, WC = S::WC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TileIn* tin = reinterpret_cast<TileIn*>(smem_raw);
-  TilePre* tpre = reinterpret_cast<TilePre*>(smem_raw + NSTAGE * sizeof(TileIn));
-  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn) + sizeof(TilePre));
+  TileIn<SPC>* tin = reinterpret_cast<TileIn<SPC>*>(smem_raw);
+  TilePre<SPC>* tpre = reinterpret_cast<TilePre<SPC>*>(smem_raw + NSTAGE * sizeof(TileIn<SPC>));
+  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>));
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
-  float* sfreq2 = reinterpret_cast<float*>(tail + 64);                     // [SLAB] (f/1e8)^2, taper only
-  TileKap* tkap = reinterpret_cast<TileKap*>(tail + 64 + PB200_SLAB * sizeof(float));   // [NSTAGE], taper only
+  float* sfreq2 = reinterpret_cast<float*>(tail + 64);                     // [SPC*SLAB] (f/1e8)^2, taper only
+  TileKap<SPC>* tkap = reinterpret_cast<TileKap<SPC>*>(tail + 64 + SPC * PB200_SLAB * sizeof(float));   // [NSTAGE], taper only
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wb = warp % WB, wc = warp / WB;           // tid % 128 == wb*32 + lane: producer and consumer baseline coincide
-  const int slab = blockIdx.x;
+  const int wb = warp % WB, wc = warp / WB;           // tid % BL == wb*32 + lane: producer and consumer baseline coincide
+  const int sl = wc / WCS, wcs = wc % WCS;            // slab within the CTA, channel block within the slab
+  const int slab = blockIdx.x * SPC + sl;
   const int bcol = wb * 32 + lane;
-  const int b = blockIdx.y * BL_PER_CTA + bcol;
+  const int b = blockIdx.y * S::BL + bcol;
   const bool valid = b < P.nbl;
-  const int kbase = slab * PB200_SLAB + wc * KT;      // first global channel of this thread
+  const int kbase = slab * PB200_SLAB + wcs * KT;     // first global channel of this thread
   const int ntiles = P.nsrc_pad / T;
   const Geometry G = load_baseline(P, b, valid);
   const double fk0 = P.f0 + (double)kbase * P.df;
   const double df = P.df;
 
-  if (TAPER && tid < PB200_SLAB) {
-    const float fs = (float)(P.freqs[slab * PB200_SLAB + tid] * 1e-8);
+  if (TAPER && tid < SPC * PB200_SLAB) {
+    const int ch = blockIdx.x * SPC * PB200_SLAB + tid;
+    const float fs = (float)(P.freqs[ch < P.nslab * PB200_SLAB ? ch : P.nslab * PB200_SLAB - 1] * 1e-8);
     sfreq2[tid] = fs * fs;
   }
   if (tid == 0) {
@@ -203,24 +217,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   }
   __syncthreads();
 
-  const float* amp_slab = P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
+  // slabs of this CTA that exist (the last CTA along x may be short when nslab % SPC != 0)
+  const int nsl = min(SPC, P.nslab - (int)blockIdx.x * SPC);
   auto issue = [&](int tile, int stage) {
-    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn));
-    tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
+    mbar_expect_tx(&full[stage], (uint32_t)(nsl * sizeof(float) * T * PB200_SLAB + sizeof(double) * T * 4));
+    for (int i = 0; i < nsl; ++i)
+      tma_bulk_g2s(&tin[stage].amp[i][0][0],
+                   P.amp + ((size_t)(blockIdx.x * SPC + i) * P.nsrc_pad + (size_t)tile * T) * PB200_SLAB,
+                   sizeof(float) * T * PB200_SLAB, &full[stage]);
     tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
   };
   if (tid == 0) {
     issue(0, 0);
     if (ntiles > 1) issue(1, 1);
   }
+  const bool live = sl < nsl;                          // warps of a missing slab only help with the precompute
 
-  // cooperative per-tile stage: tau and the channel rotation for PRE_PER_THREAD sources of this
-  // thread's own baseline (sources s = wc, wc+4, ...)
+  // cooperative per-tile stage: tau and the channel rotation for S::PRE sources of this
+  // thread's own baseline (sources s = wc, wc+WC, ...)
   auto precompute = [&](int tile) {
     const int stage = tile & 1;
     mbar_wait(&full[stage], (tile >> 1) & 1);
 #pragma unroll 2
-    for (int j = 0; j < PRE_PER_THREAD; ++j) {
+    for (int j = 0; j < S::PRE; ++j) {
       const int s = wc + WC * j;
       const double4 g = *reinterpret_cast<const double4*>(&tin[stage].geom[s][0]);
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
@@ -245,8 +264,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   for (int tile = 0; tile < ntiles; ++tile) {
     const int stage = tile & 1;
     if (tile + 1 < ntiles) precompute(tile + 1);
-    const TileIn& ti = tin[stage];
-    const TilePre& tp = tpre[stage];
+    const TileIn<SPC>& ti = tin[stage];
+    const TilePre<SPC>& tp = tpre[stage];
+    if (live) {
 
     // software pipeline over sources: the anchor of source s+1 is evaluated while the channel loop of s runs
     float2 p_next = anchor_phasor(tp.tau[0][bcol] * fk0);
@@ -257,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const int sn = (s + 1 < T) ? s + 1 : s;
       p_next = anchor_phasor(tp.tau[sn][bcol] * fk0);
       r_next = tp.rot[sn][bcol];
-      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[s][wc * KT]);
+      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KT]);
       float kap = 0.f;
       if (TAPER) kap = tkap[stage].kap[s][bcol];
 
@@ -317,11 +337,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
         }
       }
     }
+    }
     __syncthreads();                                   // tile consumed, next tile's tau/rot visible
     if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, acc_re, acc_im);
+    if (live && ((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, acc_re, acc_im);
   }
-  flush_acc(P, acc_re, acc_im);
+  if (live) flush_acc(P, acc_re, acc_im);
 }
 
 // =================================================================================================
@@ -329,16 +350,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
 // =================================================================================================
 template <bool TAPER>
 __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParams P) {
+  using S = Shape<1>;
+  constexpr int WB = S::WB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TileIn* tin = reinterpret_cast<TileIn*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * sizeof(TileIn));
-  float* sfreq2 = reinterpret_cast<float*>(smem_raw + NSTAGE * sizeof(TileIn) + 64);
-  double* sfreq64 = reinterpret_cast<double*>(smem_raw + NSTAGE * sizeof(TileIn) + 64 + PB200_SLAB * sizeof(float));
+  TileIn<1>* tin = reinterpret_cast<TileIn<1>*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * sizeof(TileIn<1>));
+  float* sfreq2 = reinterpret_cast<float*>(smem_raw + NSTAGE * sizeof(TileIn<1>) + 64);
+  double* sfreq64 = reinterpret_cast<double*>(smem_raw + NSTAGE * sizeof(TileIn<1>) + 64 + PB200_SLAB * sizeof(float));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wb = warp % WB, wc = warp / WB;
   const int slab = blockIdx.x;
-  const int b = blockIdx.y * BL_PER_CTA + wb * 32 + lane;
+  const int b = blockIdx.y * S::BL + wb * 32 + lane;
   const bool valid = b < P.nbl;
   const int kbase = slab * PB200_SLAB + wc * KT;
   const int ntiles = P.nsrc_pad / T;
@@ -357,8 +380,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
   __syncthreads();
   const float* amp_slab = P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
   auto issue = [&](int tile, int stage) {
-    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn));
-    tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
+    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn<1>));
+    tma_bulk_g2s(&tin[stage].amp[0][0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
     tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
   };
   if (tid == 0) {
@@ -372,13 +395,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
   for (int tile = 0; tile < ntiles; ++tile) {
     const int stage = tile & 1;
     mbar_wait(&full[stage], (tile >> 1) & 1);
-    const TileIn& ti = tin[stage];
+    const TileIn<1>& ti = tin[stage];
 #pragma unroll 1
     for (int s = 0; s < T; ++s) {
       const double4 g = *reinterpret_cast<const double4*>(&ti.geom[s][0]);
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;
       const double tau = tau_g - G.tau_pc;
-      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[s][wc * KT]);
+      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[0][s][wc * KT]);
       float kap = 0.f;
       if (TAPER) kap = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
 #pragma unroll
@@ -475,8 +498,14 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   P.pc[0] = h_pc[0]; P.pc[1] = h_pc[1]; P.pc[2] = h_pc[2];
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
-  dim3 grid(nslab, pb_div_up(nbl, BL_PER_CTA));
-  const size_t ntile_out = (size_t)grid.x * grid.y * (NTHREADS / 32);
+  // CTA shape: wide-channel CTAs when the slab count allows it, 1 slab otherwise
+  const char* spc_env = getenv("PB200_SKYVIS_SPC");
+  int spc = direct ? 1 : (nslab % 2 == 0 ? 2 : 1);   // measured on B200: 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4
+  if (!direct && spc_env) { int v = atoi(spc_env); if ((v == 1 || v == 2 || v == 4)) spc = v; }
+  P.spc = spc;
+  const int bl_per_cta = 32 * (NWARPS / (spc * WCS));
+  dim3 grid(pb_div_up(nslab, spc), pb_div_up(nbl, bl_per_cta));
+  const size_t ntile_out = (size_t)grid.x * grid.y * NWARPS;
   void* accum;
   rc = pb_scratch(ctx, 4, ntile_out * KT * 32 * sizeof(double2), &accum);
   if (rc) return rc;
@@ -489,21 +518,31 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
     PB_CUDA(ctx, cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
     KERNEL<<<grid, NTHREADS, (SMEM), stream>>>(P);                                                        \
   } while (0)
+#define SMEM_REC(SPC) (NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) + \
+                       (taper ? NSTAGE * sizeof(TileKap<SPC>) : 0))
+#define LAUNCH_REC(SPC)                                                     \
+  do {                                                                      \
+    if (packed && taper) LAUNCH((k_skyvis<SPC, true, true>), SMEM_REC(SPC));       \
+    else if (packed) LAUNCH((k_skyvis<SPC, true, false>), SMEM_REC(SPC));          \
+    else if (taper) LAUNCH((k_skyvis<SPC, false, true>), SMEM_REC(SPC));           \
+    else LAUNCH((k_skyvis<SPC, false, false>), SMEM_REC(SPC));                     \
+  } while (0)
   if (direct) {
-    const size_t smem = NSTAGE * sizeof(TileIn) + 64 + PB200_SLAB * (sizeof(float) + sizeof(double));
+    const size_t smem = NSTAGE * sizeof(TileIn<1>) + 64 + PB200_SLAB * (sizeof(float) + sizeof(double));
     if (taper) LAUNCH(k_skyvis_direct<true>, smem);
     else LAUNCH(k_skyvis_direct<false>, smem);
+  } else if (spc == 4) {
+    LAUNCH_REC(4);
+  } else if (spc == 2) {
+    LAUNCH_REC(2);
   } else {
-    const size_t smem = NSTAGE * (sizeof(TileIn) + sizeof(TilePre)) + 64 + PB200_SLAB * sizeof(float) +
-                        (taper ? NSTAGE * sizeof(TileKap) : 0);
-    if (packed && taper) LAUNCH((k_skyvis<true, true>), smem);
-    else if (packed) LAUNCH((k_skyvis<true, false>), smem);
-    else if (taper) LAUNCH((k_skyvis<false, true>), smem);
-    else LAUNCH((k_skyvis<false, false>), smem);
+    LAUNCH_REC(1);
   }
+#undef LAUNCH_REC
+#undef SMEM_REC
 #undef LAUNCH
   PB_CHECK_LAUNCH(ctx, "k_skyvis");
-  k_skyvis_finalize<<<(unsigned)ntile_out, 256, 0, stream>>>(P);
+  k_skyvis_finalize<<<(unsigned)ntile_out, 256, 0, stream>>>(P, (int)grid.x);
   PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
   return PB200_OK;
 }
