@@ -141,7 +141,7 @@ def run_reference_arm(args):
     from prisim_b200 import synthetic as S
     cfg = S.config2()
     cores = min(host_cores(), 64)
-    nsrc, nbl = 2000, max(cores * 16, 64)
+    nsrc, nbl = 4000, max(cores * 16, 64)
     for _ in range(args.warmup):
         cpu_sample(cfg, max(nsrc // 4, 50), nbl, cores)
     rates, times = [], []
@@ -323,10 +323,10 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cores = min(host_cores(), 64)
-            rate, dt, tterms = cpu_sample(cfg, 4000, max(cores * 16, 64), cores)
+            rate, dt, tterms = cpu_sample(cfg, 8000, max(cores * 32, 64), cores)
             cpu = {"value": rate / 1e9, "unit": "Gterms/s", "cores": cores, "kind": "port", "seconds": dt,
-                   "sample": "4000 above-horizon sources x {0} baselines x 1024 channels ({1:.2e} terms) of the same workload, "
-                             "float64 numpy restatement of interferometry.py:6332-6340, {2} processes".format(max(cores * 16, 64), tterms, cores)}
+                   "sample": "8000 above-horizon sources x {0} baselines x 1024 channels ({1:.2e} terms) of the same workload, "
+                             "float64 numpy restatement of interferometry.py:6332-6340, {2} processes".format(max(cores * 32, 64), tterms, cores)}
         line = {"metric": METRIC, "value": value, "unit": "Gterms/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -343,7 +343,8 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per k_skyvis launch at the headline size, from the
 # committed ncu capture (profiles/); None until that capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 21.88e9   # profiles/skyvis_headline_r01_ncu.txt: 20.45 GB read + 1.43 GB written (0.13 % of HBM bandwidth over 2.57 s;
+                                      # the amplitude table is re-streamed once per wave of CTAs, 26 waves x 0.73 GB)
 
 if __name__ == "__main__":
     main()
