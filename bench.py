@@ -190,6 +190,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = "cuda:{0}".format(local_rank)
+    # NCCL prints its version banner on stdout at communicator creation; keep stdout clean for the
+    # single JSON line by pointing fd 1 at stderr until the result is printed
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     warmup = max(args.warmup, 3)
@@ -335,7 +339,10 @@ def main():
                            "l2": "inputs larger than L2: amplitude table {0:.2f} GB + 1.0 GB output per step".format(nsrc * nchan * 4 / 1e9),
                            "phase_arith": "fp64 anchors, fp32 rotation recurrence, fp32 accumulate flushed to fp64"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
