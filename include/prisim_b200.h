@@ -127,7 +127,9 @@ typedef struct pb200_spectrum_desc {
  * padding rows/channels are zero.  pb200_amp_bytes gives the buffer size.                     */
 #define PB200_SLAB     128
 #define PB200_SRC_TILE 32
-size_t pb200_amp_bytes(int nsrc, int nchan);
+#define PB200_AMP_F32  0      /* default: fp32 table (7.6e-8 effect on point-source skies) */
+#define PB200_AMP_F64  1      /* fp64 table for PB200_SKYVIS_FP64 on strongly cancelling (diffuse) skies */
+size_t pb200_amp_bytes(int nsrc, int nchan);   /* fp32 table; an fp64 table is twice this */
 int pb200_nsrc_pad(int nsrc);
 
 /* d_dircos/d_index from pb200_sky_cull (nsrc entries); h_freqs [nchan] Hz (host);
@@ -135,7 +137,7 @@ int pb200_nsrc_pad(int nsrc);
  * Output: d_amp (layout above).                                                               */
 int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_index, int nsrc,
                     const pb200_spectrum_desc* spec, const pb200_beam_desc* beam, const double* d_pbeam,
-                    const double* h_freqs, int nchan, float* d_amp, void* stream);
+                    const double* h_freqs, int nchan, int amp_dtype, void* d_amp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The phase sum.  Replaces interferometry.py:6155-6165 (phase-centre delays), :6255 +
@@ -143,20 +145,22 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
  * :6332-6340 / :6348-6376 (phase matrix, exp, sum over sources):
  *     V[b,f] = sum_s amp[s,f] w[s,b,f] exp(-2 pi i f ((s_s - s_pc) . b) / c)
  *   d_dircos   [nsrc,3] fp64 source direction cosines (ENU)
- *   d_amp      amplitude table from pb200_amp_table
+ *   d_amp      amplitude table from pb200_amp_table; amp_dtype = PB200_AMP_F32, or PB200_AMP_F64
+ *              (accepted by method PB200_SKYVIS_FP64 only)
  *   d_bl       [nbl,3] fp64 baselines, local ENU metres
  *   h_pc       [3] phase-centre direction cosines (host)
  *   h_freqs    [nchan] Hz (host).  Uniformly spaced channels take the recurrence kernel;
  *              anything else takes the direct (sincospi per term) kernel.
  *   d_src_fwhm_deg  NULL, or [nsrc] sqrt(major*minor) FWHM in degrees (:6267) -> taper on
  *   d_vis      [nbl,nchan] complex128, overwritten
- *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR
+ *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64
  */
 #define PB200_SKYVIS_AUTO       0
 #define PB200_SKYVIS_RECURRENCE 1
 #define PB200_SKYVIS_DIRECT     2
 #define PB200_SKYVIS_RECURRENCE_SCALAR 3   /* same algorithm with scalar FFMA instead of packed FFMA2 (A/B measurement) */
-int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float* d_amp, int nsrc,
+#define PB200_SKYVIS_FP64       4           /* recurrence with every product and sum in fp64 (strongly cancelling skies) */
+int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                  const double* d_src_fwhm_deg, void* d_vis, int method, void* stream);
 

@@ -17,8 +17,9 @@ SKY_ALTAZ, SKY_HADEC, SKY_DIRCOS = 0, 1, 2
 BEAM_DELTA, BEAM_AIRY, BEAM_GAUSSIAN, BEAM_DIPOLE, BEAM_TABLE = 0, 1, 2, 3, 4
 ARRAY_NONE, ARRAY_ANALYTIC, ARRAY_ELEMENTS = 0, 1, 2
 DIPOLE_GENERAL, DIPOLE_SHORT, DIPOLE_HALFWAVE = 0, 1, 2
-SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR = 0, 1, 2, 3
+SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR, SKYVIS_FP64 = 0, 1, 2, 3, 4
 SLAB, SRC_TILE = 128, 32
+AMP_F32, AMP_F64 = 0, 1
 
 
 class BeamDesc(C.Structure):
@@ -53,8 +54,8 @@ SYMBOLS = {
     "pb200_sky_cull": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, C.POINTER(_i), _vp]),
     "pb200_amp_bytes": (C.c_size_t, [_i, _i]),
     "pb200_nsrc_pad": (_i, [_i]),
-    "pb200_amp_table": (_i, [_vp, _vp, _vp, _i, C.POINTER(SpectrumDesc), C.POINTER(BeamDesc), _vp, _vp, _i, _vp, _vp]),
-    "pb200_skyvis": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "pb200_amp_table": (_i, [_vp, _vp, _vp, _i, C.POINTER(SpectrumDesc), C.POINTER(BeamDesc), _vp, _vp, _i, _i, _vp, _vp]),
+    "pb200_skyvis": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "pb200_noise": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_ll), _vp, _i, _i, _d, _d, _i, _u64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pb200_delay_nout": (_i, [_i, _d, _i]),
     "pb200_delay_transform": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp]),

@@ -24,7 +24,7 @@ struct AmpParams {
   const int32_t* index;
   const double* pbeam;
   const double* freqs;   // device copy [nchan]
-  float* amp;
+  void* amp;
   int nsrc, nsrc_pad, nchan, nslab;
 };
 
@@ -36,6 +36,7 @@ __device__ __forceinline__ double airy_field(double sinx, double k, double diame
   return (2.0 * j1(arg) / arg) / (2.0 * j1(arg0) / arg0);
 }
 
+template <typename OUT>
 __global__ void __launch_bounds__(AMP_THREADS) k_amp_table(const AmpParams P) {
   const int s = blockIdx.x;
   const bool live = s < P.nsrc;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(AMP_THREADS) k_amp_table(const AmpParams P) {
 
   const int nchan_pad = P.nslab * PB200_SLAB;
   for (int f = threadIdx.x; f < nchan_pad; f += AMP_THREADS) {
-    float out = 0.0f;
+    OUT out = (OUT)0;
     if (live && f < P.nchan) {
       const double freq = P.freqs[f];
       // ---- spectrum (run_prisim.py:1629-1636 parameters; astroutils power law) ----
@@ -172,10 +173,10 @@ __global__ void __launch_bounds__(AMP_THREADS) k_amp_table(const AmpParams P) {
         }
         pb = pw;
       }
-      out = (float)(pb * flux);                                     // pbfluxes (:6254)
+      out = (OUT)(pb * flux);                                       // pbfluxes (:6254)
     }
     const int slab = f / PB200_SLAB, c = f - slab * PB200_SLAB;
-    P.amp[((size_t)slab * P.nsrc_pad + s) * PB200_SLAB + c] = out;
+    reinterpret_cast<OUT*>(P.amp)[((size_t)slab * P.nsrc_pad + s) * PB200_SLAB + c] = out;
   }
 }
 
@@ -193,11 +194,13 @@ size_t pb200_amp_bytes(int nsrc, int nchan) {
 
 int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_index, int nsrc,
                     const pb200_spectrum_desc* spec, const pb200_beam_desc* beam, const double* d_pbeam,
-                    const double* h_freqs, int nchan, float* d_amp, void* stream_) {
+                    const double* h_freqs, int nchan, int amp_dtype, void* d_amp, void* stream_) {
   if (!ctx) return PB200_EINVAL;
   if (nsrc < 0 || nchan <= 0 || !spec || !beam || !h_freqs || !d_amp)
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: bad arguments");
   if (nsrc > 0 && !d_dircos) return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: null d_dircos");
+  if (amp_dtype != PB200_AMP_F32 && amp_dtype != PB200_AMP_F64)
+    return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: amp_dtype must be PB200_AMP_F32 or PB200_AMP_F64");
   if (beam->element < PB200_BEAM_DELTA || beam->element > PB200_BEAM_TABLE)
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: unknown beam element type");
   if (beam->element == PB200_BEAM_TABLE && !d_pbeam)
@@ -220,7 +223,8 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
   P.dircos = d_dircos; P.index = d_index; P.pbeam = d_pbeam; P.freqs = (const double*)dfreq; P.amp = d_amp;
   P.nsrc = nsrc; P.nsrc_pad = pb200_nsrc_pad(nsrc > 0 ? nsrc : 1); P.nchan = nchan;
   P.nslab = (nchan + PB200_SLAB - 1) / PB200_SLAB;
-  k_amp_table<<<P.nsrc_pad, AMP_THREADS, 0, stream>>>(P);
+  if (amp_dtype == PB200_AMP_F64) k_amp_table<double><<<P.nsrc_pad, AMP_THREADS, 0, stream>>>(P);
+  else k_amp_table<float><<<P.nsrc_pad, AMP_THREADS, 0, stream>>>(P);
   PB_CHECK_LAUNCH(ctx, "k_amp_table");
   // h_freqs was staged with an async copy from (possibly pageable) host memory
   PB_CUDA(ctx, cudaStreamSynchronize(stream));

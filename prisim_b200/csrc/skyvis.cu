@@ -52,7 +52,7 @@ template <int SPC> struct Shape {
 #define PB_INV_RCP2PI_F32 (1.0 / 0.15915493667125701904296875)
 
 struct SkyvisParams {
-  const float* amp;        // [nslab][nsrc_pad][SLAB]
+  const void* amp;         // [nslab][nsrc_pad][SLAB] fp32 (fp64 for the fp64 kernel with an fp64 table)
   const double* geom;      // [nsrc_pad][4]: l, m, n, taper coefficient
   const double* bl;        // [nbl][3] metres
   const double* freqs;     // device [nchan_pad] Hz (padded channels repeat the last frequency)
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     mbar_expect_tx(&full[stage], (uint32_t)(nsl * sizeof(float) * T * PB200_SLAB + sizeof(double) * T * 4));
     for (int i = 0; i < nsl; ++i)
       tma_bulk_g2s(&tin[stage].amp[i][0][0],
-                   P.amp + ((size_t)(blockIdx.x * SPC + i) * P.nsrc_pad + (size_t)tile * T) * PB200_SLAB,
+                   (const float*)P.amp + ((size_t)(blockIdx.x * SPC + i) * P.nsrc_pad + (size_t)tile * T) * PB200_SLAB,
                    sizeof(float) * T * PB200_SLAB, &full[stage]);
     tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
   };
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const float* amp_slab = P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
+  const float* amp_slab = (const float*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
   auto issue = [&](int tile, int stage) {
     mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn<1>));
     tma_bulk_g2s(&tin[stage].amp[0][0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
@@ -428,6 +428,130 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
   flush_acc(P, acc_re, acc_im);
 }
 
+
+// =================================================================================================
+// fp64 kernel: same recurrence, every product and sum in double.  For skies whose visibilities are
+// the small residue of a strongly cancelling sum (smooth diffuse emission on resolved baselines:
+// |V_b| << sqrt(sum a^2)), where fp32 products cannot reach 1e-5 rms(V_b).  B200's FP64 pipe runs at
+// half the FP32 rate (measured 58.8 DFMA lanes/clk/SM), so this costs ~2-3x, not ~60x.
+// Thread = one baseline x 16 channels (32 fp64 accumulators); CTA = 8 channel blocks (one slab) x 2
+// baseline groups; tau and the rotation are computed once per (source, baseline) per tile with the
+// fp64 sincospi; each thread anchors its block with one fp64 sincospi.
+// =================================================================================================
+constexpr int KT64 = 16;
+constexpr int WC64 = PB200_SLAB / KT64;       // 8
+constexpr int WB64 = NWARPS / WC64;           // 2
+constexpr int BL64 = 32 * WB64;               // 64
+struct __align__(16) TilePre64 {
+  double tau[T][BL64];
+  double2 rot[T][BL64];
+  float kap[T][BL64];
+};
+template <typename AMP> struct __align__(16) TileIn64 {
+  AMP amp[T][PB200_SLAB];
+  double geom[T][4];
+};
+
+template <typename AMP, bool TAPER>
+__global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileIn64<AMP>* tin = reinterpret_cast<TileIn64<AMP>*>(smem_raw);
+  TilePre64* tpre = reinterpret_cast<TilePre64*>(smem_raw + NSTAGE * sizeof(TileIn64<AMP>));
+  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn64<AMP>) + sizeof(TilePre64));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  double* sfreq2 = reinterpret_cast<double*>(tail + 64);                   // [SLAB] (f/1e8)^2
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wb = warp % WB64, wc = warp / WB64;
+  const int slab = blockIdx.x;
+  const int bcol = wb * 32 + lane;
+  const int b = blockIdx.y * BL64 + bcol;
+  const bool valid = b < P.nbl;
+  const int kbase = slab * PB200_SLAB + wc * KT64;
+  const int ntiles = P.nsrc_pad / T;
+  const Geometry G = load_baseline(P, b, valid);
+  const double fk0 = P.f0 + (double)kbase * P.df;
+  const double df = P.df;
+
+  if (tid < PB200_SLAB) {
+    const double fs = P.freqs[slab * PB200_SLAB + tid] * 1e-8;
+    sfreq2[tid] = fs * fs;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const AMP* amp_slab = (const AMP*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
+  auto issue = [&](int tile, int stage) {
+    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn64<AMP>));
+    tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(AMP) * T * PB200_SLAB, &full[stage]);
+    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
+  };
+  if (tid == 0) {
+    issue(0, 0);
+    if (ntiles > 1) issue(1, 1);
+  }
+  auto precompute = [&](int tile) {
+    const int stage = tile & 1;
+    mbar_wait(&full[stage], (tile >> 1) & 1);
+    for (int j = 0; j < T / WC64; ++j) {
+      const int s = wc + WC64 * j;
+      const double4 g = *reinterpret_cast<const double4*>(&tin[stage].geom[s][0]);
+      const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;
+      const double tau = tau_g - G.tau_pc;
+      double sn, cs;
+      sincospi(2.0 * frac_turns(tau * df), &sn, &cs);
+      tpre[stage].tau[s][bcol] = tau;
+      tpre[stage].rot[s][bcol] = make_double2(cs, -sn);
+      if (TAPER) tpre[stage].kap[s][bcol] = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
+    }
+  };
+  double acc_re[KT64], acc_im[KT64];
+#pragma unroll
+  for (int k = 0; k < KT64; ++k) { acc_re[k] = 0.0; acc_im[k] = 0.0; }
+  precompute(0);
+  __syncthreads();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int stage = tile & 1;
+    if (tile + 1 < ntiles) precompute(tile + 1);
+    const TileIn64<AMP>& ti = tin[stage];
+    const TilePre64& tp = tpre[stage];
+#pragma unroll 1
+    for (int s = 0; s < T; ++s) {
+      double sn, cs;
+      sincospi(2.0 * frac_turns(tp.tau[s][bcol] * fk0), &sn, &cs);
+      double pr = cs, pi = -sn;
+      const double2 r = tp.rot[s][bcol];
+      const AMP* arow = &ti.amp[s][wc * KT64];
+      double kap = 0.0;
+      if (TAPER) kap = (double)tp.kap[s][bcol];
+#pragma unroll
+      for (int k4 = 0; k4 < KT64 / 4; ++k4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = 4 * k4 + j;
+          double a = (double)arow[k];
+          if (TAPER) a *= exp2(-kap * sfreq2[wc * KT64 + k]);
+          acc_re[k] = fma(a, pr, acc_re[k]);
+          acc_im[k] = fma(a, pi, acc_im[k]);
+          const double nr = fma(-pi, r.y, pr * r.x);
+          const double ni = fma(pi, r.x, pr * r.y);
+          pr = nr; pi = ni;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
+  }
+  if (valid) {
+    double2* row = reinterpret_cast<double2*>(P.vis) + (size_t)b * P.nchan;
+#pragma unroll
+    for (int k = 0; k < KT64; ++k)
+      if (kbase + k < P.nchan) row[kbase + k] = make_double2(acc_re[k], acc_im[k]);
+  }
+}
+
 // geometry staging: [nsrc_pad][4] = (l, m, n, taper coefficient), zero rows for padding
 __global__ void k_geom_stage(const double* __restrict__ dircos, const double* __restrict__ fwhm_deg, int nsrc,
                              int nsrc_pad, double* __restrict__ geom) {
@@ -447,14 +571,16 @@ __global__ void k_geom_stage(const double* __restrict__ dircos, const double* __
 
 }  // namespace
 
-extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float* d_amp, int nsrc,
+extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                             const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                             const double* d_src_fwhm_deg, void* d_vis, int method, void* stream_) {
   if (!ctx) return PB200_EINVAL;
   if (nsrc < 0 || nbl <= 0 || nchan <= 0 || !d_bl || !h_pc || !h_freqs || !d_vis)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: bad arguments");
   if (nsrc > 0 && (!d_dircos || !d_amp)) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: null source arrays");
-  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_SCALAR)
+  if (amp_dtype != PB200_AMP_F32 && !(amp_dtype == PB200_AMP_F64 && method == PB200_SKYVIS_FP64))
+    return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: an fp64 amplitude table needs method PB200_SKYVIS_FP64");
+  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_FP64)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -468,7 +594,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   bool uniform = true;
   for (int k = 0; k < nchan; ++k)
     if (fabs(h_freqs[k] - (h_freqs[0] + k * df)) > 1e-4) { uniform = false; break; }   // 1e-4 Hz * 1e-5 s = 1e-9 turn
-  const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR);
+  const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64);
   const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
   if (want_rec && !uniform)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: recurrence kernel needs uniformly spaced channels");
@@ -498,6 +624,21 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const float*
   P.pc[0] = h_pc[0]; P.pc[1] = h_pc[1]; P.pc[2] = h_pc[2];
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
+  if (method == PB200_SKYVIS_FP64) {
+    dim3 grid64(nslab, pb_div_up(nbl, BL64));
+#define LAUNCH64(AMP, TP)                                                                                     \
+  do {                                                                                                        \
+    const size_t smem = NSTAGE * (sizeof(TileIn64<AMP>) + sizeof(TilePre64)) + 64 + PB200_SLAB * sizeof(double); \
+    PB_CUDA(ctx, cudaFuncSetAttribute(k_skyvis_fp64<AMP, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_skyvis_fp64<AMP, TP><<<grid64, NTHREADS, smem, stream>>>(P);                                            \
+  } while (0)
+    const bool tp64 = d_src_fwhm_deg != nullptr;
+    if (amp_dtype == PB200_AMP_F64) { if (tp64) LAUNCH64(double, true); else LAUNCH64(double, false); }
+    else { if (tp64) LAUNCH64(float, true); else LAUNCH64(float, false); }
+#undef LAUNCH64
+    PB_CHECK_LAUNCH(ctx, "k_skyvis_fp64");
+    return PB200_OK;
+  }
   // CTA shape: wide-channel CTAs when the slab count allows it, 1 slab otherwise
   const char* spc_env = getenv("PB200_SKYVIS_SPC");
   int spc = direct ? 1 : (nslab % 2 == 0 ? 2 : 1);   // measured on B200: 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4

@@ -80,7 +80,7 @@ def make_beam_desc(**kw):
     return b
 
 
-def amp_table(dircos, index, nsrc, spectrum, beam, freqs_hz, pbeam=None, device=None):
+def amp_table(dircos, index, nsrc, spectrum, beam, freqs_hz, pbeam=None, device=None, dtype=torch.float32):
     """``pb200_amp_table``: fp32 amplitude table (slab layout) for the culled sources.
     `spectrum` is a dict of device tensors {flux_scale, index, freq_ref[, flux_offset]} indexed by
     catalogue index, or {spectrum: [nsrc0,nchan]}.  Replaces interferometry.py:6249-6254."""
@@ -89,32 +89,33 @@ def amp_table(dircos, index, nsrc, spectrum, beam, freqs_hz, pbeam=None, device=
     freqs = _h64(freqs_hz)
     nchan = freqs.size
     nbytes = ctx.lib.pb200_amp_bytes(int(nsrc), int(nchan))
-    amp = torch.empty((nbytes // 4,), dtype=torch.float32, device="cuda:{0}".format(device))
+    amp = torch.empty((nbytes // 4,), dtype=dtype, device="cuda:{0}".format(device))
+    amp_dtype = _lib.AMP_F64 if dtype == torch.float64 else _lib.AMP_F32
     sd = SpectrumDesc()
     for key, field in (("flux_scale", "d_flux_scale"), ("index", "d_index"), ("freq_ref", "d_freq_ref"),
                        ("flux_offset", "d_flux_offset"), ("spectrum", "d_spectrum")):
         t = spectrum.get(key, None)
         setattr(sd, field, None if t is None else t.data_ptr())
     ctx.check(ctx.lib.pb200_amp_table(ctx.handle, _ptr(dircos), _ptr(index), int(nsrc), C.byref(sd), C.byref(beam),
-                                      _ptr(pbeam), _ptr(freqs), int(nchan), _ptr(amp), ctx.stream()))
+                                      _ptr(pbeam), _ptr(freqs), int(nchan), amp_dtype, _ptr(amp), ctx.stream()))
     return amp
 
 
 def amp_table_to_dense(amp, nsrc, nchan):
-    """Undo the slab layout: returns a [nsrc, nchan] fp32 tensor (testing / inspection)."""
+    """Undo the slab layout: returns a [nsrc, nchan] tensor of the table's dtype (testing / inspection)."""
     nsrc_pad = ((max(nsrc, 1) + _lib.SRC_TILE - 1) // _lib.SRC_TILE) * _lib.SRC_TILE
     nslab = (nchan + _lib.SLAB - 1) // _lib.SLAB
     a = amp.view(nslab, nsrc_pad, _lib.SLAB).permute(1, 0, 2).reshape(nsrc_pad, nslab * _lib.SLAB)
     return a[:nsrc, :nchan].contiguous()
 
 
-def dense_to_amp_table(dense):
-    """[nsrc, nchan] (any float dtype, CUDA) -> slab layout fp32 table."""
+def dense_to_amp_table(dense, dtype=torch.float32):
+    """[nsrc, nchan] (any float dtype, CUDA) -> slab layout table of `dtype`."""
     nsrc, nchan = dense.shape
     nsrc_pad = ((max(nsrc, 1) + _lib.SRC_TILE - 1) // _lib.SRC_TILE) * _lib.SRC_TILE
     nslab = (nchan + _lib.SLAB - 1) // _lib.SLAB
-    full = torch.zeros((nsrc_pad, nslab * _lib.SLAB), dtype=torch.float32, device=dense.device)
-    full[:nsrc, :nchan] = dense.to(torch.float32)
+    full = torch.zeros((nsrc_pad, nslab * _lib.SLAB), dtype=dtype, device=dense.device)
+    full[:nsrc, :nchan] = dense.to(dtype)
     return full.view(nsrc_pad, nslab, _lib.SLAB).permute(1, 0, 2).contiguous().view(-1)
 
 
@@ -131,8 +132,9 @@ def skyvis(dircos, amp, nsrc, baselines_enu, pc_dircos, freqs_hz, src_fwhm_deg=N
     if out is None:
         out = torch.empty((nbl, nchan), dtype=torch.complex128, device=bl.device)
     code = {"auto": _lib.SKYVIS_AUTO, "recurrence": _lib.SKYVIS_RECURRENCE, "direct": _lib.SKYVIS_DIRECT,
-            "recurrence_scalar": _lib.SKYVIS_RECURRENCE_SCALAR}[method]
-    ctx.check(ctx.lib.pb200_skyvis(ctx.handle, _ptr(dircos), _ptr(amp), int(nsrc), _ptr(bl), int(nbl), _ptr(pc),
+            "recurrence_scalar": _lib.SKYVIS_RECURRENCE_SCALAR, "fp64": _lib.SKYVIS_FP64}[method]
+    amp_dtype = _lib.AMP_F64 if (amp is not None and amp.dtype == torch.float64) else _lib.AMP_F32
+    ctx.check(ctx.lib.pb200_skyvis(ctx.handle, _ptr(dircos), _ptr(amp), amp_dtype, int(nsrc), _ptr(bl), int(nbl), _ptr(pc),
                                    _ptr(freqs), int(nchan), _ptr(src_fwhm_deg), _ptr(out), code, ctx.stream()))
     return out
 

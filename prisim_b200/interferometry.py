@@ -263,6 +263,14 @@ class InterferometerArray(object):
         self.bl_offset = int(bl_offset)                  # position of this shard in the full baseline list
         self.nbl_total = nbl if nbl_total is None else int(nbl_total)
         self.noise_seed = int(noise_seed)
+        # 'fp32': fp32 phasors/amplitudes everywhere (fastest); 'fp64': fp64 kernel + fp64 amplitude table;
+        # 'auto': fp32 first, then every baseline whose visibilities are a strongly cancelling sum
+        # (rms_b < cancel_ratio * incoherent norm, where fp32 products cannot hold 1e-5 rms) is
+        # recomputed by the fp64 kernel (DESIGN.md K1 "precision control")
+        self.precision = "auto"
+        self.cancel_ratio = 0.45
+        self.precision_report = []                       # per snapshot: baselines recomputed in fp64
+        self._fp64_sticky = False
         self.cache_sky = True                            # keep catalogue arrays resident between snapshots
         self._sky_cache = {}
         self._d_bl = None
@@ -523,12 +531,10 @@ class InterferometerArray(object):
             else:                                                                      # :6251-6252
                 beam = PB.beam_desc_from_telescope(self.telescope, pointing_info=pb_info, pointing_center=pc_altaz,
                                                    skyunits="altaz", device=self.device)
-            amp = engine.amp_table(dircos, index, nsrc, sky["spec"], beam, self.channels, pbeam=pbeam, device=self.device)
             fwhm = None
             if "fwhm" in sky:                                                          # :6258-6267
                 fwhm = sky["fwhm"].index_select(0, index.to(torch.int64)).contiguous()
-            skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm,
-                                   device=self.device)
+            skyvis = self._phase_sum(dircos, index, nsrc, sky["spec"], beam, pbeam, pc_dircos, fwhm)
             self.obs_catalog_indices = self.obs_catalog_indices + [index.cpu().numpy().astype(NP.int64)]   # :6377
         else:                                                                          # :6378-6382
             warnings.warn("No sources found in the catalog within matching radius. Simply populating the observed visibilities and/or gradients with noise.")
@@ -550,6 +556,35 @@ class InterferometerArray(object):
         self.t_obs += t_acc
         self.n_acc += 1
         self.lst = self.lst + [lst]
+
+    def _phase_sum(self, dircos, index, nsrc, spec, beam, pbeam, pc_dircos, fwhm):
+        """Amplitude table + phase sum with precision control (see `precision` in __init__)."""
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        kw = dict(pbeam=pbeam, device=self.device)
+        uniform = nchan < 3 or NP.allclose(NP.diff(self.channels), self.freq_resolution, rtol=0, atol=1e-4)
+
+        def run64(bl):
+            amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+            return engine.skyvis(dircos, amp64, nsrc, bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, method="fp64",
+                                 device=self.device)
+
+        if uniform and (self.precision == "fp64" or (self.precision == "auto" and self._fp64_sticky)):
+            self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl})
+            return run64(self._d_bl)
+        amp = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, **kw)
+        skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device)
+        if self.precision == "auto" and uniform:
+            # incoherent norm sqrt(mean_f sum_s a^2) against the rms of each baseline's spectrum: the fp32
+            # kernel's absolute error is ~1-3.5e-6 of the former (measured), the tolerance 1e-5 of the latter
+            a2 = torch.sqrt(amp.double().square().sum() / nchan)
+            rms_b = torch.sqrt(skyvis.real.square().mean(dim=1) + skyvis.imag.square().mean(dim=1))
+            flagged = torch.nonzero(rms_b < self.cancel_ratio * a2).flatten()
+            nflag = int(flagged.numel())
+            self.precision_report.append({"fp64_baselines": nflag, "nbl": nbl})
+            if nflag > 0:
+                skyvis.index_copy_(0, flagged, run64(self._d_bl.index_select(0, flagged).contiguous()))
+            self._fp64_sticky = nflag > 0.5 * nbl
+        return skyvis
 
     # ------------------------------------------------------------------ observing_run
     def observing_run(self, pointing_init, skymodel, t_acc, duration, channels, bpass, Tsys, lst_init, roi_radius=None,
