@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     // software pipeline over sources: the anchor of source s+1 is evaluated while the channel loop of s runs
     float2 p_next = anchor_phasor(tp.tau[0][bcol] * fk0);
     float2 r_next = tp.rot[0][bcol];
-#pragma unroll 1
+#pragma unroll 4
     for (int s = 0; s < T; ++s) {
       const float2 p0 = p_next, r = r_next;
       const int sn = (s + 1 < T) ? s + 1 : s;
