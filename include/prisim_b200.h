@@ -196,6 +196,16 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
                           double pad, int downsample, void* d_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Re-phasing to a new phase centre.  Replaces the elementwise product of
+ * InterferometerArray.phase_centering, interferometry.py:7869-7881 (called via rotate_visibilities,
+ * scripts/run_prisim.py:2282):  V[b,f] *= exp(-2 pi i f b.(s_old - s_new)/c), in place.
+ *   d_vis [nbl,nchan] complex128 (in/out), d_bl [nbl,3] metres in the frame of the direction
+ *   cosines, h_dpos [3] = s_old - s_new (host), h_freqs [nchan] Hz (host).  Synchronises the stream.
+ */
+int pb200_phase_rotate(pb200_ctx* ctx, void* d_vis, const double* d_bl, int nbl, const double* h_dpos,
+                       const double* h_freqs, int nchan, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Issue-rate microbenchmark (FP32 FMA lanes / clk / SM etc.) used for the measured roofline
  * denominator.  Fills out[0..n) with: [0] FFMA lane-ops/s, [1] FFMA
  * lane-ops/clk/SM, [2] MUFU lane-ops/s, [3] DFMA lane-ops/s, [4] SM clock (Hz) seen.  Synchronises.

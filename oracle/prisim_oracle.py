@@ -717,3 +717,32 @@ def delay_transform(vis_freq, bp, bp_wts, freq_resolution, pad=1.0, downsample=T
         out = downsampler(out, 1 + pad, axis=1)                     # :8131-8134
         lags = downsampler(lags, 1 + pad)                           # delay_spectrum.py:1327
     return out, lags
+
+
+# --------------------------------------------------------------------------------------------
+# phase centring / projected baselines (interferometry.py:7712-7995)
+# --------------------------------------------------------------------------------------------
+def enu2xyz(enu, latitude, units="degrees"):
+    """GEOM.enu2xyz [AU-memory]: inverse of xyz2enu (interferometry.py:7976)."""
+    enu = NP.asarray(enu, dtype=NP.float64).reshape(-1, 3)
+    lat = NP.radians(latitude) if units == "degrees" else latitude
+    return NP.stack((-NP.sin(lat) * enu[:, 1] + NP.cos(lat) * enu[:, 2], enu[:, 0],
+                     NP.cos(lat) * enu[:, 1] + NP.sin(lat) * enu[:, 2]), axis=1)
+
+
+def phase_rotate(vis, baselines, dircos_current, dircos_new, channels):
+    """interferometry.py:7866-7871: vis [nbl,nchan,nsnap] * exp(-2 pi i b.(s_cur - s_new) f / c);
+    dircos_* are [nsnap,3]."""
+    pos_diff_dircos = NP.asarray(dircos_current) - NP.asarray(dircos_new)
+    b_dot_l = NP.dot(NP.asarray(baselines), pos_diff_dircos.T)                               # :7867
+    return vis * NP.exp(-1j * 2 * NP.pi * b_dot_l[:, NP.newaxis, :] * NP.asarray(channels).reshape(1, -1, 1) / FCNST.c)
+
+
+def project_baselines(baselines, ha_deg, dec_deg, latitude):
+    """interferometry.py:7973-7985: [nbl, 3, nsnap] uvw-frame baselines for reference HA/Dec per snapshot."""
+    ha, dec = NP.radians(NP.asarray(ha_deg, dtype=NP.float64)).ravel(), NP.radians(NP.asarray(dec_deg, dtype=NP.float64)).ravel()
+    eq_baselines = enu2xyz(baselines, latitude, units="degrees")
+    rot_matrix = NP.asarray([[NP.sin(ha), NP.cos(ha), NP.zeros(ha.size)],
+                             [-NP.sin(dec) * NP.cos(ha), NP.sin(dec) * NP.sin(ha), NP.cos(dec)],
+                             [NP.cos(dec) * NP.cos(ha), -NP.cos(dec) * NP.sin(ha), NP.sin(dec)]])
+    return NP.dot(eq_baselines, rot_matrix)

@@ -59,6 +59,7 @@ SYMBOLS = {
     "pb200_noise": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_ll), _vp, _i, _i, _d, _d, _i, _u64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pb200_delay_nout": (_i, [_i, _d, _i]),
     "pb200_delay_transform": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp]),
+    "pb200_phase_rotate": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "pb200_microbench": (_i, [_vp, C.POINTER(_d), _i]),
 }
 

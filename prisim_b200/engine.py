@@ -219,6 +219,16 @@ def delay_transform(x, bp, wts, df, pad=1.0, downsample=True, nrows=None, nchan=
     return out
 
 
+def phase_rotate(vis, baselines_dev, dpos_dircos, freqs_hz):
+    """``pb200_phase_rotate``: in-place V[b,f] *= exp(-2 pi i f b.dpos/c) (interferometry.py:7869-7881)."""
+    device = vis.device.index
+    ctx = get_context(device)
+    nbl, nchan = vis.shape
+    ctx.check(ctx.lib.pb200_phase_rotate(ctx.handle, _ptr(vis), _ptr(baselines_dev), int(nbl), _ptr(_h64(dpos_dircos)),
+                                         _ptr(_h64(freqs_hz)), int(nchan), ctx.stream()))
+    return vis
+
+
 def microbench(device=None):
     """``pb200_microbench``: measured FP32-FMA / MUFU / FP64 issue rates on this GPU."""
     device = _dev(device)

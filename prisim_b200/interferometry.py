@@ -750,9 +750,130 @@ class InterferometerArray(object):
         if verbose:
             print("delay_transform() completed successfully.")
 
-    # ------------------------------------------------------------------ out of scope on this path
-    def phase_centering(self, *args, **kwargs):
-        raise NotImplementedError("phase_centering is a 'next' row (SURVEY.md section 8f-1)")
+    # ------------------------------------------------------------------ phase centring / uvw (SURVEY 8f-1)
+    def _centre_to_dircos(self, centre, coords):
+        """[n,2|3] phase centres in `coords` -> ENU direction cosines, per snapshot (uses self.lst)."""
+        centre = NP.array(centre, dtype=NP.float64)
+        lst = NP.asarray(self.lst, dtype=NP.float64)
+        if coords == "radec":
+            centre = NP.stack((lst - centre[:, 0], centre[:, 1]), axis=1)
+            coords = "hadec"
+        if coords == "hadec":
+            centre = GEOM.hadec2altaz(centre, self.latitude, units="degrees")
+            coords = "altaz"
+        if coords == "altaz":
+            centre = GEOM.altaz2dircos(centre, units="degrees")
+        return centre
 
+    def phase_centering(self, ref_point, do_delay_transform=False, verbose=True):
+        """interferometry.py:7712-7884: multiply skyvis / vis / noise by exp(-2 pi i f b.(s_old - s_new)/c)
+        and update ``phase_center`` / ``phase_center_coords`` (kept in the current coordinate system)."""
+        if ref_point is None:
+            raise ValueError("Invalid input specified in ref_point")
+        if not isinstance(ref_point, dict):
+            raise TypeError("Input ref_point must be a dictionary")
+        if ("location" not in ref_point) or ("coords" not in ref_point):
+            raise KeyError('Both keys "location" and "coords" must be specified in input dictionary ref_point')
+        phase_center, coords_new = ref_point["location"], ref_point["coords"]
+        nsnap = len(self.lst)
+        if phase_center is None:
+            raise ValueError("Valid phase center not specified in input ref_point")
+        if not isinstance(phase_center, NP.ndarray):
+            raise TypeError("Phase center must be a numpy array")
+        phase_center = phase_center.reshape(-1, phase_center.shape[-1]).astype(NP.float64)
+        if phase_center.shape[0] == 1:
+            phase_center = NP.repeat(phase_center, nsnap, axis=0)
+        elif phase_center.shape[0] != nsnap:
+            raise ValueError("One phase center must be provided for every timestamp.")
+        if coords_new not in ("dircos", "altaz", "hadec", "radec"):
+            raise ValueError("Invalid phase center coordinate system specified")
+        if coords_new == "dircos":
+            if (phase_center.shape[1] < 2) or (phase_center.shape[1] > 3):
+                raise ValueError("Dimensions incompatible for direction cosine positions")
+            if NP.any(NP.sqrt(NP.sum(phase_center ** 2, axis=1)) > 1.0):
+                raise ValueError("direction cosines found to be exceeding unit magnitude.")
+            if phase_center.shape[1] == 2:
+                phase_center = NP.hstack((phase_center, (1.0 - NP.sqrt(NP.sum(phase_center ** 2, axis=1))).reshape(-1, 1)))  # :7787 (sic)
+        new_dircos = self._centre_to_dircos(phase_center, coords_new)                       # :7813-7846
+        cur_dircos = self._centre_to_dircos(self.phase_center, self.phase_center_coords)    # :7853-7863
+        # the stored phase centre stays in the array's current coordinate system (:7778-7846, :7867-7868)
+        lst = NP.asarray(self.lst, dtype=NP.float64)
+        cur = self.phase_center_coords
+        if cur == "altaz":
+            stored = GEOM.dircos2altaz(new_dircos, units="degrees")
+        else:
+            hadec = GEOM.altaz2hadec(GEOM.dircos2altaz(new_dircos, units="degrees"), self.latitude, units="degrees")
+            if coords_new in ("hadec", "radec") and cur in ("hadec", "radec"):                # avoid a round trip through alt-az
+                hadec = phase_center.copy() if coords_new == "hadec" else NP.stack((lst - phase_center[:, 0], phase_center[:, 1]), axis=1)
+            stored = hadec if cur == "hadec" else NP.stack((lst - hadec[:, 0], hadec[:, 1]), axis=1)
+        pos_diff = cur_dircos - new_dircos                                                  # :7866
+        for t in range(nsnap):
+            for lst_t in (self._skyvis, self._vis, self._noise):                            # :7871-7881
+                if lst_t:
+                    engine.phase_rotate(lst_t[t], self._d_bl, pos_diff[t], self.channels)
+        self.phase_center = stored
+        if do_delay_transform:
+            self.delay_transform(verbose=verbose)
+
+    def project_baselines(self, ref_point):
+        """interferometry.py:7888-7995: baselines projected on the (u,v,w) frame of a reference direction,
+        [nbl, 3, n_acc].  O(nbl x n_acc) host arithmetic."""
+        if ref_point is None:
+            raise ValueError("Invalid input specified in ref_point")
+        if not isinstance(ref_point, dict):
+            raise TypeError("Input ref_point must be a dictionary")
+        if ("location" not in ref_point) or ("coords" not in ref_point):
+            raise KeyError('Both keys "location" and "coords" must be specified in input dictionary ref_point')
+        phase_center, coords = ref_point["location"], ref_point["coords"]
+        if not isinstance(phase_center, NP.ndarray):
+            raise TypeError("The specified reference point must be a numpy array")
+        if not isinstance(coords, str):
+            raise TypeError("The specified coordinates of the reference point must be a string")
+        if coords not in ["radec", "hadec", "altaz", "dircos"]:
+            raise ValueError("Specified coordinates of reference point invalid")
+        if phase_center.ndim == 1:
+            phase_center = phase_center.reshape(1, -1)
+        if phase_center.ndim > 2:
+            raise ValueError("Reference point has invalid dimensions")
+        if (phase_center.shape[0] != self.n_acc) and (phase_center.shape[0] != 1):
+            raise ValueError("Reference point has dimensions incompatible with the number of timestamps")
+        if phase_center.shape[0] == 1:
+            phase_center = phase_center + NP.zeros(self.n_acc).reshape(-1, 1)
+        if coords in ("radec", "hadec", "altaz") and phase_center.shape[1] != 2:
+            raise ValueError("Reference point has invalid dimensions")
+        if coords == "radec":
+            ha, dec = NP.asarray(self.lst) - phase_center[:, 0], phase_center[:, 1]
+        elif coords == "hadec":
+            ha, dec = phase_center[:, 0], phase_center[:, 1]
+        else:
+            if coords == "dircos":
+                if (phase_center.shape[1] < 2) or (phase_center.shape[1] > 3):
+                    raise ValueError("Reference point has invalid dimensions")
+                if NP.any(NP.sqrt(NP.sum(phase_center ** 2, axis=1)) > 1.0):
+                    raise ValueError("direction cosines found to be exceeding unit magnitude.")
+                if phase_center.shape[1] == 2:
+                    phase_center = NP.hstack((phase_center, (1.0 - NP.sqrt(NP.sum(phase_center ** 2, axis=1))).reshape(-1, 1)))
+                phase_center = GEOM.dircos2altaz(phase_center, units="degrees")
+            hadec = GEOM.altaz2hadec(phase_center, self.latitude, units="degrees")
+            ha, dec = hadec[:, 0], hadec[:, 1]
+        ha, dec = NP.radians(ha).ravel(), NP.radians(dec).ravel()
+        eq_baselines = GEOM.enu2xyz(self.baselines, self.latitude, units="degrees")          # :7976
+        rot_matrix = NP.asarray([[NP.sin(ha), NP.cos(ha), NP.zeros(ha.size)],
+                                 [-NP.sin(dec) * NP.cos(ha), NP.sin(dec) * NP.sin(ha), NP.cos(dec)],
+                                 [NP.cos(dec) * NP.cos(ha), -NP.cos(dec) * NP.sin(ha), NP.sin(dec)]])   # :7977-7979
+        self.projected_baselines = NP.dot(eq_baselines, rot_matrix)                          # :7985
+
+    def rotate_visibilities(self, ref_point, do_delay_transform=False, verbose=True):
+        """interferometry.py:7655-7708: phase_centering + project_baselines."""
+        if ref_point is None:
+            raise ValueError("Invalid input specified in ref_point")
+        if not isinstance(ref_point, dict):
+            raise TypeError("Input ref_point must be a dictionary")
+        if ("location" not in ref_point) or ("coords" not in ref_point):
+            raise KeyError('Both keys "location" and "coords" must be specified in input dictionary ref_point')
+        self.phase_centering(ref_point, do_delay_transform=do_delay_transform, verbose=verbose)
+        self.project_baselines(ref_point)
+
+    # ------------------------------------------------------------------ out of scope on this path
     def save(self, *args, **kwargs):
         raise NotImplementedError("on-disk formats are a 'next' row (SURVEY.md section 8f-2)")

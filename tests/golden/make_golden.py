@@ -87,6 +87,12 @@ def sphdist(lon1, lat1, lon2, lat2):
     return NP.degrees(2 * NP.arcsin(NP.minimum(1.0, NP.sqrt(a))))
 
 
+def enu2xyz(enu, latitude, units=None):
+    enu = NP.asarray(enu, dtype=float).reshape(-1, 3)
+    lat = NP.radians(latitude) if units == "degrees" else latitude
+    return NP.stack((-NP.sin(lat) * enu[:, 1] + NP.cos(lat) * enu[:, 2], enu[:, 0], NP.cos(lat) * enu[:, 1] + NP.sin(lat) * enu[:, 2]), axis=1)
+
+
 def xyz2enu(xyz, latitude, units=None):
     xyz = NP.asarray(xyz, dtype=float).reshape(-1, 3)
     lat = NP.radians(latitude) if units == "degrees" else latitude
@@ -128,7 +134,7 @@ class SkyModel(object):
 def install_stubs():
     au = _mod("astroutils", __githash__="stub")
     au.geometry = _mod("astroutils.geometry", altaz2dircos=altaz2dircos, dircos2altaz=dircos2altaz, hadec2altaz=hadec2altaz,
-                       altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu)
+                       altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu, enu2xyz=enu2xyz)
     au.DSP_modules = _mod("astroutils.DSP_modules", FT1D=FT1D, spectral_axis=spectral_axis, downsampler=downsampler)
     au.catalog = _mod("astroutils.catalog", SkyModel=SkyModel)
     au.constants = _mod("astroutils.constants", Jy=1.0e-26, sday=0.99726958, rest_freq_HI=1420405751.77)
@@ -294,6 +300,19 @@ def main():
         ia.delay_transform(pad=0.5, freq_wts=window, verbose=False)
         rec["skyvis_lag_pad05"] = ia.skyvis_lag
         NP.savez_compressed(os.path.join(OUT, "observe_{0}.npz".format(tag)), **rec)
+        if tag == "hera":
+            # rotate_visibilities = phase_centering + project_baselines (interferometry.py:7655-7995), twice:
+            # to a fixed HA/Dec, then to an RA/Dec that differs per snapshot
+            rot = {}
+            ref1 = {"location": NP.asarray([[12.0, -24.0]]), "coords": "hadec"}
+            ia.rotate_visibilities(ref1, do_delay_transform=False, verbose=False)
+            rot.update(skyvis_rot1=ia.skyvis_freq, vis_rot1=ia.vis_freq, noise_rot1=ia.vis_noise_freq, pc_rot1=ia.phase_center,
+                       proj_rot1=ia.projected_baselines)
+            ref2 = {"location": NP.asarray([[350.0, -31.0], [5.0, -29.0], [30.0, -35.0]])[:nsnap], "coords": "radec"}
+            ia.rotate_visibilities(ref2, do_delay_transform=False, verbose=False)
+            rot.update(skyvis_rot2=ia.skyvis_freq, pc_rot2=ia.phase_center, proj_rot2=ia.projected_baselines,
+                       ref1=ref1["location"], ref2=ref2["location"], pc_coords=NP.asarray(ia.phase_center_coords))
+            NP.savez_compressed(os.path.join(OUT, "rotate_hera.npz"), **rot)
 
     hera = {"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}
     run_observe("hera", hera)

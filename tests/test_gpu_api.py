@@ -226,3 +226,43 @@ def test_fp64_kernel_and_precision_control_on_point_sources():
     from prisim_b200._lib import PB200Error
     with pytest.raises(PB200Error):
         engine.skyvis(dircos, amp64, nsrc, bl, (0, 0, 1.0), freqs, method="recurrence")
+
+
+def test_rotate_visibilities_against_reference_golden():
+    """phase_centering / project_baselines / rotate_visibilities replayed on the GPU shim
+    (interferometry.py:7655-7995; scripts/run_prisim.py:2282)."""
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    g = NP.load(os.path.join(GOLD, "observe_hera.npz"))
+    r = NP.load(os.path.join(GOLD, "rotate_hera.npz"))
+    case = OBSERVE_CASES["hera"]
+    nbl, nchan, nsnap = g["skyvis_freq"].shape
+    labels = [("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)]
+    ia = InterferometerArray(labels, g["bl"], g["chans"], telescope=dict(case["telescope"]), eff_Q=0.96, latitude=float(g["latitude"]),
+                             skycoords="hadec", A_eff=154.0 * 0.65, pointing_coords="hadec", device=0)
+    nsrc0 = g["flux"].size
+    for j in range(nsnap):
+        parms = {"location": g["hadec_{0}".format(j)], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+                 "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": g["spindex"], "freq-ref": NP.full(nsrc0, 150e6),
+                                "flux-scale": g["flux"]}}
+        ia.observe(SimpleTime(2451545.0 + j * 0.01, float(g["lsts"][j])), {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None},
+                   g["bandpass"], g["pointing"], SkyModel(init_parms=parms), float(g["t_acc"][j]))
+    ia.generate_noise(); ia.add_noise()
+    noise0, vis0 = ia.vis_noise_freq, ia.vis_freq
+    ia.rotate_visibilities({"location": r["ref1"], "coords": "hadec"}, verbose=False)
+    assert rel_err(ia.skyvis_freq, r["skyvis_rot1"]) <= TOL
+    assert NP.allclose(ia.phase_center, r["pc_rot1"]) and ia.phase_center_coords == "hadec"
+    assert NP.allclose(ia.projected_baselines, r["proj_rot1"], atol=1e-9)
+    # the noise and noisy visibilities are rotated by the same phasor (:7876-7881)
+    ph = r["skyvis_rot1"] / NP.where(g["skyvis_freq"] == 0, 1, g["skyvis_freq"])
+    assert NP.abs(ia.vis_noise_freq - noise0 * ph).max() <= 1e-9 * NP.abs(noise0).max()
+    assert NP.abs(ia.vis_freq - vis0 * ph).max() <= 1e-9 * NP.abs(vis0).max()
+    ia.rotate_visibilities({"location": r["ref2"], "coords": "radec"}, verbose=False)
+    assert rel_err(ia.skyvis_freq, r["skyvis_rot2"]) <= TOL
+    assert NP.allclose(ia.phase_center, r["pc_rot2"]) and NP.allclose(ia.projected_baselines, r["proj_rot2"], atol=1e-9)
+    with pytest.raises(KeyError):
+        ia.rotate_visibilities({"location": r["ref1"]})
+    with pytest.raises(TypeError):
+        ia.phase_centering({"location": [1.0, 2.0], "coords": "hadec"})
+    with pytest.raises(ValueError):
+        ia.phase_centering({"location": NP.zeros((2, 2)), "coords": "hadec"})

@@ -141,3 +141,34 @@ def test_observe_matches_reference(tag):
     assert NP.allclose(lags, g["lags"])
     kern, _ = O.delay_transform(NP.ones_like(ref), bp, wts, df, pad=1.0)
     assert NP.abs(kern - g["lag_kernel"]).max() <= 1e-12 * NP.abs(g["lag_kernel"]).max()
+
+
+def test_rotate_visibilities_matches_reference():
+    """phase_centering + project_baselines (interferometry.py:7655-7995) replayed through the oracle."""
+    g = _load("observe_hera.npz")
+    r = _load("rotate_hera.npz")
+    lat = float(g["latitude"])
+    lst = g["lsts"]
+    nsnap = lst.size
+    cur = O.altaz2dircos(O.hadec2altaz(NP.repeat(g["pointing"].reshape(1, 2), nsnap, axis=0), lat))
+    new1_hadec = NP.repeat(r["ref1"], nsnap, axis=0)
+    new1 = O.altaz2dircos(O.hadec2altaz(new1_hadec, lat))
+    V1 = O.phase_rotate(g["skyvis_freq"], g["bl"], cur, new1, g["chans"])
+    scale = NP.sqrt(NP.mean(NP.abs(r["skyvis_rot1"]) ** 2))
+    assert NP.abs(V1 - r["skyvis_rot1"]).max() <= 1e-11 * scale
+    assert NP.abs(O.phase_rotate(g["vis_freq"], g["bl"], cur, new1, g["chans"]) - r["vis_rot1"]).max() <= 1e-11 * scale
+    assert NP.allclose(r["pc_rot1"], new1_hadec)
+    assert NP.allclose(O.project_baselines(g["bl"], new1_hadec[:, 0], new1_hadec[:, 1], lat), r["proj_rot1"], atol=1e-10)
+    new2_hadec = NP.stack((lst - r["ref2"][:, 0], r["ref2"][:, 1]), axis=1)
+    new2 = O.altaz2dircos(O.hadec2altaz(new2_hadec, lat))
+    V2 = O.phase_rotate(V1, g["bl"], new1, new2, g["chans"])
+    assert NP.abs(V2 - r["skyvis_rot2"]).max() <= 1e-11 * scale
+    assert NP.allclose(r["pc_rot2"], new2_hadec) and str(r["pc_coords"]) == "hadec"
+    assert NP.allclose(O.project_baselines(g["bl"], new2_hadec[:, 0], new2_hadec[:, 1], lat), r["proj_rot2"], atol=1e-10)
+    # rotating to the new centre equals simulating with that phase centre in the first place
+    V_direct, _ = O.observe_snapshot(g["bl"], g["chans"], g["hadec_0"], "hadec", lat, g["pointing"], "hadec",
+                                     dict(OBSERVE_CASES["hera"]["telescope"]), g["flux"], g["spindex"], 150e6)
+    pbf_free = V1[:, :, 0]       # same beam (pointing unchanged), phases referred to new1
+    s_new = new1[0] - cur[0]
+    expect = V_direct * NP.exp(+2j * NP.pi * (g["bl"] @ s_new)[:, None] * g["chans"][None, :] / 299792458.0)
+    assert NP.abs(pbf_free - expect).max() <= 1e-9 * scale
