@@ -874,6 +874,23 @@ class InterferometerArray(object):
         self.phase_centering(ref_point, do_delay_transform=do_delay_transform, verbose=verbose)
         self.project_baselines(ref_point)
 
-    # ------------------------------------------------------------------ out of scope on this path
-    def save(self, *args, **kwargs):
-        raise NotImplementedError("on-disk formats are a 'next' row (SURVEY.md section 8f-2)")
+    # ------------------------------------------------------------------ on-disk (NPZ only)
+    def save(self, outfile, fmt="NPZ", tabtype="BinTableHDU", npz=True, overwrite=False, uvfits_parms=None, verbose=True):
+        """The NPZ product of interferometry.py:8859-8863 (same keys).  The HDF5/FITS layouts
+        (:8722-8854) need h5py/astropy, which this image does not have: fmt must be 'NPZ'."""
+        if not isinstance(outfile, str):
+            raise TypeError("Output filename must be a string")
+        if fmt.upper() != "NPZ":
+            raise NotImplementedError("only the NPZ product is written here (h5py/astropy are unavailable); pass fmt='NPZ'")
+        if uvfits_parms is not None:
+            raise NotImplementedError("UVFITS export is outside the hot-path scope")
+        if npz:
+            if (self._vis) and (self._noise):
+                NP.savez_compressed(outfile + ".npz", skyvis_freq=self.skyvis_freq, vis_freq=self.vis_freq,
+                                    vis_noise_freq=self.vis_noise_freq, lst=self.lst, freq=self.channels, timestamp=self.timestamp,
+                                    bl=self.baselines, bl_length=self.baseline_lengths)
+            else:
+                NP.savez_compressed(outfile + ".npz", skyvis_freq=self.skyvis_freq, lst=self.lst, freq=self.channels,
+                                    timestamp=self.timestamp, bl=self.baselines, bl_length=self.baseline_lengths)
+            if verbose:
+                print("\tInterferometer array information written successfully to NPZ file on disk:\n\t\t{0}\n".format(outfile + ".npz"))

@@ -88,6 +88,14 @@ def test_config1_observing_run_vs_oracle():
     ia.observing_run(cfg["pointing_hadec"], cfg["skymodel"], t_acc, nsnap * t_acc, cfg["channels"], NP.ones(128), 300.0, 0.0,
                      mode="drift", pointing_coords="hadec", verbose=False)
     assert ia.n_acc == nsnap and ia.skyvis_freq.shape == (171, 128, nsnap)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:                      # NPZ product, same keys as interferometry.py:8859-8863
+        ia.save(os.path.join(td, "simvis"), fmt="NPZ", verbose=False)
+        z = NP.load(os.path.join(td, "simvis.npz"))
+        assert set(z.files) == {"skyvis_freq", "lst", "freq", "timestamp", "bl", "bl_length"}
+        assert NP.array_equal(z["skyvis_freq"], ia.skyvis_freq) and NP.allclose(z["freq"], cfg["channels"])
+        with pytest.raises(NotImplementedError):
+            ia.save(os.path.join(td, "simvis"), fmt="HDF5")
     sky = cfg["skymodel"]; sp = sky.spec_parms
     Vo = []
     for j in range(nsnap):
