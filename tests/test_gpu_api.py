@@ -274,3 +274,91 @@ def test_rotate_visibilities_against_reference_golden():
         ia.phase_centering({"location": [1.0, 2.0], "coords": "hadec"})
     with pytest.raises(ValueError):
         ia.phase_centering({"location": NP.zeros((2, 2)), "coords": "hadec"})
+
+
+def _subset_oracle(cfg, lst, bsel, csel, **kw):
+    sky = cfg["skymodel"]; sp = sky.spec_parms
+    hadec = NP.stack((lst - sky.location[:, 0], sky.location[:, 1]), 1)
+    return O.observe_snapshot(cfg["baselines"][bsel], cfg["channels"][csel], hadec, "hadec", cfg["latitude"], kw.pop("pointing"),
+                              kw.pop("pointing_coords"), cfg["telescope"], sp["flux-scale"], sp["power-law-index"], sp["freq-ref"], **kw)
+
+
+def test_config3_full_size_snapshot_subset_parity():
+    """BASELINE config 3 at full size for one snapshot: nside-256 diffuse sky (786,432 pixels, ~393k above the
+    horizon, taper on) x HERA-331 (54,615 baselines) x 256 channels; parity on a baseline/channel subset."""
+    from prisim_b200 import synthetic as S
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    cfg = S.config3(nsnap=1)
+    ia = InterferometerArray(cfg["labels"], cfg["baselines"], cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
+                             skycoords="radec", pointing_coords="hadec", device=0)
+    ia.observe(SimpleTime(2451545.0, 20.0), {"Tnet": 200.0}, NP.ones(256), cfg["pointing_hadec"], cfg["skymodel"], cfg["t_acc"])
+    assert ia.baselines.shape[0] == 54615 and 380000 < ia.obs_catalog_indices[0].size < 400000
+    rng = NP.random.default_rng(3)
+    bsel = NP.sort(NP.concatenate(([0, 54614], rng.choice(54615, 6, replace=False))))
+    csel = NP.sort(rng.choice(256, 24, replace=False))
+    Vo, m2 = _subset_oracle(cfg, 20.0, bsel, csel, pointing=cfg["pointing_hadec"], pointing_coords="hadec", src_shape=cfg["skymodel"].src_shape)
+    assert NP.array_equal(ia.obs_catalog_indices[0], m2)
+    V = ia.skyvis_freq_device(0)
+    Vg = V[torch.as_tensor(bsel).cuda()][:, torch.as_tensor(csel).cuda()].cpu().numpy()
+    rms_b = V[torch.as_tensor(bsel).cuda()].abs().pow(2).mean(dim=1, keepdim=True).sqrt().cpu().numpy()
+    assert float((NP.abs(Vg - Vo) / rms_b).max()) <= TOL
+    assert ia.precision_report[0]["fp64_baselines"] > 0.5 * 54615          # the smooth sky cancels on most baselines
+
+
+def test_config4_full_size_mwa_tile_subset_parity():
+    """BASELINE config 4 at full size: 128 tiles (8,128 baselines) x 768 channels x 50k-source catalogue with the
+    phased 4x4 tile beam (quantised delays) and ground plane."""
+    from prisim_b200 import synthetic as S
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    cfg = S.config4()
+    ia = InterferometerArray(cfg["labels"], cfg["baselines"], cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
+                             skycoords="radec", pointing_coords="altaz", device=0)
+    ia.observe(SimpleTime(2451545.0, 50.0), {"Tnet": 200.0}, NP.ones(768), cfg["pointing_altaz"], cfg["skymodel"], cfg["t_acc"], pb_info=cfg["pb_info"])
+    assert ia.baselines.shape[0] == 8128
+    rng = NP.random.default_rng(4)
+    bsel = NP.sort(NP.concatenate(([0, 8127], rng.choice(8128, 10, replace=False))))
+    csel = NP.sort(rng.choice(768, 32, replace=False))
+    Vo, m2 = _subset_oracle(cfg, 50.0, bsel, csel, pointing=cfg["pointing_altaz"], pointing_coords="altaz", pb_info=cfg["pb_info"])
+    assert NP.array_equal(ia.obs_catalog_indices[0], m2)
+    V = ia.skyvis_freq_device(0)
+    Vg = V[torch.as_tensor(bsel).cuda()][:, torch.as_tensor(csel).cuda()].cpu().numpy()
+    rms_b = V[torch.as_tensor(bsel).cuda()].abs().pow(2).mean(dim=1, keepdim=True).sqrt().cpu().numpy()
+    assert float((NP.abs(Vg - Vo) / rms_b).max()) <= TOL
+
+
+def test_config5_pipeline_three_snapshots():
+    """BASELINE config 5 shape (HERA-350 x 1024 ch + Tsys noise + windowed delay transform) for 3 of the 1000
+    snapshots with a 20k-source catalogue: size-independent properties of the full pipeline."""
+    from prisim_b200 import synthetic as S
+    from prisim_b200.delay_spectrum import windowing
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    cfg = S.config5(nsnap=3, nsrc=20000)
+    ia = InterferometerArray(cfg["labels"], cfg["baselines"], cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
+                             skycoords="radec", pointing_coords="hadec", A_eff=cfg["A_eff"], eff_Q=cfg["eff_Q"], device=0, noise_seed=11)
+    for j in range(3):
+        ia.observe(SimpleTime(2451545.0 + j * 1e-4, j * 10.7 / 240.0), cfg["Tsysinfo"], NP.ones(1024), cfg["pointing_hadec"], cfg["skymodel"], cfg["t_acc"])
+    ia.generate_noise(); ia.add_noise()
+    window = 1024 * windowing(1024, "bhw", area_normalize=True)
+    ia.delay_transform(pad=1.0, freq_wts=window, verbose=False)
+    V, N, R = ia._skyvis, ia._noise, ia._rms
+    # rms follows the radiometer equation; noise is white with that rms; vis = sky + noise
+    Tsys = O.system_temperature(cfg["Tsysinfo"], cfg["channels"], 1)[0]
+    rms_o = O.thermal_noise_rms(Tsys[None, :, None], cfg["A_eff"], cfg["eff_Q"], [cfg["t_acc"]], cfg["channels"][1] - cfg["channels"][0])[0, :, 0]
+    assert NP.allclose(R[0][5].cpu().numpy(), rms_o, rtol=1e-12)
+    z = (N[1] / (R[1] / NP.sqrt(2.0)))
+    assert abs(z.real.std().item() - 1) < 2e-3 and abs(z.imag.std().item() - 1) < 2e-3 and abs(z.mean().abs().item()) < 1e-3
+    assert torch.equal(ia._vis[2], V[2] + N[2])
+    # linearity of the delay transform and Parseval with the window
+    L = ia._lag
+    assert (L["vis"][0] - L["skyvis"][0] - L["noise"][0]).abs().max().item() <= 1e-9 * L["vis"][0].abs().max().item()
+    df = cfg["channels"][1] - cfg["channels"][0]
+    w = torch.as_tensor(window).cuda()
+    lhs = L["skyvis"][1].abs().pow(2).sum(dim=1) / (1024 * df ** 2)
+    rhs = (V[1] * w).abs().pow(2).sum(dim=1)
+    assert ((lhs - rhs).abs() / rhs).max().item() < 1e-10
+    # foreground power is confined within the horizon delay limits (+ window main lobe) on a long baseline
+    b = 61074
+    blen = NP.linalg.norm(cfg["baselines"][b])
+    lag_power = L["skyvis"][0][b].abs().pow(2).cpu().numpy()
+    inside = NP.abs(ia.lags) <= blen / 299792458.0 + 4.0 / (1024 * df)
+    assert lag_power[inside].sum() > 0.999 * lag_power.sum()
