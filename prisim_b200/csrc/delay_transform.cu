@@ -3,12 +3,14 @@
 //   X = fftshift(ifft(pad_right(x * bp * wts, npad))) * (nchan + npad) * df,
 //   then DSP.downsampler(X, 1+pad) = linear interpolation at positions arange(0, n, 1+pad).
 //
-// Two hand-written kernels (no cuFFT):
-//   k_delay_fft   radix-2 decimation-in-time inverse FFT of one row in shared memory (fp64),
-//                 fused with the bp*wts multiply on load and with scale + fftshift + decimation on
-//                 store.  Used when the transform length is a power of two <= 8192.  When 1+pad
-//                 is an integer m and nchan is even, decimating the m*nchan-point padded
-//                 transform by m is exactly the nchan-point transform, so that one is computed.
+// Three hand-written kernels (no cuFFT):
+//   k_delay_fft_r8 register-resident radix-8 Stockham inverse FFT (fp64), global -> registers ->
+//                 (smem between passes) -> global with the bp*wts multiply, scale and fftshift
+//                 fused; power-of-two lengths 64..4096 without interpolation.  When 1+pad is an
+//                 integer m and nchan is even, decimating the m*nchan-point padded transform by m
+//                 is exactly the nchan-point transform, so that one is computed (default pad=1).
+//   k_delay_fft   radix-2 in-smem inverse FFT with linear-interpolated decimation on store: the
+//                 remaining power-of-two cases (non-integer decimation, N < 64, N = 8192).
 //   k_delay_dft   direct evaluation of just the output samples needed (any length, any pad):
 //                 O(nout * nchan) per row, twiddles from an exact integer-indexed table.
 // HBM-bound: algorithmic bytes per row = nchan*(16 + 8 + 8) read + nout*16 written.
@@ -88,6 +90,95 @@ __global__ void __launch_bounds__(FFT_THREADS) k_delay_fft(const DelayParams P) 
       o = a;
     }
     P.out[(size_t)row * P.nout + i] = make_double2(o.x * P.scale, o.y * P.scale);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_delay_fft_r8: register-resident mixed-radix (8,8,...,{8,4,2}) Stockham autosort inverse FFT.
+// The first pass reads global memory directly (fused bp*wts multiply and zero padding), the last
+// pass writes global memory directly (fused scale + fftshift); only the passes in between go
+// through shared memory (ping-pong buffers, one __syncthreads per pass: 3 for N=1024 instead of
+// the 10 of the radix-2 kernel).  One row = N/8 threads; a CTA carries 256/(N/8) rows (>= 1).
+// Used for 64 <= N <= 4096 when no interpolation is needed (factor == 1).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmuli(double2 a) { return make_double2(-a.y, a.x); }          // * (+i)
+
+template <int R> __device__ __forceinline__ void ifft_small(double2 (&v)[R]);
+template <> __device__ __forceinline__ void ifft_small<2>(double2 (&v)[2]) {
+  double2 a = v[0], b = v[1];
+  v[0] = cadd(a, b); v[1] = csub(a, b);
+}
+template <> __device__ __forceinline__ void ifft_small<4>(double2 (&v)[4]) {
+  double2 s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]), s2 = cadd(v[1], v[3]), s3 = cmuli(csub(v[1], v[3]));
+  v[0] = cadd(s0, s2); v[1] = cadd(s1, s3); v[2] = csub(s0, s2); v[3] = csub(s1, s3);
+}
+template <> __device__ __forceinline__ void ifft_small<8>(double2 (&v)[8]) {
+  const double h = 0.70710678118654752440;
+  double2 a[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a[i] = cadd(v[i], v[i + 4]); b[i] = csub(v[i], v[i + 4]); }
+  b[1] = make_double2(h * (b[1].x - b[1].y), h * (b[1].x + b[1].y));        // * exp(+i pi/4)
+  b[2] = cmuli(b[2]);                                                       // * exp(+i pi/2)
+  b[3] = make_double2(-h * (b[3].x + b[3].y), h * (b[3].x - b[3].y));       // * exp(+3 i pi/4)
+  ifft_small<4>(a);
+  ifft_small<4>(b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = a[i]; v[2 * i + 1] = b[i]; }
+}
+
+template <int R>
+__device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, int t, int T, int Ns, bool first, bool last,
+                                              const double2* __restrict__ src, double2* __restrict__ dst) {
+  const int N = P.nfft, NR = N / R;
+  for (int j = t; j < NR; j += T) {
+    double2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = first ? load_in(P, row, j + r * NR) : src[j + r * NR];
+    const int k = j & (Ns - 1);
+    if (Ns > 1) {
+      const int tstep = k * (N / (Ns * R));
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(&P.twiddle[(r * tstep) & (N - 1)]));
+    }
+    ifft_small<R>(v);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int o = j0 + r * Ns;
+      if (last) {
+        int i = o - P.shift; if (i < 0) i += N;                            // fftshift: out[i] = X[(i + shift) % N]
+        P.out[(size_t)row * P.nout + i] = make_double2(v[r].x * P.scale, v[r].y * P.scale);
+      } else {
+        dst[o] = v[r];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_delay_fft_r8(const DelayParams P, int T, int rows_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = P.nfft;
+  const int lrow = threadIdx.x / T, t = threadIdx.x % T;
+  const int row = blockIdx.x * rows_per_cta + lrow;
+  const bool active = lrow < rows_per_cta && row < P.nrows;
+  double2* buf0 = reinterpret_cast<double2*>(smem_raw) + (size_t)lrow * 2 * N;
+  double2* buf1 = buf0 + N;
+  int Ns = 1, rem = P.log2n, pass = 0;
+  while (rem > 0) {
+    const int lr = rem >= 3 ? 3 : rem;                                     // radix 8, then 4 or 2
+    const bool first = pass == 0, last = rem == lr;
+    const double2* src = (pass & 1) ? buf0 : buf1;                         // pass p reads what pass p-1 wrote
+    double2* dst = (pass & 1) ? buf1 : buf0;
+    if (active) {
+      if (lr == 3) stockham_pass<8>(P, row, t, T, Ns, first, last, src, dst);
+      else if (lr == 2) stockham_pass<4>(P, row, t, T, Ns, first, last, src, dst);
+      else stockham_pass<2>(P, row, t, T, Ns, first, last, src, dst);
+    }
+    if (!last) __syncthreads();
+    Ns <<= lr; rem -= lr; ++pass;
   }
 }
 
@@ -191,7 +282,14 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
   P.nrows = nrows; P.nchan = nchan; P.nfft = pl.nfft; P.log2n = pl.log2n; P.nout = pl.nout;
   P.shift = (pl.nfft + 1) / 2;
   P.scale = df; P.factor = pl.factor;
-  if (pl.pow2) {
+  if (pl.pow2 && pl.factor == 1.0 && pl.nfft >= 64 && pl.nfft <= 4096) {
+    const int T = pl.nfft / 8 < 256 ? pl.nfft / 8 : 256;
+    const int rows_per_cta = 256 / T;
+    const size_t smem = sizeof(double2) * 2 * (size_t)pl.nfft * rows_per_cta;
+    PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_delay_fft_r8<<<pb_div_up(nrows, rows_per_cta), 256, smem, stream>>>(P, T, rows_per_cta);
+    PB_CHECK_LAUNCH(ctx, "k_delay_fft_r8");
+  } else if (pl.pow2) {
     size_t smem = sizeof(double2) * (size_t)pl.nfft;
     PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_delay_fft<<<nrows, FFT_THREADS, smem, stream>>>(P);
