@@ -307,7 +307,9 @@ def main():
             dist.all_reduce(st, op=dist.ReduceOp.MAX)
         e2e = {"value": terms_total / (st[0].item() * 1e-3) / 1e9, "unit": "Gterms/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": st[0].item(),
-               "api": "InterferometerArray.observe + device->host copy of skyvis_freq (pinned)"}
+               "api": "InterferometerArray.observe (precision='auto': fp32 kernel + fp64 recompute of cancelling baselines + "
+                      "sampled fp64 audit) + device->host copy of skyvis_freq (pinned)",
+               "precision_report": ia.precision_report[-1] if ia.precision_report else None}
 
     if rank == 0:
         mb = engine.microbench(local_rank)

@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     const float fs = (float)(P.freqs[ch < P.nslab * PB200_SLAB ? ch : P.nslab * PB200_SLAB - 1] * 1e-8);
     sfreq2[tid] = fs * fs;
   }
+  // taper recurrence constants (uniform grid): F_k = F0 + k dF in units of 1e8 Hz
+  const float tF0 = (float)(fk0 * 1e-8), tdF = (float)(df * 1e-8);
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -286,16 +288,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
         const float p1r = fmaf(-p0.y, r.y, p0.x * r.x), p1i = fmaf(p0.y, r.x, p0.x * r.y);
         const float r2r = fmaf(-r.y, r.y, r.x * r.x), r2i = 2.0f * r.x * r.y;
         float2 PR = make_float2(p0.x, p1r), PI = make_float2(p0.y, p1i);
-        const float2 RR = make_float2(r2r, r2r), RI = make_float2(r2i, r2i), NRI = make_float2(-r2i, -r2i);
+        float2 RR = make_float2(r2r, r2r), RI = make_float2(r2i, r2i);
+        float2 HM1 = make_float2(0.f, 0.f);
+        if (TAPER) {
+          // Gaussian taper w_k = exp2(-kap F_k^2) by recurrence instead of one MUFU per term:
+          //   w_{k+2} = w_k G_k,  G_k = exp2(-kap (4 F_k dF + 4 dF^2)),  G_{k+2} = G_k H,  H = exp2(-8 kap dF^2)
+          // folded into the phasor (q = p w) and the rotation (R_k = r^2 G_k, R_{k+2} = R_k + R_k (H - 1));
+          // H - 1 is carried separately because H rounds to 1 - O(1e-6) in fp32.
+          const float F1 = tF0 + tdF;
+          const float w0 = exp2f(-kap * tF0 * tF0), w1 = exp2f(-kap * F1 * F1);
+          const float c4 = 4.0f * kap * tdF;
+          const float g0 = exp2f(-c4 * (tF0 + tdF)), g1 = exp2f(-c4 * (F1 + tdF));
+          const float y = -8.0f * kap * tdF * tdF * 0.69314718056f;
+          const float hm1 = fmaf(0.5f * y, y, y);
+          PR.x *= w0; PR.y *= w1; PI.x *= w0; PI.y *= w1;
+          RR = make_float2(r2r * g0, r2r * g1); RI = make_float2(r2i * g0, r2i * g1);
+          HM1 = make_float2(hm1, hm1);
+        }
+        float2 NRI = make_float2(-RI.x, -RI.y);
 #pragma unroll
         for (int k4 = 0; k4 < KT / 4; ++k4) {
           const float4 a4 = arow[k4];
-          float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w);
-          if (TAPER) {
-            const float4 f4 = *reinterpret_cast<const float4*>(&sfreq2[wc * KT + 4 * k4]);
-            A0.x *= exp2f(-kap * f4.x); A0.y *= exp2f(-kap * f4.y);
-            A1.x *= exp2f(-kap * f4.z); A1.y *= exp2f(-kap * f4.w);
-          }
+          const float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w);
           // operand order chosen for the register-reuse cache: every packed instruction reads at
           // most two fresh 64-bit operands (PR / PI / A stay in the same operand slot across
           // consecutive instructions), which keeps FFMA2 at its 2-cycle pipe rate
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
           float2 nr = __ffma2_rn(PI, NRI, t1);
           float2 ni = __ffma2_rn(PI, RR, t2);
           PR = nr; PI = ni;
+          if (TAPER) { RR = __ffma2_rn(RR, HM1, RR); RI = __ffma2_rn(RI, HM1, RI); NRI = make_float2(-RI.x, -RI.y); }
           if (k4 + 1 < KT / 4) {
             t1 = __fmul2_rn(PR, RR); t2 = __fmul2_rn(PR, RI);
           }
@@ -314,6 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
             nr = __ffma2_rn(PI, NRI, t1);
             ni = __ffma2_rn(PI, RR, t2);
             PR = nr; PI = ni;
+            if (TAPER) { RR = __ffma2_rn(RR, HM1, RR); RI = __ffma2_rn(RI, HM1, RI); NRI = make_float2(-RI.x, -RI.y); }
           }
         }
       } else {
@@ -445,7 +461,7 @@ constexpr int BL64 = 32 * WB64;               // 64
 struct __align__(16) TilePre64 {
   double tau[T][BL64];
   double2 rot[T][BL64];
-  float kap[T][BL64];
+  double kap[T][BL64];
 };
 template <typename AMP> struct __align__(16) TileIn64 {
   AMP amp[T][PB200_SLAB];
@@ -472,6 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
   const Geometry G = load_baseline(P, b, valid);
   const double fk0 = P.f0 + (double)kbase * P.df;
   const double df = P.df;
+  const double tF0 = fk0 * 1e-8, tdF = df * 1e-8;
 
   if (tid < PB200_SLAB) {
     const double fs = P.freqs[slab * PB200_SLAB + tid] * 1e-8;
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
       sincospi(2.0 * frac_turns(tau * df), &sn, &cs);
       tpre[stage].tau[s][bcol] = tau;
       tpre[stage].rot[s][bcol] = make_double2(cs, -sn);
-      if (TAPER) tpre[stage].kap[s][bcol] = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
+      if (TAPER) tpre[stage].kap[s][bcol] = g.w * fmax(G.blen2 - tau_g * tau_g, 0.0);
     }
   };
   double acc_re[KT64], acc_im[KT64];
@@ -523,22 +540,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
       sincospi(2.0 * frac_turns(tp.tau[s][bcol] * fk0), &sn, &cs);
       double pr = cs, pi = -sn;
       const double2 r = tp.rot[s][bcol];
+      double rr = r.x, ri = r.y, hm1 = 0.0;
+      if (TAPER) {
+        // w_k = exp2(-kap F_k^2), F_k = F0 + k dF (units of 1e8 Hz), by recurrence: w_{k+1} = w_k g_k,
+        // g_k = exp2(-kap (2 F_k dF + dF^2)), g_{k+1} = g_k h, h = exp2(-2 kap dF^2); folded into the
+        // phasor (q = p w) and the rotation (R_k = r g_k, R_{k+1} = R_k + R_k (h - 1))
+        const double kap = tp.kap[s][bcol];
+        const double w0 = exp2(-kap * tF0 * tF0), g0 = exp2(-kap * tdF * (2.0 * tF0 + tdF));
+        hm1 = expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
+        pr *= w0; pi *= w0; rr *= g0; ri *= g0;
+      }
       const AMP* arow = &ti.amp[s][wc * KT64];
-      double kap = 0.0;
-      if (TAPER) kap = (double)tp.kap[s][bcol];
 #pragma unroll
-      for (int k4 = 0; k4 < KT64 / 4; ++k4) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = 4 * k4 + j;
-          double a = (double)arow[k];
-          if (TAPER) a *= exp2(-kap * sfreq2[wc * KT64 + k]);
-          acc_re[k] = fma(a, pr, acc_re[k]);
-          acc_im[k] = fma(a, pi, acc_im[k]);
-          const double nr = fma(-pi, r.y, pr * r.x);
-          const double ni = fma(pi, r.x, pr * r.y);
-          pr = nr; pi = ni;
-        }
+      for (int k = 0; k < KT64; ++k) {
+        const double a = (double)arow[k];
+        acc_re[k] = fma(a, pr, acc_re[k]);
+        acc_im[k] = fma(a, pi, acc_im[k]);
+        const double nr = fma(-pi, ri, pr * rr);
+        const double ni = fma(pi, rr, pr * ri);
+        pr = nr; pi = ni;
+        if (TAPER) { rr = fma(rr, hm1, rr); ri = fma(ri, hm1, ri); }
       }
     }
     __syncthreads();

@@ -264,11 +264,14 @@ class InterferometerArray(object):
         self.nbl_total = nbl if nbl_total is None else int(nbl_total)
         self.noise_seed = int(noise_seed)
         # 'fp32': fp32 phasors/amplitudes everywhere (fastest); 'fp64': fp64 kernel + fp64 amplitude table;
-        # 'auto': fp32 first, then every baseline whose visibilities are a strongly cancelling sum
-        # (rms_b < cancel_ratio * incoherent norm, where fp32 products cannot hold 1e-5 rms) is
-        # recomputed by the fp64 kernel (DESIGN.md K1 "precision control")
+        # 'auto': fp32 first; every baseline whose visibilities are a strongly cancelling sum
+        # (rms_b < cancel_ratio * incoherent norm) is recomputed by the fp64 kernel, and a sample of the
+        # remaining baselines is audited against fp64 -- if the audit misses the tolerance the whole
+        # snapshot (and the following ones) runs in fp64 (DESIGN.md K1 "precision control")
         self.precision = "auto"
         self.cancel_ratio = 0.45
+        self.audit_baselines = 32                        # un-flagged baselines re-done in fp64 and compared per snapshot
+        self.audit_tolerance = 0.4e-5                    # max |dV|/rms_b on the audited baselines before fp64 takes over
         self.precision_report = []                       # per snapshot: baselines recomputed in fp64
         self._fp64_sticky = False
         self.cache_sky = True                            # keep catalogue arrays resident between snapshots
@@ -563,26 +566,51 @@ class InterferometerArray(object):
         kw = dict(pbeam=pbeam, device=self.device)
         uniform = nchan < 3 or NP.allclose(NP.diff(self.channels), self.freq_resolution, rtol=0, atol=1e-4)
 
-        def run64(bl):
-            amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+        def run64(bl, amp64=None):
+            if amp64 is None:
+                amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
             return engine.skyvis(dircos, amp64, nsrc, bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, method="fp64",
                                  device=self.device)
 
         if uniform and (self.precision == "fp64" or (self.precision == "auto" and self._fp64_sticky)):
-            self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl})
+            self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl, "audited": 0, "audit_max_err": 0.0})
             return run64(self._d_bl)
         amp = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, **kw)
         skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device)
         if self.precision == "auto" and uniform:
-            # incoherent norm sqrt(mean_f sum_s a^2) against the rms of each baseline's spectrum: the fp32
-            # kernel's absolute error is ~1-3.5e-6 of the former (measured), the tolerance 1e-5 of the latter
+            # (1) cancellation test.  The fp32 kernel's absolute error on incoherent (point-source) skies is
+            # ~1-3.5e-6 of the incoherent norm sqrt(mean_f sum_s a^2) (measured), the tolerance 1e-5 of each
+            # baseline's rms: baselines whose spectrum cancels below cancel_ratio x that norm go to fp64.
             a2 = torch.sqrt(amp.double().square().sum() / nchan)
             rms_b = torch.sqrt(skyvis.real.square().mean(dim=1) + skyvis.imag.square().mean(dim=1))
-            flagged = torch.nonzero(rms_b < self.cancel_ratio * a2).flatten()
+            low = rms_b < self.cancel_ratio * a2
+            flagged = torch.nonzero(low).flatten()
             nflag = int(flagged.numel())
-            self.precision_report.append({"fp64_baselines": nflag, "nbl": nbl})
+            amp64 = None
             if nflag > 0:
-                skyvis.index_copy_(0, flagged, run64(self._d_bl.index_select(0, flagged).contiguous()))
+                amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+                skyvis.index_copy_(0, flagged, run64(self._d_bl.index_select(0, flagged).contiguous(), amp64))
+            # (2) sampled fp64 audit.  On coherent skies (smooth diffuse emission: same-sign amplitudes, slowly
+            # varying phases) fp32 partial sums are much larger than the incoherent norm and so is the error;
+            # a few un-flagged baselines (shortest, longest, random) are recomputed in fp64 and compared.
+            audit_err, audited = 0.0, 0
+            keep = torch.nonzero(~low).flatten()
+            if keep.numel() > 0:
+                gen = torch.Generator(device="cpu").manual_seed(20261017 + len(self._skyvis))
+                pick = torch.randperm(int(keep.numel()), generator=gen)[: max(self.audit_baselines - 2, 0)]
+                sel = torch.unique(torch.cat((keep[[0, -1]], keep[pick.to(keep.device)])))
+                if amp64 is None:
+                    amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+                ref = run64(self._d_bl.index_select(0, sel).contiguous(), amp64)
+                got = skyvis.index_select(0, sel)
+                rms_ref = torch.sqrt(ref.real.square().mean(dim=1) + ref.imag.square().mean(dim=1)).clamp_min(1e-300)
+                audit_err = float(((got - ref).abs().amax(dim=1) / rms_ref).max().item())
+                audited = int(sel.numel())
+                skyvis.index_copy_(0, sel, ref)
+                if audit_err > self.audit_tolerance:          # fp32 is not good enough on this sky: everything in fp64
+                    skyvis.index_copy_(0, keep, run64(self._d_bl.index_select(0, keep).contiguous(), amp64))
+                    nflag = nbl
+            self.precision_report.append({"fp64_baselines": nflag, "nbl": nbl, "audited": audited, "audit_max_err": audit_err})
             self._fp64_sticky = nflag > 0.5 * nbl
         return skyvis
 
