@@ -271,7 +271,7 @@ class InterferometerArray(object):
         self.precision = "auto"
         self.cancel_ratio = 0.45
         self.audit_baselines = 32                        # un-flagged baselines re-done in fp64 and compared per snapshot
-        self.audit_tolerance = 0.4e-5                    # max |dV|/rms_b on the audited baselines before fp64 takes over
+        self.audit_tolerance = 0.8e-5                    # max |dV|/rms_b on the audited baselines before fp64 takes over
         self.precision_report = []                       # per snapshot: baselines recomputed in fp64
         self._fp64_sticky = False
         self.cache_sky = True                            # keep catalogue arrays resident between snapshots
