@@ -28,7 +28,7 @@ int pb200_ctx_create(pb200_ctx** out, int device) {
 void pb200_ctx_destroy(pb200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->twiddle) cudaFree(ctx->twiddle);
   delete ctx;

@@ -12,8 +12,8 @@ struct pb200_ctx {
   char err[512];
   long long launches;
   // scratch owned by the ctx (grown on demand, freed in pb200_ctx_destroy)
-  void* scratch[6];
-  size_t scratch_bytes[6];
+  void* scratch[8];
+  size_t scratch_bytes[8];
   // cached twiddle table for the delay transform
   void* twiddle;
   int twiddle_n;

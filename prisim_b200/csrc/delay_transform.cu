@@ -6,11 +6,11 @@
 // Three hand-written kernels (no cuFFT):
 //   k_delay_fft_r8 register-resident radix-8 Stockham inverse FFT (fp64), global -> registers ->
 //                 (smem between passes) -> global with the bp*wts multiply, scale and fftshift
-//                 fused; power-of-two lengths 64..4096 without interpolation.  When 1+pad is an
+//                 fused; power-of-two lengths 64..2048 without interpolation.  When 1+pad is an
 //                 integer m and nchan is even, decimating the m*nchan-point padded transform by m
 //                 is exactly the nchan-point transform, so that one is computed (default pad=1).
 //   k_delay_fft   radix-2 in-smem inverse FFT with linear-interpolated decimation on store: the
-//                 remaining power-of-two cases (non-integer decimation, N < 64, N = 8192).
+//                 remaining power-of-two cases (non-integer decimation, N < 64, N >= 4096).
 //   k_delay_dft   direct evaluation of just the output samples needed (any length, any pad):
 //                 O(nout * nchan) per row, twiddles from an exact integer-indexed table.
 // HBM-bound: algorithmic bytes per row = nchan*(16 + 8 + 8) read + nout*16 written.
@@ -98,9 +98,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_delay_fft(const DelayParams P) 
 // k_delay_fft_r8: register-resident mixed-radix (8,8,...,{8,4,2}) Stockham autosort inverse FFT.
 // The first pass reads global memory directly (fused bp*wts multiply and zero padding), the last
 // pass writes global memory directly (fused scale + fftshift); only the passes in between go
-// through shared memory (ping-pong buffers, one __syncthreads per pass: 3 for N=1024 instead of
-// the 10 of the radix-2 kernel).  One row = N/8 threads; a CTA carries 256/(N/8) rows (>= 1).
-// Used for 64 <= N <= 4096 when no interpolation is needed (factor == 1).
+// through shared memory (one padded row per transform, in place: read, barrier, write, barrier --
+// 5 barriers for N=1024 instead of the 10 of the radix-2 kernel, and half the shared memory of a
+// ping-pong scheme, so 6 CTAs = 12 rows are resident per SM).  One row = N/8 threads; a CTA carries 256/(N/8) rows (>= 1).
+// Used for 64 <= N <= 2048 when no interpolation is needed (factor == 1).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -129,14 +130,59 @@ template <> __device__ __forceinline__ void ifft_small<8>(double2 (&v)[8]) {
   for (int i = 0; i < 4; ++i) { v[2 * i] = a[i]; v[2 * i + 1] = b[i]; }
 }
 
-template <int R>
-__device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, int t, int T, int Ns, bool first, bool last,
-                                              const double2* __restrict__ src, double2* __restrict__ dst) {
+// branch-free loader (all loads of a butterfly in flight together): bp / wts always valid pointers
+// (the host substitutes a broadcast "ones" row), index clamped for the zero-padded tail
+template <bool HAS_X>
+__device__ __forceinline__ double2 load_in_nb(const DelayParams& P, int row, int n) {
+  const int nc = n < P.nchan ? n : P.nchan - 1;
+  const double w = P.bp[(size_t)row * P.bp_stride + nc] * P.wts[(size_t)row * P.wts_stride + nc];
+  double2 v = make_double2(1.0, 0.0);
+  if (HAS_X) v = P.x[(size_t)row * P.nchan + nc];
+  const double m = n < P.nchan ? w : 0.0;
+  return make_double2(v.x * m, v.y * m);
+}
+
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }   // 16 B of padding per 128 B: the stride-8 stores of the first pass hit distinct banks
+
+// One Stockham pass of radix R for the butterflies j = t, t+T, ... of one row.  `first` reads global
+// memory (window multiply, zero padding), `last` writes global memory (scale, fftshift); passes in
+// between work IN PLACE on one padded shared-memory row: all reads, a CTA barrier, then all writes
+// (middle passes are radix 8 with exactly one butterfly per thread, so the inputs sit in registers).
+template <int R, bool HAS_X>
+__device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, bool active, int t, int T, int Ns, bool first,
+                                              bool last, double2* __restrict__ buf) {
   const int N = P.nfft, NR = N / R;
-  for (int j = t; j < NR; j += T) {
-    double2 v[R];
+  if (last) {                                   // smem (or global, single-pass transforms) -> global
+    if (active)
+      for (int j = t; j < NR; j += T) {
+        double2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = first ? load_in(P, row, j + r * NR) : src[j + r * NR];
+        for (int r = 0; r < R; ++r) v[r] = first ? load_in_nb<HAS_X>(P, row, j + r * NR) : buf[padi(j + r * NR)];
+        const int k = j & (Ns - 1);
+        if (Ns > 1) {
+          const int tstep = k * (N / (Ns * R));
+#pragma unroll
+          for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(&P.twiddle[(r * tstep) & (N - 1)]));
+        }
+        ifft_small<R>(v);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          int i = j0 + r * Ns - P.shift; if (i < 0) i += N;                  // fftshift: out[i] = X[(i + shift) % N]
+          P.out[(size_t)row * P.nout + i] = make_double2(v[r].x * P.scale, v[r].y * P.scale);
+        }
+      }
+    return;
+  }
+  // first / middle pass: one butterfly per thread (T == NR)
+  double2 v[R];
+  const int j = t;
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = first ? load_in_nb<HAS_X>(P, row, j + r * NR) : buf[padi(j + r * NR)];
+  }
+  if (!first) __syncthreads();                  // everyone has read this pass's inputs
+  if (active) {
     const int k = j & (Ns - 1);
     if (Ns > 1) {
       const int tstep = k * (N / (Ns * R));
@@ -146,39 +192,28 @@ __device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, int
     ifft_small<R>(v);
     const int j0 = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int o = j0 + r * Ns;
-      if (last) {
-        int i = o - P.shift; if (i < 0) i += N;                            // fftshift: out[i] = X[(i + shift) % N]
-        P.out[(size_t)row * P.nout + i] = make_double2(v[r].x * P.scale, v[r].y * P.scale);
-      } else {
-        dst[o] = v[r];
-      }
-    }
+    for (int r = 0; r < R; ++r) buf[padi(j0 + r * Ns)] = v[r];
   }
+  __syncthreads();                              // outputs visible to the next pass
 }
 
+template <bool HAS_X>
 __global__ void __launch_bounds__(256) k_delay_fft_r8(const DelayParams P, int T, int rows_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.nfft;
   const int lrow = threadIdx.x / T, t = threadIdx.x % T;
   const int row = blockIdx.x * rows_per_cta + lrow;
   const bool active = lrow < rows_per_cta && row < P.nrows;
-  double2* buf0 = reinterpret_cast<double2*>(smem_raw) + (size_t)lrow * 2 * N;
-  double2* buf1 = buf0 + N;
-  int Ns = 1, rem = P.log2n, pass = 0;
+  double2* buf = reinterpret_cast<double2*>(smem_raw) + (size_t)lrow * (N + (N >> 3));
+  int Ns = 1, rem = P.log2n;
+  bool first = true;
   while (rem > 0) {
     const int lr = rem >= 3 ? 3 : rem;                                     // radix 8, then 4 or 2
-    const bool first = pass == 0, last = rem == lr;
-    const double2* src = (pass & 1) ? buf0 : buf1;                         // pass p reads what pass p-1 wrote
-    double2* dst = (pass & 1) ? buf1 : buf0;
-    if (active) {
-      if (lr == 3) stockham_pass<8>(P, row, t, T, Ns, first, last, src, dst);
-      else if (lr == 2) stockham_pass<4>(P, row, t, T, Ns, first, last, src, dst);
-      else stockham_pass<2>(P, row, t, T, Ns, first, last, src, dst);
-    }
-    if (!last) __syncthreads();
-    Ns <<= lr; rem -= lr; ++pass;
+    const bool last = rem == lr;
+    if (lr == 3) stockham_pass<8, HAS_X>(P, row, active, t, T, Ns, first, last, buf);
+    else if (lr == 2) stockham_pass<4, HAS_X>(P, row, active, t, T, Ns, first, last, buf);
+    else stockham_pass<2, HAS_X>(P, row, active, t, T, Ns, first, last, buf);
+    Ns <<= lr; rem -= lr; first = false;
   }
 }
 
@@ -218,6 +253,11 @@ __global__ void __launch_bounds__(FFT_THREADS) k_delay_dft(const DelayParams P) 
     }
     P.out[(size_t)row * P.nout + i] = make_double2(o.x * P.scale, o.y * P.scale);
   }
+}
+
+__global__ void k_fill_ones(double* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1.0;
 }
 
 __global__ void k_twiddle(double2* tw, int n) {
@@ -282,12 +322,27 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
   P.nrows = nrows; P.nchan = nchan; P.nfft = pl.nfft; P.log2n = pl.log2n; P.nout = pl.nout;
   P.shift = (pl.nfft + 1) / 2;
   P.scale = df; P.factor = pl.factor;
-  if (pl.pow2 && pl.factor == 1.0 && pl.nfft >= 64 && pl.nfft <= 4096) {
-    const int T = pl.nfft / 8 < 256 ? pl.nfft / 8 : 256;
+  if (pl.pow2 && pl.factor == 1.0 && pl.nfft >= 64 && pl.nfft <= 2048) {
+    const int T = pl.nfft / 8;                         // one radix-8 butterfly per thread and pass
     const int rows_per_cta = 256 / T;
-    const size_t smem = sizeof(double2) * 2 * (size_t)pl.nfft * rows_per_cta;
-    PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_delay_fft_r8<<<pb_div_up(nrows, rows_per_cta), 256, smem, stream>>>(P, T, rows_per_cta);
+    const size_t smem = sizeof(double2) * (size_t)(pl.nfft + (pl.nfft >> 3)) * rows_per_cta;
+    // bp / wts default to a broadcast row of ones so the loader needs no null checks
+    if (!P.bp || !P.wts) {
+      void* ones;
+      int rc1 = pb_scratch(ctx, 6, sizeof(double) * (size_t)nchan, &ones);
+      if (rc1) return rc1;
+      k_fill_ones<<<pb_div_up(nchan, 256), 256, 0, stream>>>((double*)ones, nchan);
+      PB_CHECK_LAUNCH(ctx, "k_fill_ones");
+      if (!P.bp) { P.bp = (const double*)ones; P.bp_stride = 0; }
+      if (!P.wts) { P.wts = (const double*)ones; P.wts_stride = 0; }
+    }
+    if (P.x) {
+      PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_r8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_delay_fft_r8<true><<<pb_div_up(nrows, rows_per_cta), 256, smem, stream>>>(P, T, rows_per_cta);
+    } else {
+      PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_r8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_delay_fft_r8<false><<<pb_div_up(nrows, rows_per_cta), 256, smem, stream>>>(P, T, rows_per_cta);
+    }
     PB_CHECK_LAUNCH(ctx, "k_delay_fft_r8");
   } else if (pl.pow2) {
     size_t smem = sizeof(double2) * (size_t)pl.nfft;
