@@ -340,3 +340,33 @@ def test_delay_transform_vs_oracle(eng, nchan, pad):
     assert rel_err_per_baseline(kern, refk[:, :, 0]) <= 1e-11
     if pad == 0.0:
         assert NP.allclose(NP.sum(NP.abs(out2) ** 2, axis=1) / (nchan * df ** 2), NP.sum(NP.abs(x) ** 2, axis=1), rtol=1e-10)
+
+
+def test_skyvis_random_shapes_property(eng):
+    """Property test over ragged shapes (hypothesis): any (nsrc, nbl, nchan) -- source counts that are not a
+    multiple of the 32-row tile, baseline counts that leave partially filled CTAs, channel counts that leave
+    partially filled or missing slabs -- matches the oracle, for every kernel variant."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=14, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(nsrc=st.integers(1, 200), nbl=st.integers(1, 150), nchan=st.integers(2, 300), seed=st.integers(0, 10 ** 6),
+           method=st.sampled_from(["auto", "recurrence_scalar", "direct", "fp64"]), spc=st.sampled_from(["1", "2", "4"]))
+    def check(nsrc, nbl, nchan, seed, method, spc):
+        rng = NP.random.default_rng(seed)
+        bl = rng.normal(0, 80.0, (nbl, 3)); bl[:, 2] *= 0.05
+        freqs = 150e6 + (NP.arange(nchan) - nchan // 2) * 97656.25
+        altaz = NP.stack((NP.degrees(NP.arcsin(rng.uniform(0, 1, nsrc))), rng.uniform(0, 360, nsrc)), 1)
+        dense = rng.uniform(0.05, 5.0, (nsrc, nchan))
+        dircos, _ = eng.sky_cull(altaz, "altaz")
+        amp = eng.dense_to_amp_table(torch.as_tensor(dense).cuda(), dtype=torch.float64 if method == "fp64" else torch.float32)
+        amp_used = eng.amp_table_to_dense(amp, nsrc, nchan).double().cpu().numpy()
+        os.environ["PB200_SKYVIS_SPC"] = spc
+        try:
+            V = eng.skyvis(dircos, amp, nsrc, bl, (0.0, 0.0, 1.0), freqs, method=method).cpu().numpy()
+        finally:
+            os.environ.pop("PB200_SKYVIS_SPC", None)
+        Vo = O.skyvis_snapshot(bl, altaz, amp_used, freqs, NP.asarray([90.0, 270.0]))
+        assert V.shape == (nbl, nchan)
+        assert rel_err_per_baseline(V, Vo) <= (1e-11 if method == "fp64" else TOL)
+
+    check()
