@@ -34,7 +34,7 @@ constexpr int WCS = PB200_SLAB / KT;           // channel blocks per slab = 4
 constexpr int NWARPS = 16;
 constexpr int NTHREADS = 32 * NWARPS;          // 512
 constexpr int T = PB200_SRC_TILE;              // sources per tile
-constexpr int FLUSH_TILES = 32;                // fp32 -> fp64 flush cadence (1024 sources)
+constexpr int FLUSH_TILES = 16;                // fp32 -> fp64 flush cadence (512 sources); measured max error at C2 / speed: 6.3e-6 / 4.42 @32, 5.5e-6 @16, 4.7e-6 / 4.29 @8
 constexpr int NSTAGE = 2;
 // CTA shape: SPC slabs (SPC*128 channels) x WB baseline groups, SPC*WCS*WB = 16 warps.  A wider
 // channel extent shares each (source, baseline) delay/rotation among more warps (less per-tile
