@@ -76,6 +76,8 @@ int pb200_sky_cull(pb200_ctx* ctx, const double* d_skypos, int nsrc0, int coords
 #define PB200_BEAM_GAUSSIAN 2   /* shape 'gaussian' (:374-377) */
 #define PB200_BEAM_DIPOLE   3   /* 'mwa_dipole'/'paper' presets (:320-349), shape 'dipole' (:360-368) */
 #define PB200_BEAM_TABLE    4   /* caller-supplied pbeam[nsrc,nchan] (roi_info['pbeam'], interferometry.py:6189-6202) */
+#define PB200_BEAM_LOGTABLE 5   /* d_pbeam holds log10 beam[nsrc,nchan] from pb200_healpix_beam; pb = 10^(log - d_logmax[f])
+                                   (scripts/run_prisim.py:1904-1908) */
 
 #define PB200_ARRAY_NONE     0
 #define PB200_ARRAY_ANALYTIC 1  /* isotropic_radiators_array_field_pattern, 'mwa' preset without pointing_info (:273-285) */
@@ -108,6 +110,7 @@ typedef struct pb200_beam_desc {
   const double* d_element_locs;   /* [n_elements,3] metres ENU */
   const double* d_delays;         /* seconds */
   const double* d_gains;
+  const double* d_logmax;         /* [nchan] per-channel normalisation for PB200_BEAM_LOGTABLE (device) */
 } pb200_beam_desc;
 
 /* power-law spectrum (astroutils SkyModel 'func'/'power-law', parameters as built at
@@ -194,6 +197,19 @@ int pb200_delay_nout(int nchan, double pad, int downsample);
 int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, long long bp_row_stride,
                           const double* d_wts, long long wts_row_stride, int nrows, int nchan, double df,
                           double pad, int downsample, void* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gridded (HEALPix, RING) primary beam.  Replaces the external-beam step of scripts/run_prisim.py:1897-1908
+ * (OPS.healpix_interp_along_axis = healpy bilinear interpolation at (theta, phi) = (pi/2 - alt, az) + spectral
+ * interpolation, then renormalisation by the per-channel maximum over the ROI).  The two interpolations are
+ * linear and commute: d_map is the log10 power beam ALREADY resampled to the observing channels,
+ * [npix = 12 nside^2][nchan] (channel fastest), fp32 or fp64 (map_dtype = PB200_AMP_F32/F64).
+ *   d_dircos [nsrc,3] culled ENU direction cosines (beam frame: pole = zenith, phi = azimuth)
+ *   outputs: d_logbeam [nsrc,nchan] fp64 interpolated log10 beam; d_colmax [nchan] = max(0, max_s logbeam)
+ * Feed both to pb200_amp_table with element PB200_BEAM_LOGTABLE (d_pbeam = d_logbeam, d_logmax = d_colmax).
+ */
+int pb200_healpix_beam(pb200_ctx* ctx, const void* d_map, int map_dtype, int nside, const double* d_dircos, int nsrc,
+                       int nchan, double* d_logbeam, double* d_colmax, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Re-phasing to a new phase centre.  Replaces the elementwise product of

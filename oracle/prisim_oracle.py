@@ -746,3 +746,101 @@ def project_baselines(baselines, ha_deg, dec_deg, latitude):
                              [-NP.sin(dec) * NP.cos(ha), NP.sin(dec) * NP.sin(ha), NP.cos(dec)],
                              [NP.cos(dec) * NP.cos(ha), -NP.cos(dec) * NP.sin(ha), NP.sin(dec)]])
     return NP.dot(eq_baselines, rot_matrix)
+
+
+# --------------------------------------------------------------------------------------------
+# External HEALPix beam (scripts/run_prisim.py:1897-1908); healpy / astroutils restated [AU-memory]
+# --------------------------------------------------------------------------------------------
+def _hp_ring_info(ring, nside):
+    """HEALPix RING scheme: (startpix, ringpix, theta, shifted) of ring index 1..4nside-1 (arrays)."""
+    ring = NP.asarray(ring, dtype=NP.int64)
+    npix, ncap = 12 * nside * nside, 2 * nside * (nside - 1)
+    fact2 = 4.0 / npix
+    fact1 = 2.0 * nside * fact2
+    northring = NP.where(ring > 2 * nside, 4 * nside - ring, ring)
+    cap = northring < nside
+    tmp = northring.astype(NP.float64) ** 2 * fact2
+    theta = NP.where(cap, NP.arctan2(NP.sqrt(NP.clip(tmp * (2.0 - tmp), 0, None)), 1.0 - tmp),
+                     NP.arccos(NP.clip((2.0 * nside - northring) * fact1, -1.0, 1.0)))
+    ringpix = NP.where(cap, 4 * northring, 4 * nside)
+    shifted = NP.where(cap, True, ((northring - nside) & 1) == 0)
+    startpix = NP.where(cap, 2 * northring * (northring - 1), ncap + (northring - nside) * ringpix)
+    south = northring != ring
+    theta = NP.where(south, NP.pi - theta, theta)
+    startpix = NP.where(south, npix - startpix - ringpix, startpix)
+    return startpix, ringpix, theta, shifted
+
+
+def healpix_interp_weights(nside, theta, phi):
+    """healpy.get_interp_weights(nside, theta, phi) for the RING scheme [AU-memory of healpy/HEALPix C++
+    get_interpol]: the two neighbours in each of the two rings bracketing theta.  Returns (pix [4,n], wgt [4,n])."""
+    theta = NP.asarray(theta, dtype=NP.float64).ravel()
+    phi = NP.asarray(phi, dtype=NP.float64).ravel() % (2 * NP.pi)
+    npix = 12 * nside * nside
+    z = NP.cos(theta)
+    az = NP.abs(z)
+    ir1 = NP.where(az <= 2.0 / 3.0, (nside * (2.0 - 1.5 * z)).astype(NP.int64),
+                   NP.where(z > 0, (nside * NP.sqrt(3.0 * (1.0 - az))).astype(NP.int64),
+                            4 * nside - (nside * NP.sqrt(3.0 * (1.0 - az))).astype(NP.int64) - 1))
+    ir2 = ir1 + 1
+    pix = NP.zeros((4, theta.size), dtype=NP.int64)
+    wgt = NP.zeros((4, theta.size))
+    thetas = []
+    for k, ir in enumerate((ir1, ir2)):
+        valid = (ir > 0) & (ir < 4 * nside)
+        sp, nr, th, sh = _hp_ring_info(NP.where(valid, ir, 1), nside)
+        dphi = 2 * NP.pi / nr
+        shf = NP.where(sh, 0.5, 0.0)
+        tmp = phi / dphi - shf
+        i1 = NP.where(tmp < 0, tmp.astype(NP.int64) - 1, tmp.astype(NP.int64))
+        w1 = (phi - (i1 + shf) * dphi) / dphi
+        i2 = i1 + 1
+        i1 = NP.where(i1 < 0, i1 + nr, i1)
+        i2 = NP.where(i2 >= nr, i2 - nr, i2)
+        pix[2 * k], pix[2 * k + 1] = NP.where(valid, sp + i1, 0), NP.where(valid, sp + i2, 0)
+        wgt[2 * k], wgt[2 * k + 1] = NP.where(valid, 1.0 - w1, 0.0), NP.where(valid, w1, 0.0)
+        thetas.append(NP.where(valid, th, 0.0))
+    theta1, theta2 = thetas
+    north, south = ir1 == 0, ir2 == 4 * nside
+    mid = ~(north | south)
+    wt = NP.where(mid, (theta - theta1) / NP.where(mid, theta2 - theta1, 1.0), 0.0)
+    wgt[0] = NP.where(mid, wgt[0] * (1 - wt), wgt[0]); wgt[1] = NP.where(mid, wgt[1] * (1 - wt), wgt[1])
+    wgt[2] = NP.where(mid, wgt[2] * wt, wgt[2]); wgt[3] = NP.where(mid, wgt[3] * wt, wgt[3])
+    wtn = NP.where(north, theta / NP.where(north, theta2, 1.0), 0.0)
+    fac = (1.0 - wtn) * 0.25
+    wgt[2] = NP.where(north, wgt[2] * wtn + fac, wgt[2]); wgt[3] = NP.where(north, wgt[3] * wtn + fac, wgt[3])
+    wgt[0] = NP.where(north, fac, wgt[0]); wgt[1] = NP.where(north, fac, wgt[1])
+    pix[0] = NP.where(north, (pix[2] + 2) & 3, pix[0]); pix[1] = NP.where(north, (pix[3] + 2) & 3, pix[1])
+    wts = NP.where(south, (theta - theta1) / NP.where(south, NP.pi - theta1, 1.0), 0.0)
+    facs = wts * 0.25
+    wgt[0] = NP.where(south, wgt[0] * (1 - wts) + facs, wgt[0]); wgt[1] = NP.where(south, wgt[1] * (1 - wts) + facs, wgt[1])
+    wgt[2] = NP.where(south, facs, wgt[2]); wgt[3] = NP.where(south, facs, wgt[3])
+    pix[2] = NP.where(south, ((pix[0] + 2) & 3) + npix - 4, pix[2]); pix[3] = NP.where(south, ((pix[1] + 2) & 3) + npix - 4, pix[3])
+    return pix, wgt
+
+
+def healpix_interp_along_axis(indata, theta_phi, inloc_axis, outloc_axis, kind="linear"):
+    """OPS.healpix_interp_along_axis [AU-memory] (run_prisim.py:1900): healpy.get_interp_val of every column of
+    indata [npix, nin] at (theta, phi), then scipy interp1d along the column axis from inloc_axis to outloc_axis."""
+    indata = NP.asarray(indata, dtype=NP.float64)
+    nside = int(round(NP.sqrt(indata.shape[0] / 12.0)))
+    pix, wgt = healpix_interp_weights(nside, theta_phi[:, 0], theta_phi[:, 1])
+    spatial = NP.einsum("kn,knf->nf", wgt, indata[pix])
+    inloc, outloc = NP.asarray(inloc_axis, dtype=NP.float64), NP.asarray(outloc_axis, dtype=NP.float64)
+    if inloc.size == outloc.size and NP.allclose(inloc, outloc):
+        return spatial
+    return interpolate.interp1d(inloc, spatial, axis=1, kind=kind, bounds_error=False, fill_value="extrapolate")(outloc)
+
+
+def external_beam_table(external_beam, beam_freqs, src_altaz_deg, chans_hz, chromatic=True, select_freq=None, kind="cubic"):
+    """scripts/run_prisim.py:1897-1908: power beam [nsrc, nchan] from a HEALPix (RING) map [npix, nfreq_b]."""
+    theta_phi = NP.hstack((NP.pi / 2 - NP.radians(src_altaz_deg[:, 0]).reshape(-1, 1), NP.radians(src_altaz_deg[:, 1]).reshape(-1, 1)))
+    if chromatic:
+        interp_logbeam = healpix_interp_along_axis(NP.log10(external_beam), theta_phi, beam_freqs, chans_hz, kind=kind)
+    else:
+        nearest = NP.argmin(NP.abs(NP.asarray(beam_freqs) - select_freq))
+        interp_logbeam = healpix_interp_along_axis(NP.log10(NP.repeat(external_beam[:, nearest].reshape(-1, 1), len(chans_hz), axis=1)),
+                                                   theta_phi, chans_hz, chans_hz)
+    mx = NP.nanmax(interp_logbeam, axis=0)
+    mx[mx <= 0.0] = 0.0
+    return 10 ** (interp_logbeam - mx.reshape(1, -1))

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libprisim_b200.so")
 
 PB200_OK = 0
 SKY_ALTAZ, SKY_HADEC, SKY_DIRCOS = 0, 1, 2
-BEAM_DELTA, BEAM_AIRY, BEAM_GAUSSIAN, BEAM_DIPOLE, BEAM_TABLE = 0, 1, 2, 3, 4
+BEAM_DELTA, BEAM_AIRY, BEAM_GAUSSIAN, BEAM_DIPOLE, BEAM_TABLE, BEAM_LOGTABLE = 0, 1, 2, 3, 4, 5
 ARRAY_NONE, ARRAY_ANALYTIC, ARRAY_ELEMENTS = 0, 1, 2
 DIPOLE_GENERAL, DIPOLE_SHORT, DIPOLE_HALFWAVE = 0, 1, 2
 SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR, SKYVIS_FP64 = 0, 1, 2, 3, 4
@@ -33,7 +33,7 @@ class BeamDesc(C.Structure):
         ("sep1", C.c_double), ("sep2", C.c_double), ("east2ax1_deg", C.c_double),
         ("array_pointing", C.c_double * 3),
         ("n_elements", C.c_int32), ("nrand", C.c_int32),
-        ("d_element_locs", C.c_void_p), ("d_delays", C.c_void_p), ("d_gains", C.c_void_p),
+        ("d_element_locs", C.c_void_p), ("d_delays", C.c_void_p), ("d_gains", C.c_void_p), ("d_logmax", C.c_void_p),
     ]
 
 
@@ -60,6 +60,7 @@ SYMBOLS = {
     "pb200_delay_nout": (_i, [_i, _d, _i]),
     "pb200_delay_transform": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp]),
     "pb200_phase_rotate": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "pb200_healpix_beam": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "pb200_microbench": (_i, [_vp, C.POINTER(_d), _i]),
 }
 

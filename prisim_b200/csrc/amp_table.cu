@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(AMP_THREADS) k_amp_table(const AmpParams P) {
       double pb;
       if (B.element == PB200_BEAM_TABLE) {
         pb = P.pbeam[(size_t)s * P.nchan + f];
+      } else if (B.element == PB200_BEAM_LOGTABLE) {
+        pb = exp10(P.pbeam[(size_t)s * P.nchan + f] - B.d_logmax[f]);        // run_prisim.py:1906-1908
       } else {
         double ep = 1.0;                                            // delta (:355-359)
         if (B.element == PB200_BEAM_AIRY) {
@@ -201,10 +203,12 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
   if (nsrc > 0 && !d_dircos) return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: null d_dircos");
   if (amp_dtype != PB200_AMP_F32 && amp_dtype != PB200_AMP_F64)
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: amp_dtype must be PB200_AMP_F32 or PB200_AMP_F64");
-  if (beam->element < PB200_BEAM_DELTA || beam->element > PB200_BEAM_TABLE)
+  if (beam->element < PB200_BEAM_DELTA || beam->element > PB200_BEAM_LOGTABLE)
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: unknown beam element type");
-  if (beam->element == PB200_BEAM_TABLE && !d_pbeam)
-    return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: PB200_BEAM_TABLE needs d_pbeam");
+  if ((beam->element == PB200_BEAM_TABLE || beam->element == PB200_BEAM_LOGTABLE) && !d_pbeam)
+    return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: PB200_BEAM_TABLE / LOGTABLE need d_pbeam");
+  if (beam->element == PB200_BEAM_LOGTABLE && !beam->d_logmax)
+    return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: PB200_BEAM_LOGTABLE needs d_logmax");
   if (beam->array_mode == PB200_ARRAY_ELEMENTS &&
       (beam->n_elements <= 0 || beam->nrand <= 0 || !beam->d_element_locs || !beam->d_delays))
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: element array needs locations, delays, nrand >= 1");

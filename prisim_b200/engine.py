@@ -72,7 +72,7 @@ def make_beam_desc(**kw):
     b.array_pointing = (C.c_double * 3)(*[float(v) for v in kw.get("array_pointing", (0.0, 0.0, 1.0))])
     b.n_elements = int(kw.get("n_elements", 0)); b.nrand = int(kw.get("nrand", 1))
     keep = []
-    for name in ("d_element_locs", "d_delays", "d_gains"):
+    for name in ("d_element_locs", "d_delays", "d_gains", "d_logmax"):
         t = kw.get(name, None)
         keep.append(t)
         setattr(b, name, None if t is None else t.data_ptr())
@@ -217,6 +217,20 @@ def delay_transform(x, bp, wts, df, pad=1.0, downsample=True, nrows=None, nchan=
                                             int(nrows), int(nchan), float(df), float(pad), int(bool(downsample)),
                                             _ptr(out), ctx.stream()))
     return out
+
+
+def healpix_beam(map_dev, nside, dircos, nsrc, nchan):
+    """``pb200_healpix_beam``: bilinear HEALPix interpolation of a log10 beam map [npix, nchan] (fp32/fp64 CUDA
+    tensor, already on the observing channels) at the culled directions.  Returns (logbeam [nsrc,nchan] f64,
+    colmax [nchan] f64).  Replaces scripts/run_prisim.py:1897-1905."""
+    device = map_dev.device.index
+    ctx = get_context(device)
+    logbeam = torch.empty((max(nsrc, 1), nchan), dtype=torch.float64, device=map_dev.device)
+    colmax = torch.empty((nchan,), dtype=torch.float64, device=map_dev.device)
+    dt = _lib.AMP_F64 if map_dev.dtype == torch.float64 else _lib.AMP_F32
+    ctx.check(ctx.lib.pb200_healpix_beam(ctx.handle, _ptr(map_dev), dt, int(nside), _ptr(dircos), int(nsrc), int(nchan),
+                                         _ptr(logbeam), _ptr(colmax), ctx.stream()))
+    return logbeam[:nsrc], colmax
 
 
 def phase_rotate(vis, baselines_dev, dpos_dircos, freqs_hz):

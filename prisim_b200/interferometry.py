@@ -531,6 +531,13 @@ class InterferometerArray(object):
         if nsrc > 0:
             if pbeam is not None:
                 beam = engine.make_beam_desc(element=engine._lib.BEAM_TABLE)
+            elif isinstance(pb_info, dict) and pb_info.get("external_beam", None) is not None:
+                # gridded HEALPix beam gathered on the device (the run_prisim external-beam step, :1897-1908)
+                hb = pb_info["external_beam"]
+                if hb.nchan != nchan:
+                    raise ValueError("external beam was prepared for a different number of channels")
+                pbeam, logmax = hb.table(dircos, nsrc)
+                beam = engine.make_beam_desc(element=engine._lib.BEAM_LOGTABLE, d_logmax=logmax)
             else:                                                                      # :6251-6252
                 beam = PB.beam_desc_from_telescope(self.telescope, pointing_info=pb_info, pointing_center=pc_altaz,
                                                    skyunits="altaz", device=self.device)

@@ -172,6 +172,55 @@ def beam_desc_from_telescope(telescope, pointing_info=None, pointing_center=None
     return engine.make_beam_desc(**kw)
 
 
+class HealpixBeam(object):
+    """External gridded beam (HEALPix RING map) prepared for the device gather ``pb200_healpix_beam``.
+
+    The reference (scripts/run_prisim.py:482-524, :1897-1908) interpolates log10(external_beam [npix, nfreq_b])
+    bilinearly on the sphere at every source and then along frequency onto the observing channels, per snapshot.
+    Both interpolations are linear in the map, so here the map is resampled to the channels ONCE (this constructor,
+    scipy interp1d of kind `spec_interp`; `chromatic=False` takes the map nearest to `select_freq` for all channels,
+    :1902-1903) and stored on the GPU as [npix, nchan]; per snapshot the device only gathers."""
+
+    def __init__(self, external_beam, beam_freqs_hz, channels_hz, chromatic=True, select_freq=None, spec_interp="cubic",
+                 dtype=torch.float32, device=None):
+        from scipy import interpolate
+        external_beam = NP.asarray(external_beam, dtype=NP.float64)
+        if external_beam.ndim != 2:
+            raise ValueError("external_beam must be [npix, nfreq]")
+        npix = external_beam.shape[0]
+        nside = int(round(NP.sqrt(npix / 12.0)))
+        if 12 * nside * nside != npix or nside & (nside - 1):
+            raise ValueError("external_beam must be a HEALPix map with nside a power of two")
+        beam_freqs_hz = NP.asarray(beam_freqs_hz, dtype=NP.float64).ravel()
+        channels_hz = NP.asarray(channels_hz, dtype=NP.float64).ravel()
+        if spec_interp == "fft":
+            raise NotImplementedError("'fft' spectral interpolation of external beams is not supported; use 'cubic' or 'linear'")
+        with NP.errstate(divide="ignore"):
+            logbeam = NP.log10(external_beam)
+        if chromatic:
+            if beam_freqs_hz.size != external_beam.shape[1]:
+                raise ValueError("beam_freqs_hz must match the second axis of external_beam")
+            logmap = interpolate.interp1d(beam_freqs_hz, logbeam, axis=1, kind=spec_interp, bounds_error=False,
+                                          fill_value="extrapolate")(channels_hz)
+        else:
+            nearest = int(NP.argmin(NP.abs(beam_freqs_hz - (channels_hz[channels_hz.size // 2] if select_freq is None else select_freq))))
+            logmap = NP.repeat(logbeam[:, nearest].reshape(-1, 1), channels_hz.size, axis=1)
+        self.nside, self.nchan = nside, channels_hz.size
+        self.device = engine._dev(device)
+        self.map = torch.as_tensor(NP.ascontiguousarray(logmap)).to(device="cuda:{0}".format(self.device), dtype=dtype).contiguous()
+
+    def table(self, dircos, nsrc):
+        """(log10 beam [nsrc, nchan], per-channel max(0, max)) at culled ENU direction cosines (device tensors)."""
+        return engine.healpix_beam(self.map, self.nside, dircos, nsrc, self.nchan)
+
+    def pbeam(self, skypos_altaz_deg):
+        """Power beam [nsrc, nchan] as numpy -- what run_prisim puts in roi_info['pbeam'] (:1908)."""
+        altaz = NP.asarray(skypos_altaz_deg, dtype=NP.float64).reshape(-1, 2)
+        dircos, _ = engine.sky_cull(altaz, "altaz", roi_radius_deg=180.0, device=self.device)
+        logbeam, colmax = self.table(dircos, altaz.shape[0])
+        return torch.pow(10.0, logbeam - colmax.unsqueeze(0)).cpu().numpy()
+
+
 def primary_beam_generator(skypos, frequency, telescope, freq_scale="GHz", skyunits="degrees", east2ax1=0.0,
                            pointing_info=None, pointing_center=None, short_dipole_approx=False,
                            half_wave_dipole_approx=False, device=None):

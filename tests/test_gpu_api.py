@@ -362,3 +362,45 @@ def test_config5_pipeline_three_snapshots():
     lag_power = L["skyvis"][0][b].abs().pow(2).cpu().numpy()
     inside = NP.abs(ia.lags) <= blen / 299792458.0 + 4.0 / (1024 * df)
     assert lag_power[inside].sum() > 0.999 * lag_power.sum()
+
+
+def test_gridded_healpix_beam_vs_oracle():
+    """External HEALPix beam gathered on the device (scripts/run_prisim.py:1897-1908) through observe and through
+    HealpixBeam.pbeam; config 3's 'Airy sampled on a HEALPix grid' beam variant at nside 32."""
+    from prisim_b200 import synthetic as S
+    from prisim_b200 import primary_beams as PB
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    nside = 32
+    ra, dec = S.healpix_ring_centers(nside)                            # beam frame: pole = zenith, longitude = azimuth
+    pix_altaz = NP.stack((dec, ra), 1)
+    bf = NP.linspace(140e6, 160e6, 6)
+    up = pix_altaz[:, 0] > 0
+    beam = NP.full((ra.size, bf.size), 1e-7)
+    beam[up] = NP.maximum(O.airy_disk_pattern(14.0, pix_altaz[up], bf, power=True), 1e-7)
+    cfg = S.config1(nsrc=1500, nchan=96, nsnap=1)
+    chans = cfg["channels"]
+    rng = NP.random.default_rng(5)
+    altaz = NP.stack((rng.uniform(0.0, 90.0, 300), rng.uniform(0, 360, 300)), 1)
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 3e-6)):
+        hb = PB.HealpixBeam(beam, bf, chans, spec_interp="cubic", dtype=dtype, device=0)
+        ref = O.external_beam_table(beam, bf, altaz, chans, kind="cubic")
+        assert NP.abs(hb.pbeam(altaz) - ref).max() <= tol
+    hb_a = PB.HealpixBeam(beam, bf, chans, chromatic=False, select_freq=151e6, dtype=torch.float64, device=0)
+    assert NP.abs(hb_a.pbeam(altaz) - O.external_beam_table(beam, bf, altaz, chans, chromatic=False, select_freq=151e6)).max() <= 1e-11
+    # through observe: same visibilities as the reference's route (beam table handed over in roi_info)
+    hb = PB.HealpixBeam(beam, bf, chans, spec_interp="cubic", dtype=torch.float32, device=0)
+    ia = InterferometerArray(cfg["labels"], cfg["baselines"], chans, telescope=cfg["telescope"], latitude=cfg["latitude"],
+                             skycoords="radec", pointing_coords="hadec", device=0)
+    ia.observe(SimpleTime(2451545.0, 33.0), {"Tnet": 200.0}, NP.ones(96), cfg["pointing_hadec"], cfg["skymodel"], cfg["t_acc"],
+               pb_info={"external_beam": hb})
+    sky = cfg["skymodel"]; sp = sky.spec_parms
+    hadec = NP.stack((33.0 - sky.location[:, 0], sky.location[:, 1]), 1)
+    src_altaz = O.hadec2altaz(hadec, cfg["latitude"])
+    m2 = O.roi_select(src_altaz)
+    pbeam = O.external_beam_table(beam, bf, src_altaz[m2], chans, kind="cubic")
+    Vo, _ = O.observe_snapshot(cfg["baselines"], chans, hadec, "hadec", cfg["latitude"], cfg["pointing_hadec"], "hadec", cfg["telescope"],
+                               sp["flux-scale"], sp["power-law-index"], sp["freq-ref"], roi_info={"ind": m2, "pbeam": pbeam})
+    assert NP.array_equal(ia.obs_catalog_indices[0], m2)
+    assert rel_err(ia.skyvis_freq[:, :, 0], Vo) <= TOL
+    with pytest.raises(ValueError):
+        PB.HealpixBeam(beam[:-1], bf, chans)

@@ -34,7 +34,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     from prisim_b200 import _lib
     # pb200_beam_desc: 4 int32 + 11 doubles(+3+3 arrays) ... computed from the C declaration order
-    assert ctypes.sizeof(_lib.BeamDesc) == 4 * 4 + 8 * (1 + 3 + 3 + 4) + 2 * 4 + 8 * 3 + 8 * 3 + 2 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.BeamDesc) == 4 * 4 + 8 * (1 + 3 + 3 + 4) + 2 * 4 + 8 * 3 + 8 * 3 + 2 * 4 + 4 * 8
     assert ctypes.sizeof(_lib.SpectrumDesc) == 5 * 8
 
 

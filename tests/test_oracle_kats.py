@@ -204,3 +204,40 @@ def test_taper_limits():
     u = blen / (FCNST.c / f[0])
     d = 2 * NP.sin(NP.radians(fwhm) / 2)
     assert NP.allclose(w[0, :, 0], NP.exp(-NP.log(2) * (u * d) ** 2))     # half power at u d = 1
+
+
+def test_healpix_interpolation_kats():
+    """The RING-scheme bilinear interpolation restated for the external-beam path (run_prisim.py:1897-1908)."""
+    from prisim_b200.synthetic import healpix_ring_centers
+    for nside in (1, 2, 8, 32):
+        npix = 12 * nside * nside
+        ra, dec = healpix_ring_centers(nside)
+        theta_c, phi_c = NP.radians(90.0 - dec), NP.radians(ra)
+        rng = NP.random.default_rng(nside)
+        theta, phi = NP.arccos(rng.uniform(-1, 1, 4000)), rng.uniform(0, 2 * NP.pi, 4000)
+        pix, wgt = O.healpix_interp_weights(nside, theta, phi)
+        assert pix.min() >= 0 and pix.max() < npix
+        assert NP.allclose(wgt.sum(axis=0), 1.0) and wgt.min() >= -1e-12
+        # at a pixel centre the interpolation returns that pixel
+        pc, wc = O.healpix_interp_weights(nside, theta_c, phi_c)
+        val = NP.arange(npix, dtype=float)
+        assert NP.allclose(NP.sum(wc * val[pc], axis=0), val, atol=1e-9 * npix)
+        # a smooth function is reproduced to O(pixel size^2)
+        fmap = NP.cos(theta_c) + 0.3 * NP.sin(theta_c) * NP.cos(phi_c)
+        got = NP.sum(wgt * fmap[pix], axis=0)
+        assert NP.abs(got - (NP.cos(theta) + 0.3 * NP.sin(theta) * NP.cos(phi))).max() < 1.5 / nside ** 2 + (0.5 if nside == 1 else 0)
+    # the two interpolations commute (what the device path relies on)
+    nside = 8
+    ra, dec = healpix_ring_centers(nside)
+    bf = NP.linspace(100e6, 200e6, 6)
+    beam = NP.exp(-((90.0 - dec[:, None]) / (40.0 * 150e6 / bf[None, :])) ** 2) + 1e-4
+    altaz = NP.stack((rng.uniform(0, 90, 50), rng.uniform(0, 360, 50)), 1)
+    chans = NP.linspace(110e6, 190e6, 9)
+    t1 = O.external_beam_table(beam, bf, altaz, chans, kind="cubic")
+    from scipy import interpolate
+    logmap = interpolate.interp1d(bf, NP.log10(beam), axis=1, kind="cubic")(chans)
+    tp = NP.stack((NP.radians(90.0 - altaz[:, 0]), NP.radians(altaz[:, 1])), 1)
+    lb = O.healpix_interp_along_axis(logmap, tp, chans, chans)
+    mx = NP.clip(lb.max(axis=0), 0, None)
+    assert NP.allclose(t1, 10 ** (lb - mx), rtol=1e-12)
+    assert t1.max() <= 1.0 + 1e-12
