@@ -331,6 +331,8 @@ def main():
             cores = min(host_cores(), 64)
             rate, dt, tterms = cpu_sample(cfg, 8000, max(cores * 32, 64), cores)
             cpu = {"value": rate / 1e9, "unit": "Gterms/s", "cores": cores, "kind": "port", "seconds": dt,
+                   "mterms_per_s_per_core": rate / 1e6 / cores,
+                   "extrapolated_full_config_seconds": terms_local / rate,
                    "sample": "8000 above-horizon sources x {0} baselines x 1024 channels ({1:.2e} terms) of the same workload, "
                              "float64 numpy restatement of interferometry.py:6332-6340, {2} processes".format(max(cores * 32, 64), tterms, cores)}
         line = {"metric": METRIC, "value": value, "unit": "Gterms/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
