@@ -212,8 +212,11 @@ def main():
     d_bl = engine._f64(cfg["baselines"], local_rank)
     pc_dircos = NP.asarray([0.0, 0.0, 1.0])
     beam = PB.beam_desc_from_telescope(cfg["telescope"], pointing_center=NP.asarray([90.0, 270.0]), skyunits="altaz", device=local_rank)
-    vis = torch.empty((nbl, nchan), dtype=torch.complex128, device=dev)
-    gathered = torch.empty((world, nbl, nchan), dtype=torch.complex128, device=dev) if (world > 1 and rank == 0) else None
+    # multi-GPU: the phase-sum kernel's epilogue stores each rank's snapshot straight into rank 0's buffer over
+    # NVLink peer memory (sharding.PeerGatherBuffer); NCCL point-to-point is the fallback if mapping fails
+    from prisim_b200.sharding import PeerGatherBuffer
+    gbuf = PeerGatherBuffer((nbl, nchan), local_rank, dst=0) if world > 1 else None
+    vis = gbuf.local if gbuf is not None else torch.empty((nbl, nchan), dtype=torch.complex128, device=dev)
     k1_events = []
 
     def step(timed):
@@ -226,14 +229,8 @@ def main():
         e1.record()
         if timed:
             k1_events.append((e0, e1))
-        if world > 1:                                     # the single gather of the path (to the writing rank)
-            if rank == 0:
-                gathered[0].copy_(vis)
-                ops = [dist.P2POp(dist.irecv, gathered[r], r) for r in range(1, world)]
-            else:
-                ops = [dist.P2POp(dist.isend, vis, 0)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        if gbuf is not None:                              # the single gather of the path (to the writing rank)
+            gbuf.wait()
         return nsrc
 
     def fence():
@@ -339,7 +336,9 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "nsrc_catalogue": args.nsrc, "nsrc_above_horizon": nsrc, "nbl": nbl, "nchan": nchan,
-                           "terms_per_step_per_gpu": terms_local, "sharding": "one snapshot per GPU, gather to rank 0",
+                           "terms_per_step_per_gpu": terms_local, "sharding": "one snapshot per GPU, results land in rank 0's buffer ({0})".format(
+                               "single GPU" if gbuf is None else ("kernel epilogue stores over NVLink peer memory" if gbuf.mode == "peer"
+                                                                  else "NCCL point-to-point gather")),
                            "l2": "inputs larger than L2: amplitude table {0:.2f} GB + 1.0 GB output per step".format(nsrc * nchan * 4 / 1e9),
                            "phase_arith": "fp64 anchors, fp32 rotation recurrence, fp32 accumulate flushed to fp64"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
@@ -348,6 +347,7 @@ def main():
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:
+        gbuf.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -222,6 +222,19 @@ int pb200_phase_rotate(pb200_ctx* ctx, void* d_vis, const double* d_bl, int nbl,
                        const double* h_freqs, int nchan, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU gather through peer memory.  Replaces the exchange through _part_N.hdf5 files and the rank-0
+ * concatenation of scripts/run_prisim.py:1995, :2233-2276.  The writing rank allocates the full output buffer
+ * (pb200_device_alloc) and exports it (pb200_peer_export, 64-byte CUDA IPC handle); every other rank maps it
+ * (pb200_peer_open; peer access over NVLink is enabled lazily) and passes its slice as d_vis to pb200_skyvis, whose
+ * epilogue then stores the finished visibilities directly into the writing rank's HBM -- no separate collective.
+ */
+int pb200_device_alloc(pb200_ctx* ctx, size_t bytes, void** d_out);
+int pb200_device_free(pb200_ctx* ctx, void* d_ptr);
+int pb200_peer_export(pb200_ctx* ctx, void* d_ptr, void* h_handle64);
+int pb200_peer_open(pb200_ctx* ctx, const void* h_handle64, void** d_out);
+int pb200_peer_close(pb200_ctx* ctx, void* d_ptr);
+
+/* ---------------------------------------------------------------------------------------------
  * Issue-rate microbenchmark (FP32 FMA lanes / clk / SM etc.) used for the measured roofline
  * denominator.  Fills out[0..n) with: [0] FFMA lane-ops/s, [1] FFMA
  * lane-ops/clk/SM, [2] MUFU lane-ops/s, [3] DFMA lane-ops/s, [4] SM clock (Hz) seen.  Synchronises.

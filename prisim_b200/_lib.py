@@ -61,6 +61,11 @@ SYMBOLS = {
     "pb200_delay_transform": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp]),
     "pb200_phase_rotate": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "pb200_healpix_beam": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "pb200_device_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "pb200_device_free": (_i, [_vp, _vp]),
+    "pb200_peer_export": (_i, [_vp, _vp, _vp]),
+    "pb200_peer_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "pb200_peer_close": (_i, [_vp, _vp]),
     "pb200_microbench": (_i, [_vp, C.POINTER(_d), _i]),
 }
 

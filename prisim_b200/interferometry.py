@@ -593,27 +593,26 @@ class InterferometerArray(object):
             low = rms_b < self.cancel_ratio * a2
             flagged = torch.nonzero(low).flatten()
             nflag = int(flagged.numel())
-            amp64 = None
-            if nflag > 0:
-                amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
-                skyvis.index_copy_(0, flagged, run64(self._d_bl.index_select(0, flagged).contiguous(), amp64))
             # (2) sampled fp64 audit.  On coherent skies (smooth diffuse emission: same-sign amplitudes, slowly
             # varying phases) fp32 partial sums are much larger than the incoherent norm and so is the error;
             # a few un-flagged baselines (shortest, longest, random) are recomputed in fp64 and compared.
-            audit_err, audited = 0.0, 0
+            # Flagged and audited baselines share ONE fp64 launch (both are far fewer than a wave of CTAs).
             keep = torch.nonzero(~low).flatten()
-            if keep.numel() > 0:
+            sel = keep[:0]
+            if keep.numel() > 0 and self.audit_baselines > 0:
                 gen = torch.Generator(device="cpu").manual_seed(20261017 + len(self._skyvis))
                 pick = torch.randperm(int(keep.numel()), generator=gen)[: max(self.audit_baselines - 2, 0)]
                 sel = torch.unique(torch.cat((keep[[0, -1]], keep[pick.to(keep.device)])))
-                if amp64 is None:
-                    amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
-                ref = run64(self._d_bl.index_select(0, sel).contiguous(), amp64)
-                got = skyvis.index_select(0, sel)
-                rms_ref = torch.sqrt(ref.real.square().mean(dim=1) + ref.imag.square().mean(dim=1)).clamp_min(1e-300)
-                audit_err = float(((got - ref).abs().amax(dim=1) / rms_ref).max().item())
-                audited = int(sel.numel())
-                skyvis.index_copy_(0, sel, ref)
+            audit_err, audited = 0.0, int(sel.numel())
+            both = torch.cat((flagged, sel))
+            if both.numel() > 0:
+                amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+                ref = run64(self._d_bl.index_select(0, both).contiguous(), amp64)
+                if audited:
+                    ref_a, got = ref[nflag:], skyvis.index_select(0, sel)
+                    rms_ref = torch.sqrt(ref_a.real.square().mean(dim=1) + ref_a.imag.square().mean(dim=1)).clamp_min(1e-300)
+                    audit_err = float(((got - ref_a).abs().amax(dim=1) / rms_ref).max().item())
+                skyvis.index_copy_(0, both, ref)
                 if audit_err > self.audit_tolerance:          # fp32 is not good enough on this sky: everything in fp64
                     skyvis.index_copy_(0, keep, run64(self._d_bl.index_select(0, keep).contiguous(), amp64))
                     nflag = nbl

@@ -73,3 +73,77 @@ def make_sharded_array(cls, labels, baselines, channels, rank=None, world_size=N
     sl = shard_slice(baselines.shape[0], world_size, rank)
     labels = NP.asarray(labels)[sl] if not isinstance(labels, list) else labels[sl]
     return cls(labels, baselines[sl], channels, bl_offset=sl.start, nbl_total=baselines.shape[0], **kwargs)
+
+
+class _RawCudaBuffer(object):
+    """Minimal ``__cuda_array_interface__`` carrier so torch can view memory this package allocated or mapped."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerGatherBuffer(object):
+    """Gather through peer memory: rank `dst` owns a [world, *shape] complex128 buffer; every other rank maps it over
+    NVLink (CUDA IPC) and lets its kernels write the result slice directly (pass ``local`` as ``out=`` to
+    ``engine.skyvis``).  ``wait()`` = stream sync + barrier; afterwards ``full`` on `dst` holds all slices.
+    Falls back to an NCCL point-to-point gather when peer mapping is unavailable (``mode == 'nccl'``)."""
+
+    def __init__(self, shape, device, dst=0, group=None):
+        import ctypes as C
+        from . import _lib
+        self.group, self.dst, self.shape = group, dst, tuple(shape)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = int(device)
+        self.ctx = _lib.get_context(self.device)
+        dev = "cuda:{0}".format(self.device)
+        nel = int(NP.prod(self.shape))
+        self._base = C.c_void_p()
+        self._mapped = False
+        handle = torch.zeros(65, dtype=torch.uint8, device=dev)               # 64-byte handle + ok flag
+        if self.rank == dst:
+            ok = self.ctx.lib.pb200_device_alloc(self.ctx.handle, nel * 16 * self.world, C.byref(self._base)) == 0
+            hb = (C.c_ubyte * 64)()
+            ok = ok and self.ctx.lib.pb200_peer_export(self.ctx.handle, self._base, hb) == 0
+            handle[:64] = torch.tensor(list(hb), dtype=torch.uint8)
+            handle[64] = 1 if ok else 0
+        dist.broadcast(handle, src=dst, group=group)
+        ok = bool(handle[64].item())
+        if ok and self.rank != dst:
+            hb = (C.c_ubyte * 64)(*handle[:64].cpu().tolist())
+            ok = self.ctx.lib.pb200_peer_open(self.ctx.handle, hb, C.byref(self._base)) == 0
+            self._mapped = ok
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.mode = "peer" if bool(flag.item()) else "nccl"
+        if self.mode == "peer":
+            base = self._base.value
+            self.local = torch.as_tensor(_RawCudaBuffer(base + self.rank * nel * 16, self.shape, "<c16"), device=dev)
+            self.full = (torch.as_tensor(_RawCudaBuffer(base, (self.world,) + self.shape, "<c16"), device=dev)
+                         if self.rank == dst else None)
+        else:
+            self.full = torch.empty((self.world,) + self.shape, dtype=torch.complex128, device=dev) if self.rank == dst else None
+            self.local = self.full[dst] if self.rank == dst else torch.empty(self.shape, dtype=torch.complex128, device=dev)
+
+    def wait(self):
+        """Make every rank's slice visible on `dst` (peer mode: stores are complete when the writers' streams are;
+        nccl mode: one batched point-to-point gather)."""
+        if self.mode == "nccl":
+            if self.rank == self.dst:
+                ops = [dist.P2POp(dist.irecv, self.full[r], r, group=self.group) for r in range(self.world) if r != self.dst]
+            else:
+                ops = [dist.P2POp(dist.isend, self.local, self.dst, group=self.group)]
+            for req in (dist.batch_isend_irecv(ops) if ops else []):
+                req.wait()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.mode == "peer" and self._base.value:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self.local = self.full = None
+            if self.rank == self.dst:
+                self.ctx.lib.pb200_device_free(self.ctx.handle, self._base)
+            elif self._mapped:
+                self.ctx.lib.pb200_peer_close(self.ctx.handle, self._base)
+            self._base.value = None

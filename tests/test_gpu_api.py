@@ -404,3 +404,31 @@ def test_gridded_healpix_beam_vs_oracle():
     assert rel_err(ia.skyvis_freq[:, :, 0], Vo) <= TOL
     with pytest.raises(ValueError):
         PB.HealpixBeam(beam[:-1], bf, chans)
+
+
+def test_peer_gather_buffer_single_rank():
+    """sharding.PeerGatherBuffer on a one-rank NCCL group: the library-allocated, IPC-exported buffer is a valid
+    output target for the phase-sum kernel (the 2- and 8-GPU runs of bench.py use the same path across ranks)."""
+    import socket
+    import torch.distributed as dist
+    from prisim_b200 import engine
+    from prisim_b200.sharding import PeerGatherBuffer
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:{0}".format(port), world_size=1, rank=0,
+                            device_id=torch.device("cuda:0"))
+    try:
+        nbl, nchan, nsrc = 70, 130, 90
+        g = PeerGatherBuffer((nbl, nchan), 0, dst=0)
+        assert g.mode == "peer" and g.full.shape == (1, nbl, nchan)
+        rng = NP.random.default_rng(1)
+        bl = rng.normal(0, 100, (nbl, 3)); freqs = 150e6 + NP.arange(nchan) * 1e5
+        altaz = NP.stack((NP.degrees(NP.arcsin(rng.uniform(0, 1, nsrc))), rng.uniform(0, 360, nsrc)), 1)
+        dircos, _ = engine.sky_cull(altaz, "altaz")
+        amp = engine.dense_to_amp_table(torch.rand((nsrc, nchan), device="cuda"))
+        engine.skyvis(dircos, amp, nsrc, bl, (0, 0, 1.0), freqs, out=g.local)
+        ref = engine.skyvis(dircos, amp, nsrc, bl, (0, 0, 1.0), freqs)
+        g.wait()
+        assert torch.equal(g.full[0], ref)
+        g.close()
+    finally:
+        dist.destroy_process_group()
