@@ -600,7 +600,7 @@ class InterferometerArray(object):
             keep = torch.nonzero(~low).flatten()
             sel = keep[:0]
             if keep.numel() > 0 and self.audit_baselines > 0:
-                gen = torch.Generator(device="cpu").manual_seed(20261017 + len(self._skyvis))
+                gen = torch.Generator(device="cpu").manual_seed(20261017 + getattr(self, "_drained", 0) + len(self._skyvis))
                 pick = torch.randperm(int(keep.numel()), generator=gen)[: max(self.audit_baselines - 2, 0)]
                 sel = torch.unique(torch.cat((keep[[0, -1]], keep[pick.to(keep.device)])))
             audit_err, audited = 0.0, int(sel.numel())
@@ -719,9 +719,10 @@ class InterferometerArray(object):
         aeff, effq = self._aeff_effq()
         nbl, nchan = self.baselines.shape[0], self.channels.size
         self._rms, self._noise = [], []
+        base = getattr(self, "_drained", 0)
         for t in range(len(self._skyvis)):
-            rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[t],
-                                      self.noise_seed, nbl, nchan, snapshot=t, bl_offset=self.bl_offset,
+            rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
+                                      self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
                                       nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
                                       want=("rms", "noise"), device=self.device)
             self._rms.append(rms)
@@ -783,6 +784,46 @@ class InterferometerArray(object):
             self._lag["kernel"].append(kern if krows == nbl else kern[0])
         if verbose:
             print("delay_transform() completed successfully.")
+
+    # ------------------------------------------------------------------ bounded-memory streaming
+    def drain(self, sink, noise=True, delay_transform=None):
+        """Stream the resident snapshots out and free their device memory (a 1000-snapshot HERA-350 run is
+        ~7.5 GB per snapshot with all products and cannot stay resident; the reference keeps growing numpy
+        arrays, interferometry.py:6390).  For every resident snapshot: optionally generate noise + add it
+        (same Philox stream as generate_noise/add_noise: keyed by the global snapshot index) and delay-transform
+        (``delay_transform=dict(pad=..., freq_wts=...)``), then call ``sink(j, products)`` with a dict of
+        [nbl, n] CUDA tensors ('skyvis_freq', 'vis_freq', 'vis_noise_freq', 'vis_rms_freq', 'skyvis_lag', ...),
+        and drop them.  Bookkeeping (timestamp, lst, t_acc, pointing centres, indices) is kept; snapshot numbering
+        continues."""
+        base = getattr(self, "_drained", 0)
+        nres = len(self._skyvis)
+        if nres == 0:
+            return 0
+        if noise:
+            aeff, effq = self._aeff_effq()
+            nbl, nchan = self.baselines.shape[0], self.channels.size
+        getter = None
+        if delay_transform is not None and delay_transform.get("freq_wts", None) is not None:
+            getter = self._freq_wts_getter(delay_transform["freq_wts"])
+        for t in range(nres):
+            prod = {"skyvis_freq": self._skyvis[t]}
+            if noise:
+                rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
+                                          self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
+                                          nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
+                                          want=("rms", "noise"), device=self.device)
+                prod.update(vis_rms_freq=rms, vis_noise_freq=nz, vis_freq=engine.add_noise(self._skyvis[t], nz))
+            if delay_transform is not None:
+                pad = delay_transform.get("pad", 1.0)
+                wts = None if getter is None else getter(t)
+                for key in [k for k in ("skyvis_freq", "vis_freq", "vis_noise_freq") if k in prod]:
+                    prod[key.replace("_freq", "_lag")] = engine.delay_transform(prod[key], self._bp[t], wts, self.freq_resolution,
+                                                                               pad=pad, downsample=True)
+            sink(base + t, prod)
+        self._skyvis, self._vis, self._noise, self._rms, self._bp, self._Tsys = [], [], [], [], [], []
+        self._lag = {}
+        self._drained = base + nres
+        return nres
 
     # ------------------------------------------------------------------ phase centring / uvw (SURVEY 8f-1)
     def _centre_to_dircos(self, centre, coords):
