@@ -10,14 +10,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprisim_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libprisim_b200.so")   # PB200_LIB: developer override (tools/variants.sh)
 
 PB200_OK = 0
 SKY_ALTAZ, SKY_HADEC, SKY_DIRCOS = 0, 1, 2
 BEAM_DELTA, BEAM_AIRY, BEAM_GAUSSIAN, BEAM_DIPOLE, BEAM_TABLE, BEAM_LOGTABLE = 0, 1, 2, 3, 4, 5
 ARRAY_NONE, ARRAY_ANALYTIC, ARRAY_ELEMENTS = 0, 1, 2
 DIPOLE_GENERAL, DIPOLE_SHORT, DIPOLE_HALFWAVE = 0, 1, 2
-SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR, SKYVIS_FP64 = 0, 1, 2, 3, 4
+SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR, SKYVIS_FP64, SKYVIS_RECURRENCE_LIFT = 0, 1, 2, 3, 4, 5
 SLAB, SRC_TILE = 128, 32
 AMP_F32, AMP_F64 = 0, 1
 

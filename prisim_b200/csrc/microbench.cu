@@ -125,6 +125,49 @@ __global__ void k_rot_packed(float* out, float x, float y, long long* cyc) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// 4b. the same loop in the operand-reuse order (each instruction keeps one operand of its predecessor in the same
+//     slot): t1 = PR*RR, t2 = PR*RI, are += PR*A, aim += PI*A, nr = PI*NRI + t1, ni = PI*RR + t2.  LDSA = 1: the
+//     amplitudes come from shared memory (one LDS.128 broadcast per two steps per source), as in the kernel.
+template <int LDSA>
+__global__ void k_rot_packed_reuse(float* out, float x, float y, long long* cyc) {
+  __shared__ float4 sm[1024];
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sm[i] = make_float4(1.f + i * 1e-4f, 1.f, 1.01f, 0.99f);
+  __syncthreads();
+  unsigned long long PR[4], PI[4], RR[4], RI[4], NRI[4], AR[16], AI[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { PR[j] = pk(1.f, x); PI[j] = pk(0.f, y); RR[j] = pk(x + j * 1e-6f, x + j * 1e-6f); RI[j] = pk(y, y); NRI[j] = pk(-y, -y); }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { AR[j] = 0ull; AI[j] = 0ull; }
+  unsigned long long A0 = pk(threadIdx.x * 1e-4f + 1.f, threadIdx.x * 1e-4f + 1.1f);
+  long long t0 = clock64();
+  for (int it = 0; it < ITER / 16; ++it) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        unsigned long long A = A0;
+        if (LDSA) {
+          const float4 v = sm[((it * 4 + j) * 8 + (c >> 1)) & 1023];
+          A = (c & 1) ? pk(v.z, v.w) : pk(v.x, v.y);
+        }
+        unsigned long long t1, t2;
+        asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(t1) : "l"(PR[j]), "l"(RR[j]));
+        asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(PR[j]), "l"(RI[j]));
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AR[c]) : "l"(PR[j]), "l"(A));
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AI[c]) : "l"(PI[j]), "l"(A));
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(PR[j]) : "l"(PI[j]), "l"(NRI[j]), "l"(t1));
+        asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(PI[j]) : "l"(PI[j]), "l"(RR[j]), "l"(t2));
+      }
+    }
+  }
+  long long t1c = clock64();
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += lo(AR[j]) + lo(AI[j]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1c - t0;
+}
+
 // 5. MUFU: sin.approx + cos.approx pairs (each = FMUL by 1/2pi + MUFU)
 __global__ void k_mufu(float* out, float x, float y, long long* cyc) {
   float acc[NCH];
@@ -202,6 +245,142 @@ __global__ void k_mix(float* out, float x, float y, long long* cyc) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// 8. FP32-pipe + FP64-pipe co-issue: NF independent FFMA2 chains interleaved with ND independent DFMA chains.
+template <int NF, int ND>
+__global__ void k_coissue(float* out, float x, float y, long long* cyc) {
+  unsigned long long acc[NF];
+  unsigned long long x2 = pk(x, x * 1.0001f), y2 = pk(y, y * 0.999f);
+  double d[ND]; double xd = x, yd = y;
+#pragma unroll
+  for (int j = 0; j < NF; ++j) acc[j] = pk(threadIdx.x * 1e-3f + j, j);
+#pragma unroll
+  for (int j = 0; j < ND; ++j) d[j] = threadIdx.x * 1e-3 + j;
+  constexpr int NMAX = NF > ND ? NF : ND;
+  long long t0 = clock64();
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+      if (j * NF / NMAX != (j + 1) * NF / NMAX || NF == NMAX) {
+        const int k = NF == NMAX ? j : j * NF / NMAX;
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[k]) : "l"(x2), "l"(y2));
+      }
+      if (j * ND / NMAX != (j + 1) * ND / NMAX || ND == NMAX) {
+        const int k = ND == NMAX ? j : j * ND / NMAX;
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[k]) : "d"(xd), "d"(yd));
+      }
+    }
+  }
+  long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < NF; ++j) s += lo(acc[j]);
+#pragma unroll
+  for (int j = 0; j < ND; ++j) s += (float)d[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// 9. hybrid rotate+accumulate: warps with bit 2 of the warp id clear run the packed fp32 loop over 32 channels per
+//    source (96 FFMA2), the others the same recurrence in fp64 over 16 channels per source (96 DFMA), i.e. each
+//    scheduler holds 2 + 2 warps at 4 warps per scheduler; NS independent sources in flight per thread.  AMP = 1:
+//    amplitudes come from shared memory (LDS.128 broadcast) and the fp64 warps convert them (cvt.f64.f32).
+//    FRAC64: 1 = as described, 0 = all warps fp32.
+template <int AMP, int FRAC64, int NS>
+__global__ void k_hybrid(float* out, float x, float y, long long* cyc) {
+  __shared__ float4 sm[512];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) sm[i] = make_float4(1.f + i * 1e-4f, 1.f, 1.01f, 0.99f);
+  __syncthreads();
+  const bool role64 = FRAC64 && ((threadIdx.x >> 7) & 1);
+  float s = 0;
+  long long t0 = clock64();
+  if (!role64) {
+    unsigned long long AR[16], AI[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { AR[j] = 0ull; AI[j] = 0ull; }
+    for (int it = 0; it < ITER / 16 / NS; ++it) {
+      unsigned long long PR[NS], PI[NS], RR[NS], RI[NS], NRI[NS], A[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        PR[j] = pk(1.f, x); PI[j] = pk(0.f, y); RR[j] = pk(x + (it + j) * 1e-6f, x + it * 1e-6f); RI[j] = pk(y, y); NRI[j] = pk(-y, -y);
+        A[j] = pk(threadIdx.x * 1e-4f + 1.f, threadIdx.x * 1e-4f + 1.1f);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          if (AMP && (c & 1) == 0) {
+            float4 v = sm[((it * NS + j) * 8 + (c >> 1)) & 511];
+            A[j] = pk(v.x, v.y);
+            if (c & 2) A[j] = pk(v.z, v.w);
+          }
+          unsigned long long nr, ni;
+          asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(nr) : "l"(PR[j]), "l"(RR[j]));
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(nr) : "l"(PI[j]), "l"(NRI[j]));
+          asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(ni) : "l"(PR[j]), "l"(RI[j]));
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ni) : "l"(PI[j]), "l"(RR[j]));
+          PR[j] = nr; PI[j] = ni;
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AR[c]) : "l"(A[j]), "l"(nr));
+          asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(AI[c]) : "l"(A[j]), "l"(ni));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += lo(AR[j]) + lo(AI[j]);
+  } else {
+    double ar[16], ai[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { ar[j] = 0; ai[j] = 0; }
+    for (int it = 0; it < ITER / 16 / NS; ++it) {
+      double pr[NS], pi[NS], rr[NS], ri[NS], a[NS];
+      float4 v[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) { pr[j] = 1.0; pi[j] = 0.0; rr[j] = (double)(x + (it + j) * 1e-6f); ri[j] = (double)y; a[j] = threadIdx.x * 1e-4 + 1.0; }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          if (AMP) {
+            if ((c & 3) == 0) v[j] = sm[((it * NS + j) * 4 + (c >> 2)) & 511];
+            a[j] = (double)((c & 3) == 0 ? v[j].x : (c & 3) == 1 ? v[j].y : (c & 3) == 2 ? v[j].z : v[j].w);
+          }
+          double nr, ni;
+          asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(nr) : "d"(pr[j]), "d"(rr[j]));
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(nr) : "d"(-pi[j]), "d"(ri[j]));
+          asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(ni) : "d"(pr[j]), "d"(ri[j]));
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(ni) : "d"(pi[j]), "d"(rr[j]));
+          pr[j] = nr; pi[j] = ni;
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(ar[c]) : "d"(a[j]), "d"(nr));
+          asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(ai[c]) : "d"(a[j]), "d"(ni));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += (float)(ar[j] + ai[j]);
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// 10. dependent-issue latency of one chain per thread, one warp per scheduler
+template <int OP>
+__global__ void k_latency(float* out, float x, float y, long long* cyc) {
+  double d = threadIdx.x * 1e-3, xd = x, yd = y; float f = threadIdx.x * 1e-3f;
+  unsigned long long p = pk(f, f), x2 = pk(x, x), y2 = pk(y, y);
+  long long t0 = clock64();
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (OP == 0) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(x), "f"(y));
+      if (OP == 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p) : "l"(x2), "l"(y2));
+      if (OP == 2) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d) : "d"(xd), "d"(yd));
+    }
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = f + lo(p) + (float)d;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 struct Res { double ms; double cyc; };
 
 template <typename K>
@@ -240,6 +419,8 @@ int main() {
   rep("ffma2_packed", run(k_ffma2, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");
   rep("rotacc_scalar_terms", run(k_rot_scalar, blocks, threads, out, cyc), (double)(ITER / 4) * 16, "terms");
   rep("rotacc_packed_terms", run(k_rot_packed, blocks, threads, out, cyc), (double)(ITER / 4) * 16 * 2, "terms");
+  rep("rotacc_packed_reuse_order_terms", run(k_rot_packed_reuse<0>, blocks, threads, out, cyc), (double)(ITER / 16) * 16 * 4 * 2, "terms");
+  rep("rotacc_packed_reuse_order_lds_terms", run(k_rot_packed_reuse<1>, blocks, threads, out, cyc), (double)(ITER / 16) * 16 * 4 * 2, "terms");
   rep("mufu_ex2", run(k_mufu, blocks, threads, out, cyc), (double)ITER * NCH, "mufu");
   rep("dfma", run(k_dfma, blocks, threads, out, cyc), (double)ITER * NCH, "dfma");
   rep("mix_ffma2x16_only", run(k_mix<0, 0, 0>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");
@@ -248,7 +429,26 @@ int main() {
   rep("mix_ffma2x16_dfma2", run(k_mix<0, 2, 0>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");
   rep("mix_ffma2x16_dfma4", run(k_mix<0, 4, 0>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");
   rep("mix_ffma2x16_lds4", run(k_mix<0, 0, 4>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");
-  rep("mix_ffma2x16_m2_d2_l4", run(k_mix<2, 2, 4>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma", true);
+  rep("mix_ffma2x16_m2_d2_l4", run(k_mix<2, 2, 4>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");
+  // co-issue: the value is FFMA-lane-equivalents, counting one DFMA as one lane op (so 118 + 58.8 = 177 if both pipes fill)
+  rep("coissue_f16_d4", run(k_coissue<16, 4>, blocks, threads, out, cyc), (double)ITER * (16 * 2 + 4), "fma_plus_dfma");
+  rep("coissue_f16_d8", run(k_coissue<16, 8>, blocks, threads, out, cyc), (double)ITER * (16 * 2 + 8), "fma_plus_dfma");
+  rep("coissue_f16_d16", run(k_coissue<16, 16>, blocks, threads, out, cyc), (double)ITER * (16 * 2 + 16), "fma_plus_dfma");
+  rep("coissue_f8_d16", run(k_coissue<8, 16>, blocks, threads, out, cyc), (double)ITER * (8 * 2 + 16), "fma_plus_dfma");
+  // hybrid rotate+accumulate: terms per thread averaged over the two roles (fp32 warp 32 per source, fp64 warp 16)
+  rep("hybrid_allfp32_terms", run(k_hybrid<0, 0, 4>, blocks, threads, out, cyc), (double)(ITER / 16) * 32, "terms");
+  rep("hybrid_allfp32_lds_terms", run(k_hybrid<1, 0, 4>, blocks, threads, out, cyc), (double)(ITER / 16) * 32, "terms");
+  rep("hybrid_2to1_ns1_terms", run(k_hybrid<0, 1, 1>, blocks, threads, out, cyc), (double)(ITER / 16) * 24, "terms");
+  rep("hybrid_2to1_ns2_terms", run(k_hybrid<0, 1, 2>, blocks, threads, out, cyc), (double)(ITER / 16) * 24, "terms");
+  rep("hybrid_2to1_ns4_terms", run(k_hybrid<0, 1, 4>, blocks, threads, out, cyc), (double)(ITER / 16) * 24, "terms");
+  rep("hybrid_2to1_ns4_lds_cvt_terms", run(k_hybrid<1, 1, 4>, blocks, threads, out, cyc), (double)(ITER / 16) * 24, "terms");
+  {
+    // latency: cycles per dependent instruction (128 threads = 1 warp per scheduler, 1 CTA per SM)
+    const char* nm[3] = {"latency_ffma", "latency_ffma2", "latency_dfma"};
+    Res r0 = run(k_latency<0>, sms, 128, out, cyc), r1 = run(k_latency<1>, sms, 128, out, cyc), r2 = run(k_latency<2>, sms, 128, out, cyc);
+    double c[3] = {r0.cyc, r1.cyc, r2.cyc};
+    for (int i = 0; i < 3; ++i) printf("  \"%s\": {\"cycles_per_dependent_op\": %.2f}%s\n", nm[i], c[i] / (ITER * 16.0), i == 2 ? "" : ",");
+  }
   printf("}\n");
   return 0;
 }

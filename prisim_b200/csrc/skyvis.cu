@@ -26,6 +26,7 @@
 //     (b,f): no atomics, deterministic order).
 #include "common.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -34,8 +35,21 @@ constexpr int WCS = PB200_SLAB / KT;           // channel blocks per slab = 4
 constexpr int NWARPS = 16;
 constexpr int NTHREADS = 32 * NWARPS;          // 512
 constexpr int T = PB200_SRC_TILE;              // sources per tile
-constexpr int FLUSH_TILES = 16;                // fp32 -> fp64 flush cadence (512 sources); measured max error at C2 / speed: 6.3e-6 / 4.42 @32, 5.5e-6 @16, 4.7e-6 / 4.29 @8
+#ifndef PB_FLUSH_TILES
+#define PB_FLUSH_TILES 16
+#endif
+#ifndef PB_STAGGER
+#define PB_STAGGER 4
+#endif
+#ifndef PB_LIFT_MAX_ANGLE
+#define PB_LIFT_MAX_ANGLE 2.0   // rad per two-channel step; tan(1) = 1.56 keeps the shear intermediates below 2.6
+#endif
+#ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
+#define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
+#endif
+constexpr int FLUSH_TILES = PB_FLUSH_TILES;                // fp32 -> fp64 flush cadence (512 sources); measured max error at C2 / speed: 6.3e-6 / 4.42 @32, 5.5e-6 @16, 4.7e-6 / 4.29 @8
 constexpr int NSTAGE = 2;
+constexpr int STAGGER = PB_STAGGER;                     // source-loop chunks per tile between which the warps of a scheduler take turns precomputing
 // CTA shape: SPC slabs (SPC*128 channels) x WB baseline groups, SPC*WCS*WB = 16 warps.  A wider
 // channel extent shares each (source, baseline) delay/rotation among more warps (less per-tile
 // precompute); a wider baseline extent re-reads the amplitude tile less often.
@@ -62,6 +76,8 @@ struct SkyvisParams {
   double f0, df;           // uniform channels: f_k = f0 + k df
   int nsrc_pad, nbl, nchan, nslab;
   int spc;                 // slabs per CTA of the launch that filled `accum` (finalize)
+  int lift;                // allow the lifted (3-shear) rotation on CTA rows whose step angle stays small
+  const unsigned* smax2_bits;   // device: float bits of max_s |s - s_pc|^2 (k_geom_stage)
 };
 
 template <int SPC> struct __align__(16) TileIn {   // TMA destination
@@ -235,6 +251,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   }
   const bool live = sl < nsl;                          // warps of a missing slab only help with the precompute
 
+  // Lifted rotation (3 FFMA2 instead of 2 FMUL2 + 2 FFMA2 per two-channel step): a rotation by phi is the shear
+  // product  x += t y;  y += s x;  x += t y  with t = -tan(phi/2), s = sin(phi).  Determinant 1 by construction and
+  // more accurate than the complex multiply while |phi| <= PB_LIFT_MAX_ANGLE (measured in tools/lift_accuracy.py);
+  // tan blows up towards pi, so a CTA row uses it only if every (source, baseline) pair of the row stays below the
+  // limit:  |phi| = 4 pi df |tau|,  |tau| <= |b|/c max_s |s - s_pc|.  The decision is CTA-uniform.
+  bool lift_row = false;
+  if (PACKED && !TAPER && P.lift) {
+    const float smax2 = __uint_as_float(*P.smax2_bits);
+    const double lim = PB_LIFT_MAX_ANGLE / (4.0 * 3.14159265358979323846 * fabs(df));
+    lift_row = !__syncthreads_or(valid && G.blen2 * (double)smax2 > lim * lim);
+  }
+
   // cooperative per-tile stage: tau and the channel rotation for S::PRE sources of this
   // thread's own baseline (sources s = wc, wc+WC, ...)
   auto precompute = [&](int tile) {
@@ -247,7 +275,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
       const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
       tpre[stage].tau[s][bcol] = tau;
-      tpre[stage].rot[s][bcol] = rotation_phasor(tau * df);
+      float2 rp = rotation_phasor(tau * df);
+      // lifted rows: shear coefficients of the two-channel step, t = -tan(phi) and s = sin(2 phi) for r = e^{i phi}
+      if (lift_row) rp = make_float2(-__fdiv_rn(rp.y, rp.x), 2.0f * rp.x * rp.y);
+      tpre[stage].rot[s][bcol] = rp;
       if (TAPER) {
         // w = exp(-1/2 (u_proj/sigma)^2), u_proj^2 = (|b|^2 - (c tau_g)^2) f^2/c^2 (interferometry.py:6262-6283);
         // g.w = ln2 d^2 1e16 log2(e)  so that  w = exp2(-g.w (|b/c|^2 - tau_g^2) (f/1e8)^2); sqrt argument clamped at 0
@@ -263,27 +294,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   precompute(0);
   __syncthreads();
 
-  for (int tile = 0; tile < ntiles; ++tile) {
+  auto run_tile = [&](int tile, auto lift_c) {
+    constexpr bool LIFT = decltype(lift_c)::value;
     const int stage = tile & 1;
-    if (tile + 1 < ntiles) precompute(tile + 1);
     const TileIn<SPC>& ti = tin[stage];
     const TilePre<SPC>& tp = tpre[stage];
-    if (live) {
-
-    // software pipeline over sources: the anchor of source s+1 is evaluated while the channel loop of s runs
+    // software pipeline over sources: the anchor(s) of source s+1 are evaluated while the channel loop of s runs
     float2 p_next = anchor_phasor(tp.tau[0][bcol] * fk0);
+    float2 q_next = LIFT ? anchor_phasor(tp.tau[0][bcol] * (fk0 + df)) : make_float2(0.f, 0.f);
     float2 r_next = tp.rot[0][bcol];
+    // the next tile's precompute (fp64 / XU / ALU work, no FFMA2) is staggered over the four warps of a
+    // scheduler (warp >> 2 = index within the scheduler): at any time at most one of them is off the FMA
+    // pipe and the other three keep it fed, instead of all 16 warps leaving it idle together
+#pragma unroll 1
+    for (int chunk = 0; chunk < STAGGER; ++chunk) {
+    if (chunk == (warp >> 2) % STAGGER && tile + 1 < ntiles && !((PB_ABLATE & 1) && tile > 0)) precompute(tile + 1);
 #pragma unroll 4
-    for (int s = 0; s < T; ++s) {
-      const float2 p0 = p_next, r = r_next;
+    for (int s = chunk * (T / STAGGER); s < (chunk + 1) * (T / STAGGER); ++s) {
+      const float2 p0 = p_next, q0 = q_next, r = r_next;
       const int sn = (s + 1 < T) ? s + 1 : s;
-      p_next = anchor_phasor(tp.tau[sn][bcol] * fk0);
+      p_next = (PB_ABLATE & 2) ? tp.rot[sn][bcol ^ 1] : anchor_phasor(tp.tau[sn][bcol] * fk0);
+      if (LIFT) q_next = (PB_ABLATE & 2) ? tp.rot[sn][bcol ^ 2] : anchor_phasor(tp.tau[sn][bcol] * (fk0 + df));
       r_next = tp.rot[sn][bcol];
       const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KT]);
       float kap = 0.f;
       if (TAPER) kap = tkap[stage].kap[s][bcol];
 
-      if (PACKED) {
+      if (LIFT) {
+        // both channels of the pair are anchored directly (the XU and FP64 pipes are idle under the FFMA2
+        // stream), then stepped two channels at a time by three packed shears; r = (t, s)
+        float2 PR = make_float2(p0.x, q0.x), PI = make_float2(p0.y, q0.y);
+        const float2 TT = make_float2(r.x, r.x), SS = make_float2(r.y, r.y);
+#pragma unroll
+        for (int k4 = 0; k4 < KT / 4; ++k4) {
+          const float4 a4 = (PB_ABLATE & 8) ? make_float4(kap + 1.f, kap + 2.f, kap + 3.f, kap + 4.f) : arow[k4];
+          const float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w);
+          acc_re[2 * k4] = __ffma2_rn(PR, A0, acc_re[2 * k4]);
+          acc_im[2 * k4] = __ffma2_rn(PI, A0, acc_im[2 * k4]);
+          float2 x1 = __ffma2_rn(PI, TT, PR);
+          PI = __ffma2_rn(x1, SS, PI);
+          PR = __ffma2_rn(PI, TT, x1);
+          acc_re[2 * k4 + 1] = __ffma2_rn(PR, A1, acc_re[2 * k4 + 1]);
+          acc_im[2 * k4 + 1] = __ffma2_rn(PI, A1, acc_im[2 * k4 + 1]);
+          if (k4 + 1 < KT / 4) {
+            x1 = __ffma2_rn(PI, TT, PR);
+            PI = __ffma2_rn(x1, SS, PI);
+            PR = __ffma2_rn(PI, TT, x1);
+          }
+        }
+      } else if (PACKED) {
         // two channels per packed register: P = (p_k, p_{k+1}), stepped by r^2
         const float p1r = fmaf(-p0.y, r.y, p0.x * r.x), p1i = fmaf(p0.y, r.x, p0.x * r.y);
         const float r2r = fmaf(-r.y, r.y, r.x * r.x), r2i = 2.0f * r.x * r.y;
@@ -308,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
         float2 NRI = make_float2(-RI.x, -RI.y);
 #pragma unroll
         for (int k4 = 0; k4 < KT / 4; ++k4) {
-          const float4 a4 = arow[k4];
+          const float4 a4 = (PB_ABLATE & 8) ? make_float4(kap + 1.f, kap + 2.f, kap + 3.f, kap + 4.f) : arow[k4];
           const float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w);
           // operand order chosen for the register-reuse cache: every packed instruction reads at
           // most two fresh 64-bit operands (PR / PI / A stay in the same operand slot across
@@ -354,9 +413,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       }
     }
     }
+  };
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    if (!live && tile + 1 < ntiles) precompute(tile + 1);
+    if (live) {
+      if (lift_row) run_tile(tile, std::integral_constant<bool, PACKED && !TAPER>());
+      else run_tile(tile, std::false_type());
+    }
     __syncthreads();                                   // tile consumed, next tile's tau/rot visible
-    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-    if (live && ((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, acc_re, acc_im);
+    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, tile & 1);
+    // flushes are staggered over the warps of a scheduler like the precompute (accumulators are thread-private,
+    // so a warp may flush at any tile boundary): one warp waits on its global read-modify-write, three keep going
+    if (live && ((tile + 1 + (warp >> 2) * (FLUSH_TILES / 4)) % FLUSH_TILES) == 0 && !(PB_ABLATE & 4)) flush_acc(P, acc_re, acc_im);
   }
   if (live) flush_acc(P, acc_re, acc_im);
 }
@@ -574,13 +643,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
 }
 
 // geometry staging: [nsrc_pad][4] = (l, m, n, taper coefficient), zero rows for padding
+// also: max_s |s - s_pc|^2 (float bits, atomicMax on the unsigned pattern of a non-negative float; rounded up),
+// the bound on |tau|/|b/c| that decides which CTA rows may use the lifted rotation
 __global__ void k_geom_stage(const double* __restrict__ dircos, const double* __restrict__ fwhm_deg, int nsrc,
-                             int nsrc_pad, double* __restrict__ geom) {
+                             int nsrc_pad, double* __restrict__ geom, double pcx, double pcy, double pcz,
+                             unsigned* __restrict__ smax2_bits) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsrc_pad) return;
   double4 g = make_double4(0, 0, 0, 0);
   if (s < nsrc) {
     g.x = dircos[3 * (size_t)s]; g.y = dircos[3 * (size_t)s + 1]; g.z = dircos[3 * (size_t)s + 2];
+    const double dx = g.x - pcx, dy = g.y - pcy, dz = g.z - pcz;
+    atomicMax(smax2_bits, __float_as_uint(__double2float_ru(dx * dx + dy * dy + dz * dz)));
     if (fwhm_deg) {
       double d = 2.0 * sin(0.5 * fwhm_deg[s] * 0.017453292519943295769);      // interferometry.py:6268
       // 1/(2 sigma^2) = ln2 * d^2 (:6270); fold the (f/1e8)^2 scaling and log2(e)
@@ -601,7 +675,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   if (nsrc > 0 && (!d_dircos || !d_amp)) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: null source arrays");
   if (amp_dtype != PB200_AMP_F32 && !(amp_dtype == PB200_AMP_F64 && method == PB200_SKYVIS_FP64))
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: an fp64 amplitude table needs method PB200_SKYVIS_FP64");
-  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_FP64)
+  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_LIFT)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -615,7 +689,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   bool uniform = true;
   for (int k = 0; k < nchan; ++k)
     if (fabs(h_freqs[k] - (h_freqs[0] + k * df)) > 1e-4) { uniform = false; break; }   // 1e-4 Hz * 1e-5 s = 1e-9 turn
-  const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64);
+  const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64 ||
+                         method == PB200_SKYVIS_RECURRENCE_LIFT);
   const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
   if (want_rec && !uniform)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: recurrence kernel needs uniformly spaced channels");
@@ -624,8 +699,10 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   const int nchan_pad = nslab * PB200_SLAB;
   const int nsrc_pad = pb200_nsrc_pad(nsrc);
   void *geom, *dfreq;
-  int rc = pb_scratch(ctx, 2, sizeof(double) * 4 * (size_t)nsrc_pad, &geom);
+  int rc = pb_scratch(ctx, 2, sizeof(double) * 4 * (size_t)nsrc_pad + 16, &geom);
   if (rc) return rc;
+  unsigned* smax2_bits = reinterpret_cast<unsigned*>((double*)geom + 4 * (size_t)nsrc_pad);
+  PB_CUDA(ctx, cudaMemsetAsync(smax2_bits, 0, 16, stream));
   rc = pb_scratch(ctx, 3, sizeof(double) * (size_t)nchan_pad, &dfreq);
   if (rc) return rc;
   {
@@ -637,7 +714,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
     delete[] tmp;
     if (e != cudaSuccess) return pb_fail(ctx, PB200_ECUDA, "freq upload: %s", cudaGetErrorString(e));
   }
-  k_geom_stage<<<pb_div_up(nsrc_pad, 256), 256, 0, stream>>>(d_dircos, d_src_fwhm_deg, nsrc, nsrc_pad, (double*)geom);
+  k_geom_stage<<<pb_div_up(nsrc_pad, 256), 256, 0, stream>>>(d_dircos, d_src_fwhm_deg, nsrc, nsrc_pad, (double*)geom,
+                                                             h_pc[0], h_pc[1], h_pc[2], smax2_bits);
   PB_CHECK_LAUNCH(ctx, "k_geom_stage");
 
   SkyvisParams P;
@@ -645,6 +723,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   P.pc[0] = h_pc[0]; P.pc[1] = h_pc[1]; P.pc[2] = h_pc[2];
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
+  P.smax2_bits = smax2_bits;
+  P.lift = (method == PB200_SKYVIS_RECURRENCE_LIFT) ? 1 : 0;
   if (method == PB200_SKYVIS_FP64) {
     dim3 grid64(nslab, pb_div_up(nbl, BL64));
 #define LAUNCH64(AMP, TP)                                                                                     \

@@ -10,6 +10,9 @@ alt = NP.degrees(NP.arcsin(rng.uniform(0, 1, nsrc))); az = rng.uniform(0, 360, n
 dircos, idx = engine.sky_cull(NP.stack((alt, az), 1), 'altaz')
 amp = engine.dense_to_amp_table(torch.rand((nsrc, nchan), device='cuda'))
 bl = rng.normal(0, 150, (nbl, 3)); bl[:, 2] *= 0.01
+if nbl == 61075:      # the HERA-350 baselines of config 2 (sorted by length, as orient_and_sort_baselines leaves them)
+    from prisim_b200 import synthetic as S
+    bl = NP.asarray(S.config2(nsrc=16)['baselines'])
 freqs = 150e6 + (NP.arange(nchan) - nchan // 2) * 97656.25
 pc = NP.array([0, 0, 1.0])
 out = torch.empty((nbl, nchan), dtype=torch.complex128, device='cuda')
