@@ -156,13 +156,15 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
  *              anything else takes the direct (sincospi per term) kernel.
  *   d_src_fwhm_deg  NULL, or [nsrc] sqrt(major*minor) FWHM in degrees (:6267) -> taper on
  *   d_vis      [nbl,nchan] complex128, overwritten
- *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT
+ *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM
  */
 #define PB200_SKYVIS_AUTO       0
 #define PB200_SKYVIS_RECURRENCE 1
 #define PB200_SKYVIS_DIRECT     2
 #define PB200_SKYVIS_RECURRENCE_SCALAR 3   /* same algorithm with scalar FFMA instead of packed FFMA2 (A/B measurement) */
 #define PB200_SKYVIS_FP64       4           /* recurrence with every product and sum in fp64 (strongly cancelling skies) */
+#define PB200_SKYVIS_RECURRENCE_3TERM_SCALAR 7   /* the same with scalar FFMA */
+#define PB200_SKYVIS_RECURRENCE_3TERM 6    /* packed three-term recurrence Z_{j+1} = 2cos(2phi) Z_j - Z_{j-1} in 16-channel half blocks */
 #define PB200_SKYVIS_RECURRENCE_LIFT 5     /* packed recurrence with the 3-op lifted (shear) rotation on CTA rows of short baselines
                                               (A/B measurement: fewer FFMA2 and more accurate, but slower -- the loop is bound by
                                               register-file operand bandwidth, not by the FMA pipe) */

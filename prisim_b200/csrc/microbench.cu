@@ -168,6 +168,60 @@ __global__ void k_rot_packed_reuse(float* out, float x, float y, long long* cyc)
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1c - t0;
 }
 
+// 4c. the three-term packed loop of k_skyvis (Z_{j+1} = C Z_j - Z_{j-1}; accumulate A Z_j), 2 sources x 2 half blocks
+//     per iteration, 64 FFMA2-class issues per source.  VAR 0: as in the kernel (C a 32-bit splat, negated addend);
+//     1: C with distinct halves (full 64-bit operand); 2: no negation (Z_{j+1} = C Z_j + Z_{j-1}, diverges, timing only);
+//     3: accumulate only (no recurrence); 4: recurrence only (no accumulate)
+template <int VAR>
+__global__ void k_three_term(float* out, float x, float y, long long* cyc) {
+  float2 are[16], aim[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { are[j] = make_float2(0.f, 0.f); aim[j] = make_float2(0.f, 0.f); }
+  const float2 A0 = make_float2(threadIdx.x * 1e-4f + 1.f, 1.1f), A1 = make_float2(0.9f, threadIdx.x * 1e-4f + 1.f);
+  long long t0 = clock64();
+  for (int it = 0; it < ITER / 16; ++it) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float c = x + (it + s) * 1e-7f;
+      const float2 CC = VAR == 1 ? make_float2(c, c * 1.0000001f) : make_float2(c, c);
+      const float2 RR = make_float2(c * 0.5f, c * 0.5f), RI = make_float2(y, y), NRI = make_float2(-y, -y);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float2 PRm = make_float2(1.f, c), PIm = make_float2(0.f, y + h);
+        const float2 t1 = __fmul2_rn(PRm, RR), t2 = __fmul2_rn(PRm, RI);
+        float2 PRc = __ffma2_rn(PIm, NRI, t1), PIc = __ffma2_rn(PIm, RR, t2);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int j = h * 8 + 2 * k4;
+          if (k4 > 0 && VAR != 3) {
+            const float sg = VAR == 2 ? 1.f : -1.f;
+            const float2 PRn = __ffma2_rn(CC, PRc, make_float2(sg * PRm.x, sg * PRm.y));
+            const float2 PIn = __ffma2_rn(CC, PIc, make_float2(sg * PIm.x, sg * PIm.y));
+            PRm = __ffma2_rn(CC, PRn, make_float2(sg * PRc.x, sg * PRc.y));
+            PIm = __ffma2_rn(CC, PIn, make_float2(sg * PIc.x, sg * PIc.y));
+            const float2 tr = PRm, ti = PIm;
+            PRm = PRn; PIm = PIn; PRc = tr; PIc = ti;
+          }
+          if (VAR != 4) {
+            are[j] = __ffma2_rn(PRm, A0, are[j]);
+            aim[j] = __ffma2_rn(PIm, A0, aim[j]);
+            are[j + 1] = __ffma2_rn(PRc, A1, are[j + 1]);
+            aim[j + 1] = __ffma2_rn(PIc, A1, aim[j + 1]);
+          } else {
+            are[j].x += PRm.x + PIm.x + PRc.x + PIc.x;       // keep the chain alive (scalar FADDs, timing of VAR 4 is indicative only)
+          }
+        }
+      }
+    }
+  }
+  long long t1c = clock64();
+  float sum = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sum += are[j].x + are[j].y + aim[j].x + aim[j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1c - t0;
+}
+
 // 5. MUFU: sin.approx + cos.approx pairs (each = FMUL by 1/2pi + MUFU)
 __global__ void k_mufu(float* out, float x, float y, long long* cyc) {
   float acc[NCH];
@@ -421,6 +475,11 @@ int main() {
   rep("rotacc_packed_terms", run(k_rot_packed, blocks, threads, out, cyc), (double)(ITER / 4) * 16 * 2, "terms");
   rep("rotacc_packed_reuse_order_terms", run(k_rot_packed_reuse<0>, blocks, threads, out, cyc), (double)(ITER / 16) * 16 * 4 * 2, "terms");
   rep("rotacc_packed_reuse_order_lds_terms", run(k_rot_packed_reuse<1>, blocks, threads, out, cyc), (double)(ITER / 16) * 16 * 4 * 2, "terms");
+  rep("three_term_kernel_form_terms", run(k_three_term<0>, blocks, threads, out, cyc), (double)(ITER / 16) * 2 * 32, "terms");
+  rep("three_term_c64_terms", run(k_three_term<1>, blocks, threads, out, cyc), (double)(ITER / 16) * 2 * 32, "terms");
+  rep("three_term_noneg_terms", run(k_three_term<2>, blocks, threads, out, cyc), (double)(ITER / 16) * 2 * 32, "terms");
+  rep("three_term_acc_only_terms", run(k_three_term<3>, blocks, threads, out, cyc), (double)(ITER / 16) * 2 * 32, "terms");
+  rep("three_term_rec_only_terms", run(k_three_term<4>, blocks, threads, out, cyc), (double)(ITER / 16) * 2 * 32, "terms");
   rep("mufu_ex2", run(k_mufu, blocks, threads, out, cyc), (double)ITER * NCH, "mufu");
   rep("dfma", run(k_dfma, blocks, threads, out, cyc), (double)ITER * NCH, "dfma");
   rep("mix_ffma2x16_only", run(k_mix<0, 0, 0>, blocks, threads, out, cyc), (double)ITER * NCH * 2, "fma");

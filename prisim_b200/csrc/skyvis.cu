@@ -76,7 +76,6 @@ struct SkyvisParams {
   double f0, df;           // uniform channels: f_k = f0 + k df
   int nsrc_pad, nbl, nchan, nslab;
   int spc;                 // slabs per CTA of the launch that filled `accum` (finalize)
-  int lift;                // allow the lifted (3-shear) rotation on CTA rows whose step angle stays small
   const unsigned* smax2_bits;   // device: float bits of max_s |s - s_pc|^2 (k_geom_stage)
 };
 
@@ -197,8 +196,12 @@ __global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P, i
 // =================================================================================================
 // Recurrence kernel (uniform channel grid)
 // =================================================================================================
-template <int SPC, bool PACKED, bool TAPER>
+// MODE: phasor stepping of the channel loop -- 0 complex rotation by r^2 (4 ops per two channels), 1 lifted rotation
+// (3 shears) on CTA rows of short baselines, 2 three-term recurrence in 16-channel half blocks.  TAPER implies MODE 0.
+template <int SPC, bool PACKED, bool TAPER, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
+  static_assert(!TAPER || MODE == 0, "the taper folds into the complex rotation only");
+  static_assert(MODE != 1 || PACKED, "the lifted rotation is packed only");
   using S = Shape<SPC>;
   constexpr int WB = S::WB, WC = S::WC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -256,8 +259,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   // more accurate than the complex multiply while |phi| <= PB_LIFT_MAX_ANGLE (measured in tools/lift_accuracy.py);
   // tan blows up towards pi, so a CTA row uses it only if every (source, baseline) pair of the row stays below the
   // limit:  |phi| = 4 pi df |tau|,  |tau| <= |b|/c max_s |s - s_pc|.  The decision is CTA-uniform.
+  constexpr bool three_term = MODE == 2;
   bool lift_row = false;
-  if (PACKED && !TAPER && P.lift) {
+  if (MODE == 1) {
     const float smax2 = __uint_as_float(*P.smax2_bits);
     const double lim = PB_LIFT_MAX_ANGLE / (4.0 * 3.14159265358979323846 * fabs(df));
     lift_row = !__syncthreads_or(valid && G.blen2 * (double)smax2 > lim * lim);
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
       const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
       tpre[stage].tau[s][bcol] = tau;
-      float2 rp = rotation_phasor(tau * df);
+      float2 rp = rotation_phasor(three_term ? 2.0 * tau * df : tau * df);   // three-term rows: the two-channel rotation
       // lifted rows: shear coefficients of the two-channel step, t = -tan(phi) and s = sin(2 phi) for r = e^{i phi}
       if (lift_row) rp = make_float2(-__fdiv_rn(rp.y, rp.x), 2.0f * rp.x * rp.y);
       tpre[stage].rot[s][bcol] = rp;
@@ -415,10 +419,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     }
   };
 
+  // Three-term recurrence (method PB200_SKYVIS_RECURRENCE_3TERM): Z_{j+1} = 2 cos(2 phi) Z_j - Z_{j-1} on packed channel
+  // pairs Z_j = (z_2j, z_2j+1): ONE FFMA2 per component and step and no intermediate results, where the complex
+  // rotation needs two and writes two temporaries -- the loop is bound by register-file result bandwidth (DESIGN.md
+  // K1).  The recurrence error grows like (steps^2 / 2) * ulp(2 cos), so a 32-channel block is split into two
+  // 16-channel halves of 8 steps: Z_0 from two MUFU anchors (free: XU/FP64 pipes are idle), Z_1 = Z_0 r^2 by one
+  // complex rotation, Z_2..Z_7 by the recurrence.
+  auto run_tile3 = [&](int tile) {
+    // PACKED: FFMA2/FMUL2 on (even, odd) channel pairs; otherwise the same arithmetic as scalar FFMA on the two halves
+    auto fma2 = [](float2 a, float2 b, float2 c) { return PACKED ? __ffma2_rn(a, b, c) : make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); };
+    auto mul2 = [](float2 a, float2 b) { return PACKED ? __fmul2_rn(a, b) : make_float2(a.x * b.x, a.y * b.y); };
+    const int stage = tile & 1;
+    const TileIn<SPC>& ti = tin[stage];
+    const TilePre<SPC>& tp = tpre[stage];
+    constexpr int H = KT / 2;                            // channels per half block
+    auto anchors = [&](int s, float2 (&an)[4]) {
+      const double tau = tp.tau[s][bcol];
+      const double d = frac_turns(tau * df);
+      const double f0 = frac_turns(tau * fk0), fh = frac_turns(f0 + (double)H * d);
+      const float x0 = (float)(f0 * PB_INV_RCP2PI_F32), x1 = (float)((f0 + d) * PB_INV_RCP2PI_F32);
+      const float x2 = (float)(fh * PB_INV_RCP2PI_F32), x3 = (float)((fh + d) * PB_INV_RCP2PI_F32);
+      an[0] = make_float2(__cosf(x0), -__sinf(x0)); an[1] = make_float2(__cosf(x1), -__sinf(x1));
+      an[2] = make_float2(__cosf(x2), -__sinf(x2)); an[3] = make_float2(__cosf(x3), -__sinf(x3));
+    };
+    float2 an_next[4];
+    anchors(0, an_next);
+    float2 r_next = tp.rot[0][bcol];
+#pragma unroll 1
+    for (int chunk = 0; chunk < STAGGER; ++chunk) {
+    if (chunk == (warp >> 2) % STAGGER && tile + 1 < ntiles) precompute(tile + 1);
+#pragma unroll 2
+    for (int s = chunk * (T / STAGGER); s < (chunk + 1) * (T / STAGGER); ++s) {
+      float2 an[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) an[i] = an_next[i];
+      const float2 r = r_next;
+      const int sn = (s + 1 < T) ? s + 1 : s;
+      if (PB_ABLATE & 2) { an_next[0] = tp.rot[sn][bcol ^ 1]; an_next[1] = tp.rot[sn][bcol ^ 2]; an_next[2] = tp.rot[sn][bcol ^ 3]; an_next[3] = tp.rot[sn][bcol ^ 4]; }
+      else anchors(sn, an_next);
+      r_next = tp.rot[sn][bcol];
+      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KT]);
+      const float2 RR = make_float2(r.x, r.x), RI = make_float2(r.y, r.y), NRI = make_float2(-r.y, -r.y);
+      const float2 CC = make_float2(2.0f * r.x, 2.0f * r.x);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float2 PRm = make_float2(an[2 * h].x, an[2 * h + 1].x), PIm = make_float2(an[2 * h].y, an[2 * h + 1].y);   // Z_0
+        const float2 t1 = mul2(PRm, RR), t2 = mul2(PRm, RI);
+        float2 PRc = fma2(PIm, NRI, t1), PIc = fma2(PIm, RR, t2);                                       // Z_1
+#pragma unroll
+        for (int k4 = 0; k4 < H / 4; ++k4) {
+          const float4 a4 = (PB_ABLATE & 8) ? make_float4(r.x + 1.f, r.x + 2.f, r.y + 3.f, r.y + 4.f) : arow[h * (H / 4) + k4];
+          const float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w);
+          const int j = h * (H / 2) + 2 * k4;             // accumulator (channel pair) index of A0
+          if (k4 > 0) {                                   // advance two steps: (m, c) <- (c, C c - m), twice
+            const float2 PRn = fma2(CC, PRc, make_float2(-PRm.x, -PRm.y));
+            const float2 PIn = fma2(CC, PIc, make_float2(-PIm.x, -PIm.y));
+            PRm = fma2(CC, PRn, make_float2(-PRc.x, -PRc.y));
+            PIm = fma2(CC, PIn, make_float2(-PIc.x, -PIc.y));
+            // now (PRn, PIn) = Z_2k4 and (PRm, PIm) = Z_2k4+1: rename so that m < c again
+            const float2 tr = PRm, tii = PIm;
+            PRm = PRn; PIm = PIn; PRc = tr; PIc = tii;
+          }
+          acc_re[j] = fma2(PRm, A0, acc_re[j]);
+          acc_im[j] = fma2(PIm, A0, acc_im[j]);
+          acc_re[j + 1] = fma2(PRc, A1, acc_re[j + 1]);
+          acc_im[j + 1] = fma2(PIc, A1, acc_im[j + 1]);
+        }
+      }
+    }
+    }
+  };
+
   for (int tile = 0; tile < ntiles; ++tile) {
     if (!live && tile + 1 < ntiles) precompute(tile + 1);
     if (live) {
-      if (lift_row) run_tile(tile, std::integral_constant<bool, PACKED && !TAPER>());
+      if constexpr (MODE == 2) run_tile3(tile);
+      else if constexpr (MODE == 1) { if (lift_row) run_tile(tile, std::true_type()); else run_tile(tile, std::false_type()); }
       else run_tile(tile, std::false_type());
     }
     __syncthreads();                                   // tile consumed, next tile's tau/rot visible
@@ -675,7 +751,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   if (nsrc > 0 && (!d_dircos || !d_amp)) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: null source arrays");
   if (amp_dtype != PB200_AMP_F32 && !(amp_dtype == PB200_AMP_F64 && method == PB200_SKYVIS_FP64))
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: an fp64 amplitude table needs method PB200_SKYVIS_FP64");
-  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_LIFT)
+  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_3TERM_SCALAR)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -690,7 +766,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   for (int k = 0; k < nchan; ++k)
     if (fabs(h_freqs[k] - (h_freqs[0] + k * df)) > 1e-4) { uniform = false; break; }   // 1e-4 Hz * 1e-5 s = 1e-9 turn
   const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64 ||
-                         method == PB200_SKYVIS_RECURRENCE_LIFT);
+                         method == PB200_SKYVIS_RECURRENCE_LIFT || method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR);
   const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
   if (want_rec && !uniform)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: recurrence kernel needs uniformly spaced channels");
@@ -724,7 +800,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
   P.smax2_bits = smax2_bits;
-  P.lift = (method == PB200_SKYVIS_RECURRENCE_LIFT) ? 1 : 0;
+  const int mode = method == PB200_SKYVIS_RECURRENCE_LIFT ? 1 : (method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ? 2 : 0);
   if (method == PB200_SKYVIS_FP64) {
     dim3 grid64(nslab, pb_div_up(nbl, BL64));
 #define LAUNCH64(AMP, TP)                                                                                     \
@@ -754,7 +830,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   PB_CUDA(ctx, cudaMemsetAsync(accum, 0, ntile_out * KT * 32 * sizeof(double2), stream));
   P.accum = (double2*)accum;
   const bool taper = d_src_fwhm_deg != nullptr;
-  const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR;
+  const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR && method != PB200_SKYVIS_RECURRENCE_3TERM_SCALAR;
 #define LAUNCH(KERNEL, SMEM)                                                                              \
   do {                                                                                                    \
     PB_CUDA(ctx, cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
@@ -762,12 +838,20 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   } while (0)
 #define SMEM_REC(SPC) (NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) + \
                        (taper ? NSTAGE * sizeof(TileKap<SPC>) : 0))
-#define LAUNCH_REC(SPC)                                                     \
-  do {                                                                      \
-    if (packed && taper) LAUNCH((k_skyvis<SPC, true, true>), SMEM_REC(SPC));       \
-    else if (packed) LAUNCH((k_skyvis<SPC, true, false>), SMEM_REC(SPC));          \
-    else if (taper) LAUNCH((k_skyvis<SPC, false, true>), SMEM_REC(SPC));           \
-    else LAUNCH((k_skyvis<SPC, false, false>), SMEM_REC(SPC));                     \
+#define LAUNCH_REC(SPC)                                                                   \
+  do {                                                                                    \
+    if (taper) {                                                                          \
+      if (packed) LAUNCH((k_skyvis<SPC, true, true, 0>), SMEM_REC(SPC));                  \
+      else LAUNCH((k_skyvis<SPC, false, true, 0>), SMEM_REC(SPC));                        \
+    } else if (mode == 2) {                                                               \
+      if (packed) LAUNCH((k_skyvis<SPC, true, false, 2>), SMEM_REC(SPC));                 \
+      else LAUNCH((k_skyvis<SPC, false, false, 2>), SMEM_REC(SPC));                       \
+    } else if (mode == 1) {                                                               \
+      LAUNCH((k_skyvis<SPC, true, false, 1>), SMEM_REC(SPC));                             \
+    } else {                                                                              \
+      if (packed) LAUNCH((k_skyvis<SPC, true, false, 0>), SMEM_REC(SPC));                 \
+      else LAUNCH((k_skyvis<SPC, false, false, 0>), SMEM_REC(SPC));                       \
+    }                                                                                     \
   } while (0)
   if (direct) {
     const size_t smem = NSTAGE * sizeof(TileIn<1>) + 64 + PB200_SLAB * (sizeof(float) + sizeof(double));

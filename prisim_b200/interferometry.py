@@ -270,6 +270,7 @@ class InterferometerArray(object):
         # snapshot (and the following ones) runs in fp64 (DESIGN.md K1 "precision control")
         self.precision = "auto"
         self.cancel_ratio = 0.45
+        self.skyvis_method = "auto"                      # fp32 kernel variant (engine.skyvis method; A/B measurements)
         self.audit_baselines = 32                        # un-flagged baselines re-done in fp64 and compared per snapshot
         self.audit_tolerance = 0.8e-5                    # max |dV|/rms_b on the audited baselines before fp64 takes over
         self.precision_report = []                       # per snapshot: baselines recomputed in fp64
@@ -583,7 +584,8 @@ class InterferometerArray(object):
             self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl, "audited": 0, "audit_max_err": 0.0})
             return run64(self._d_bl)
         amp = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, **kw)
-        skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device)
+        skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device,
+                               method=self.skyvis_method)
         if self.precision == "auto" and uniform:
             # (1) cancellation test.  The fp32 kernel's absolute error on incoherent (point-source) skies is
             # ~1-3.5e-6 of the incoherent norm sqrt(mean_f sum_s a^2) (measured), the tolerance 1e-5 of each

@@ -350,7 +350,7 @@ def test_skyvis_random_shapes_property(eng):
 
     @settings(max_examples=14, deadline=None, suppress_health_check=list(HealthCheck))
     @given(nsrc=st.integers(1, 200), nbl=st.integers(1, 150), nchan=st.integers(2, 300), seed=st.integers(0, 10 ** 6),
-           method=st.sampled_from(["auto", "recurrence_lift", "recurrence_scalar", "direct", "fp64"]), spc=st.sampled_from(["1", "2", "4"]))
+           method=st.sampled_from(["auto", "recurrence_lift", "recurrence_3term", "recurrence_3term_scalar", "recurrence_scalar", "direct", "fp64"]), spc=st.sampled_from(["1", "2", "4"]))
     def check(nsrc, nbl, nchan, seed, method, spc):
         rng = NP.random.default_rng(seed)
         bl = rng.normal(0, 80.0, (nbl, 3)); bl[:, 2] *= 0.05
