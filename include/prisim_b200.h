@@ -142,6 +142,12 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
                     const pb200_spectrum_desc* spec, const pb200_beam_desc* beam, const double* d_pbeam,
                     const double* h_freqs, int nchan, int amp_dtype, void* d_amp, void* stream);
 
+/* d_amp_out = d_amp_in with source row s multiplied by d_scale[s * scale_stride] (fp64, device); in place allowed.
+ * With d_scale = one column of d_dircos (stride 3) the scaled table fed to pb200_skyvis gives one component of the
+ * visibility gradient w.r.t. the baseline vector, gradient_mode='baseline' (interferometry.py:6312-6343).       */
+int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsrc, int nchan, const double* d_scale,
+                    int scale_stride, void* d_amp_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * The phase sum.  Replaces interferometry.py:6155-6165 (phase-centre delays), :6255 +
  * baseline_delay_horizon.py:240 (geometric delays), :6258-6283 (extended-source taper) and

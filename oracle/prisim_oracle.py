@@ -519,20 +519,24 @@ def source_taper(baseline_lengths, geometric_delays, channels, src_shape):
 
 
 def skyvis_snapshot(baselines_enu, skypos_altaz_roi, pbfluxes, channels, pc_altaz, src_shape=None,
-                    max_slab_bytes=2.0e8):
+                    max_slab_bytes=2.0e8, gradient=False):
     """The phase-sum DFT of one snapshot, interferometry.py:6155-6165 (phase-centre delays),
     :6255 (geometric delays), :6332 + :6340 (phase matrix, sum over sources), evaluated over
     source slabs like the reference's low-memory branch :6348-6376.
 
     baselines_enu [nbl,3] m, skypos_altaz_roi [nsrc,2] deg, pbfluxes [nsrc,nchan], channels [nchan]
-    Hz, pc_altaz [2] deg.  Returns complex128 [nbl, nchan]."""
+    Hz, pc_altaz [2] deg.  Returns complex128 [nbl, nchan]; with ``gradient=True`` also the
+    visibility gradient w.r.t. the baseline vector, G[i,b,f] = sum_s dircos_s[i] * (term of V)
+    (gradient_mode='baseline', :6338 / :6343), complex128 [3, nbl, nchan]."""
     baselines_enu = NP.asarray(baselines_enu, dtype=NP.float64)
     channels = NP.asarray(channels, dtype=NP.float64)
     nbl, nchan = baselines_enu.shape[0], channels.size
     skyvis = NP.zeros((nbl, nchan), dtype=NP.complex128)
     nsrc = skypos_altaz_roi.shape[0]
+    grad = NP.zeros((3, nbl, nchan), dtype=NP.complex128)
     if nsrc == 0:                                                   # :6378-6382
-        return skyvis
+        return (skyvis, grad) if gradient else skyvis
+    skypos_dircos_roi = altaz2dircos(skypos_altaz_roi, "degrees")   # :6263
     pc_dircos = altaz2dircos(pc_altaz, "degrees")                   # :6164
     pc_delay_offsets = geometric_delay(baselines_enu, pc_dircos, altaz=False, hadec=False, dircos=True)   # :6165
     geometric_delays = geometric_delay(baselines_enu, skypos_altaz_roi, altaz=True, hadec=False)          # :6255
@@ -547,12 +551,31 @@ def skyvis_snapshot(baselines_enu, skypos_altaz_roi, pbfluxes, channels, pc_alta
             vis_wts = source_taper(baseline_lengths, geometric_delays[sl], channels, src_shape[sl])
             term = term * vis_wts                                   # :6335
         skyvis += NP.sum(term, axis=0)
-    return skyvis
+        if gradient:                                                # :6338, :6343
+            grad += NP.sum(skypos_dircos_roi[sl, :, NP.newaxis, NP.newaxis] * term[:, NP.newaxis, :, :], axis=0)
+    return (skyvis, grad) if gradient else skyvis
+
+
+def apply_gradients(gradient_baseline, perturbations, channels):
+    """First-order perturbed visibilities, interferometry.py:6811-6819:
+    dV = -i 2 pi / lambda * sum_i db[..., i, b] G[i, b, f, t].  gradient_baseline [3,nbl,nchan,nsnap],
+    perturbations [..., 3, nbl] (metres) -> [..., nbl, nchan, nsnap]."""
+    pert = NP.asarray(perturbations, dtype=NP.float64)
+    if pert.ndim == 2:
+        pert = pert[NP.newaxis, ...]
+    inpshape = pert.shape
+    pert = pert.reshape(-1, inpshape[-2], inpshape[-1])
+    if pert.shape[1] < 3:                                           # :6801-6806 zero-fill missing axes
+        pert = NP.concatenate((pert, NP.zeros((pert.shape[0], 3 - pert.shape[1], pert.shape[2]))), axis=1)
+    pert = pert[:, :3, :]
+    wl = FCNST.c / NP.asarray(channels, dtype=NP.float64)
+    out = -1j * 2.0 * NP.pi / wl.reshape(1, 1, -1, 1) * NP.sum(pert[..., NP.newaxis, NP.newaxis] * gradient_baseline[NP.newaxis, ...], axis=1)
+    return out.reshape(tuple(inpshape[:-2]) + gradient_baseline.shape[1:])
 
 
 def observe_snapshot(baselines_enu, channels, skypos, skycoords, latitude, pointing_center, pointing_coords,
                      telescope, flux_scale, spindex, freq_ref, flux_offset=None, src_shape=None,
-                     pb_info=None, roi_radius=None, roi_info=None, lst=None):
+                     pb_info=None, roi_radius=None, roi_info=None, lst=None, gradient=False):
     """One pass of InterferometerArray.observe (interferometry.py:5874-6410) for a power-law
     sky given in 'hadec' or 'altaz' coordinates (degrees).  Returns (skyvis [nbl,nchan], m2)."""
     skypos = NP.asarray(skypos, dtype=NP.float64)
@@ -587,7 +610,7 @@ def observe_snapshot(baselines_enu, channels, skypos, skycoords, latitude, point
                                     freq_scale="GHz")
     pbfluxes = pb * fluxes                                          # :6254
     shp = None if src_shape is None else NP.asarray(src_shape, dtype=NP.float64)[m2]
-    return skyvis_snapshot(baselines_enu, skypos_altaz_roi, pbfluxes, channels, pc_altaz, src_shape=shp), m2
+    return skyvis_snapshot(baselines_enu, skypos_altaz_roi, pbfluxes, channels, pc_altaz, src_shape=shp, gradient=gradient), m2
 
 
 # --------------------------------------------------------------------------------------------

@@ -184,7 +184,47 @@ __global__ void __launch_bounds__(AMP_THREADS) k_amp_table(const AmpParams P) {
 
 }  // namespace
 
+// out[slab][s][c] = in[slab][s][c] * scale[s * stride]: the amplitude table of one component of the visibility
+// gradient w.r.t. the baseline vector (interferometry.py:6343: dircos[s, i] * pbfluxes[s, f])
+template <typename T>
+__global__ void k_amp_scale(const T* __restrict__ in, const double* __restrict__ scale, int stride, int nsrc,
+                            int nsrc_pad, int nslab, T* __restrict__ out) {
+  const size_t n4 = (size_t)nslab * nsrc_pad * (PB200_SLAB / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)((i / (PB200_SLAB / 4)) % nsrc_pad);
+    const double f = s < nsrc ? scale[(size_t)s * stride] : 0.0;
+    if (sizeof(T) == 4) {
+      float4 v = reinterpret_cast<const float4*>(in)[i];
+      v.x = (float)(v.x * f); v.y = (float)(v.y * f); v.z = (float)(v.z * f); v.w = (float)(v.w * f);
+      reinterpret_cast<float4*>(out)[i] = v;
+    } else {
+      double4 v = reinterpret_cast<const double4*>(in)[i];
+      v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+      reinterpret_cast<double4*>(out)[i] = v;
+    }
+  }
+}
+
 extern "C" {
+
+int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsrc, int nchan, const double* d_scale,
+                    int scale_stride, void* d_amp_out, void* stream_) {
+  if (!ctx) return PB200_EINVAL;
+  if (nsrc <= 0 || nchan <= 0 || !d_amp_in || !d_amp_out || !d_scale || scale_stride <= 0)
+    return pb_fail(ctx, PB200_EINVAL, "pb200_amp_scale: bad arguments");
+  if (amp_dtype != PB200_AMP_F32 && amp_dtype != PB200_AMP_F64)
+    return pb_fail(ctx, PB200_EINVAL, "pb200_amp_scale: amp_dtype must be PB200_AMP_F32 or PB200_AMP_F64");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int nslab = (nchan + PB200_SLAB - 1) / PB200_SLAB, nsrc_pad = pb200_nsrc_pad(nsrc);
+  const int blocks = ctx->sm_count * 8;
+  if (amp_dtype == PB200_AMP_F32)
+    k_amp_scale<float><<<blocks, 256, 0, stream>>>((const float*)d_amp_in, d_scale, scale_stride, nsrc, nsrc_pad, nslab, (float*)d_amp_out);
+  else
+    k_amp_scale<double><<<blocks, 256, 0, stream>>>((const double*)d_amp_in, d_scale, scale_stride, nsrc, nsrc_pad, nslab, (double*)d_amp_out);
+  PB_CHECK_LAUNCH(ctx, "k_amp_scale");
+  return PB200_OK;
+}
 
 int pb200_nsrc_pad(int nsrc) { return ((nsrc + PB200_SRC_TILE - 1) / PB200_SRC_TILE) * PB200_SRC_TILE; }
 

@@ -101,6 +101,19 @@ def amp_table(dircos, index, nsrc, spectrum, beam, freqs_hz, pbeam=None, device=
     return amp
 
 
+def amp_scale(amp, nsrc, nchan, dircos, component, out=None, device=None):
+    """``pb200_amp_scale``: the amplitude table with source row s multiplied by dircos[s, component] -- the table of
+    one component of the visibility gradient w.r.t. the baseline vector (interferometry.py:6343)."""
+    device = _dev(device)
+    ctx = get_context(device)
+    if out is None:
+        out = torch.empty_like(amp)
+    amp_dtype = _lib.AMP_F64 if amp.dtype == torch.float64 else _lib.AMP_F32
+    col = C.c_void_p(dircos.data_ptr() + 8 * int(component))
+    ctx.check(ctx.lib.pb200_amp_scale(ctx.handle, _ptr(amp), amp_dtype, int(nsrc), int(nchan), col, 3, _ptr(out), ctx.stream()))
+    return out
+
+
 def amp_table_to_dense(amp, nsrc, nchan):
     """Undo the slab layout: returns a [nsrc, nchan] tensor of the table's dtype (testing / inspection)."""
     nsrc_pad = ((max(nsrc, 1) + _lib.SRC_TILE - 1) // _lib.SRC_TILE) * _lib.SRC_TILE

@@ -13,7 +13,7 @@ Deliberate deviations from the reference (documented in DESIGN.md):
     input producer outside the parity boundary.  'altaz' sky coordinates are accepted (the
     reference raises NameError, Appendix C #2).
   * ``geometric_delays`` is never materialised (Appendix C #4); ``memsave`` is ignored (fp64 path
-    is the parity target); ``gradient_mode`` raises NotImplementedError (out of scope).
+    is the parity target); ``gradient_mode='baseline'`` fills ``gradient`` (three more phase sums).
   * noise uses a counter-based Philox generator instead of numpy's global state (Appendix C #16).
 """
 from __future__ import annotations
@@ -206,7 +206,7 @@ class InterferometerArray(object):
             self.bl_reversemap = blgroupinfo["reversemap"]
         self.latitude, self.longitude, self.altitude = latitude, longitude, altitude
         self.gradient_mode = None
-        self.gradient = {}
+        self._gradient = []                              # per snapshot [3, nbl, nchan] complex128 (gradient_mode='baseline')
         self.gaininfo = None
         scale = {None: 1.0, "hz": 1.0, "ghz": 1.0e9, "mhz": 1.0e6, "khz": 1.0e3}                # :5772-5786
         key = freq_scale.lower() if isinstance(freq_scale, str) else freq_scale
@@ -365,6 +365,57 @@ class InterferometerArray(object):
     def lag_kernel(self):
         return self._stack(self._lag.get("kernel", []), expand=True)
 
+    @property
+    def gradient(self):
+        """{} or {'baseline': [3, nbl, nchan, nsnap] complex128} (interferometry.py:4834-4845, :6386-6394)."""
+        if self.gradient_mode is None or not self._gradient:
+            return {}
+        return {self.gradient_mode: torch.stack(self._gradient, dim=3).cpu().numpy()}
+
+    def apply_gradients(self, gradient_mode=None, perturbations=None):
+        """First-order perturbed visibilities from the stored gradient, same call as interferometry.py:6726-6819:
+        perturbations = {'baseline': [..., 3, nbl] metres} -> [..., nbl, nchan, nsnap] complex128."""
+        if gradient_mode is None:
+            gradient_mode = self.gradient_mode
+        if perturbations is None:
+            perturbations = {gradient_mode: NP.zeros((1, 1, 1))}
+        if self.gradient_mode is None or not self._gradient:
+            raise AttributeError("No gradient attribute found")
+        if not isinstance(perturbations, dict):
+            raise TypeError("Input perturbations must be a dictionary")
+        if not isinstance(gradient_mode, str):
+            raise TypeError("Input gradient_mode must be a string")
+        if gradient_mode not in ["baseline"]:
+            raise KeyError("Specified gradient mode {0} not currently supported".format(gradient_mode))
+        if gradient_mode not in perturbations:
+            raise KeyError("{0} key not found in input perturbations".format(gradient_mode))
+        if gradient_mode != self.gradient_mode:
+            raise ValueError("Specified gradient mode {0} not found in attribute".format(gradient_mode))
+        pert = perturbations[gradient_mode]
+        if not isinstance(pert, NP.ndarray):
+            raise TypeError("Perturbations must be specified as a numpy array")
+        if pert.ndim == 2:
+            pert = pert[NP.newaxis, ...]
+        if pert.ndim < 2:
+            raise ValueError("Perturbations must be two--dimensions or higher")
+        inpshape = pert.shape
+        pert = pert.reshape(-1, inpshape[-2], inpshape[-1])
+        nbl, nchan = self.baselines.shape[0], self.channels.size
+        if pert.shape[2] != nbl:
+            raise ValueError("Number of {0} perturbations not equal to that in the gradient attribute".format(gradient_mode))
+        if pert.shape[1] < 3:                                                          # :6801-6806
+            warnings.warn("Only {0}-dimensional coordinates specified. Proceeding with zero perturbations in other coordinate axes.".format(pert.shape[1]))
+            pert = NP.concatenate((pert, NP.zeros((pert.shape[0], 3 - pert.shape[1], nbl))), axis=1)
+        elif pert.shape[1] > 3:                                                        # :6807-6809
+            warnings.warn("{0}-dimensional coordinates specified. Proceeding with only the first three dimensions of coordinate axes.".format(3))
+            pert = pert[:, :3, :]
+        p = engine._f64(NP.ascontiguousarray(pert), self.device).to(torch.complex128)   # [nseed, 3, nbl]
+        k = torch.as_tensor(-2.0j * NP.pi * self.channels / FCNST.c, device=self._dev_str())   # -i 2 pi / lambda   :6811
+        out = torch.empty((pert.shape[0], nbl, nchan, len(self._gradient)), dtype=torch.complex128, device=self._dev_str())
+        for t, G in enumerate(self._gradient):                                         # :6813
+            out[:, :, :, t] = torch.einsum("sib,ibf->sbf", p, G) * k[None, None, :]
+        return out.cpu().numpy().reshape(tuple(inpshape[:-2]) + (nbl, nchan, len(self._gradient)))
+
     def skyvis_freq_device(self, snapshot=-1):
         """The [nbl,nchan] complex128 CUDA tensor of one snapshot (no copy)."""
         return self._skyvis[snapshot]
@@ -397,8 +448,15 @@ class InterferometerArray(object):
                 gradient_mode=None, memsave=False, vmemavail=None, store_prev_skymodel_file=None):
         """One snapshot; same arguments as interferometry.py:5874-5878."""
         nbl, nchan = self.baselines.shape[0], self.channels.size
-        if gradient_mode is not None:
-            raise NotImplementedError("gradient_mode is outside the hot-path scope (SURVEY.md section 2)")
+        if gradient_mode is not None:                                                  # :6306-6311
+            if not isinstance(gradient_mode, str):
+                raise TypeError("Input gradient_mode must be a string")
+            if gradient_mode.lower() not in ["baseline", "skypos", "frequency"]:
+                raise ValueError("Invalid value specified in input gradient_mode")
+            if gradient_mode.lower() != "baseline":
+                raise NotImplementedError("only gradient_mode='baseline' is computed (as in the reference, :6312)")
+            if self.gradient_mode is None:
+                self.gradient_mode = gradient_mode
         bandpass = NP.asarray(bandpass)
         if bandpass.ndim == 1:                                                         # :5993-5996
             if bandpass.size != nchan:
@@ -545,11 +603,13 @@ class InterferometerArray(object):
             fwhm = None
             if "fwhm" in sky:                                                          # :6258-6267
                 fwhm = sky["fwhm"].index_select(0, index.to(torch.int64)).contiguous()
-            skyvis = self._phase_sum(dircos, index, nsrc, sky["spec"], beam, pbeam, pc_dircos, fwhm)
+            skyvis, grad = self._phase_sum(dircos, index, nsrc, sky["spec"], beam, pbeam, pc_dircos, fwhm,
+                                           gradient=gradient_mode is not None)
             self.obs_catalog_indices = self.obs_catalog_indices + [index.cpu().numpy().astype(NP.int64)]   # :6377
         else:                                                                          # :6378-6382
             warnings.warn("No sources found in the catalog within matching radius. Simply populating the observed visibilities and/or gradients with noise.")
             skyvis = torch.zeros((nbl, nchan), dtype=torch.complex128, device=self._dev_str())
+            grad = torch.zeros((3, nbl, nchan), dtype=torch.complex128, device=self._dev_str()) if gradient_mode is not None else None
 
         # bookkeeping (:6103-6108, :6384-6399)
         if not self.timestamp:
@@ -559,6 +619,8 @@ class InterferometerArray(object):
             self.pointing_center = NP.vstack((self.pointing_center, pointing_center))
             self.phase_center = NP.vstack((self.phase_center, pointing_center))
         self._skyvis.append(skyvis)
+        if gradient_mode is not None:                                                  # :6386-6394
+            self._gradient.append(grad)
         self._bp.append(bp_t)
         self._Tsys.append(Tsys_t)
         self.Tsysinfo += [Tsysinfo]
@@ -568,8 +630,12 @@ class InterferometerArray(object):
         self.n_acc += 1
         self.lst = self.lst + [lst]
 
-    def _phase_sum(self, dircos, index, nsrc, spec, beam, pbeam, pc_dircos, fwhm):
-        """Amplitude table + phase sum with precision control (see `precision` in __init__)."""
+    def _phase_sum(self, dircos, index, nsrc, spec, beam, pbeam, pc_dircos, fwhm, gradient=False):
+        """Amplitude table + phase sum with precision control (see `precision` in __init__).  Returns (V, G): G is the
+        [3, nbl, nchan] gradient of V w.r.t. the baseline vector (three more phase sums over the amplitude table scaled
+        by one direction cosine each, interferometry.py:6338/:6343) or None.  Unlike the reference -- whose gradient
+        branch reads direction cosines that only exist when the sky model has src_shape (:6263) -- it is also computed
+        for point-source skies.  Each gradient component goes through the same precision control as V."""
         nbl, nchan = self.baselines.shape[0], self.channels.size
         kw = dict(pbeam=pbeam, device=self.device)
         uniform = nchan < 3 or NP.allclose(NP.diff(self.channels), self.freq_resolution, rtol=0, atol=1e-4)
@@ -580,17 +646,32 @@ class InterferometerArray(object):
             return engine.skyvis(dircos, amp64, nsrc, bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, method="fp64",
                                  device=self.device)
 
+        def scaled(amp_any, i):
+            return engine.amp_scale(amp_any, nsrc, nchan, dircos, i, device=self.device)
+
         if uniform and (self.precision == "fp64" or (self.precision == "auto" and self._fp64_sticky)):
             self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl, "audited": 0, "audit_max_err": 0.0})
-            return run64(self._d_bl)
+            amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+            grad = torch.stack([run64(self._d_bl, scaled(amp64, i)) for i in range(3)]) if gradient else None
+            return run64(self._d_bl, amp64), grad
         amp = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, **kw)
-        skyvis = engine.skyvis(dircos, amp, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device,
-                               method=self.skyvis_method)
-        if self.precision == "auto" and uniform:
+        amp64_cache = {}
+
+        def amp64_table():
+            if "t" not in amp64_cache:
+                amp64_cache["t"] = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+            return amp64_cache["t"]
+
+        def certified(amp32, amp64_fn, report):
+            """fp32 phase sum of one amplitude table + the 'auto' cancellation test and fp64 audit."""
+            skyvis = engine.skyvis(dircos, amp32, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device,
+                                   method=self.skyvis_method)
+            if not (self.precision == "auto" and uniform):
+                return skyvis
             # (1) cancellation test.  The fp32 kernel's absolute error on incoherent (point-source) skies is
             # ~1-3.5e-6 of the incoherent norm sqrt(mean_f sum_s a^2) (measured), the tolerance 1e-5 of each
             # baseline's rms: baselines whose spectrum cancels below cancel_ratio x that norm go to fp64.
-            a2 = torch.sqrt(amp.double().square().sum() / nchan)
+            a2 = torch.sqrt(amp32.double().square().sum() / nchan)
             rms_b = torch.sqrt(skyvis.real.square().mean(dim=1) + skyvis.imag.square().mean(dim=1))
             low = rms_b < self.cancel_ratio * a2
             flagged = torch.nonzero(low).flatten()
@@ -608,7 +689,7 @@ class InterferometerArray(object):
             audit_err, audited = 0.0, int(sel.numel())
             both = torch.cat((flagged, sel))
             if both.numel() > 0:
-                amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
+                amp64 = amp64_fn()
                 ref = run64(self._d_bl.index_select(0, both).contiguous(), amp64)
                 if audited:
                     ref_a, got = ref[nflag:], skyvis.index_select(0, sel)
@@ -618,9 +699,16 @@ class InterferometerArray(object):
                 if audit_err > self.audit_tolerance:          # fp32 is not good enough on this sky: everything in fp64
                     skyvis.index_copy_(0, keep, run64(self._d_bl.index_select(0, keep).contiguous(), amp64))
                     nflag = nbl
-            self.precision_report.append({"fp64_baselines": nflag, "nbl": nbl, "audited": audited, "audit_max_err": audit_err})
-            self._fp64_sticky = nflag > 0.5 * nbl
-        return skyvis
+            if report:
+                self.precision_report.append({"fp64_baselines": nflag, "nbl": nbl, "audited": audited, "audit_max_err": audit_err})
+                self._fp64_sticky = nflag > 0.5 * nbl
+            return skyvis
+
+        skyvis = certified(amp, amp64_table, True)
+        grad = None
+        if gradient:      # every component is certified like V itself (the l and m weights change sign over the sky: they cancel more)
+            grad = torch.stack([certified(scaled(amp, i), lambda i=i: scaled(amp64_table(), i), False) for i in range(3)])
+        return skyvis, grad
 
     # ------------------------------------------------------------------ observing_run
     def observing_run(self, pointing_init, skymodel, t_acc, duration, channels, bpass, Tsys, lst_init, roi_radius=None,
@@ -809,6 +897,8 @@ class InterferometerArray(object):
             getter = self._freq_wts_getter(delay_transform["freq_wts"])
         for t in range(nres):
             prod = {"skyvis_freq": self._skyvis[t]}
+            if self._gradient:
+                prod["gradient_" + self.gradient_mode] = self._gradient[t]
             if noise:
                 rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
                                           self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
@@ -822,7 +912,7 @@ class InterferometerArray(object):
                     prod[key.replace("_freq", "_lag")] = engine.delay_transform(prod[key], self._bp[t], wts, self.freq_resolution,
                                                                                pad=pad, downsample=True)
             sink(base + t, prod)
-        self._skyvis, self._vis, self._noise, self._rms, self._bp, self._Tsys = [], [], [], [], [], []
+        self._skyvis, self._vis, self._noise, self._rms, self._bp, self._Tsys, self._gradient = [], [], [], [], [], [], []
         self._lag = {}
         self._drained = base + nres
         return nres

@@ -26,6 +26,9 @@ from scipy import interpolate
 
 REF = "/root/reference/prisim"
 OUT = os.path.dirname(os.path.abspath(__file__))
+# `make_golden.py tag1 tag2 ...` rewrites only those files (every case still runs, so the shared random stream --
+# and with it every other file's content -- is unchanged); no arguments = all files
+ONLY = set(sys.argv[1:])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,13 +235,15 @@ def main():
                                                           pointing_info={"delays": delays.copy()})
     beams["pb_mwa_tile_pointing"] = PB.primary_beam_generator(altaz.copy(), freqs_ghz.copy(), dict(mwa_el), skyunits="altaz",
                                                             pointing_info={"pointing_center": NP.asarray([52.806, 101.31]), "pointing_coords": "altaz"})
-    NP.savez_compressed(os.path.join(OUT, "beams.npz"), altaz=altaz, freqs_ghz=freqs_ghz, pc_altaz=pc_altaz,
+    if not ONLY or "beams" in ONLY:
+      NP.savez_compressed(os.path.join(OUT, "beams.npz"), altaz=altaz, freqs_ghz=freqs_ghz, pc_altaz=pc_altaz,
                         element_locs=element_locs, tile_delays=delays, **beams)
 
     # ---------------- geometric delays (baseline_delay_horizon.py executed as is) ----------------
     bl = rng.normal(0, 120.0, (9, 3)); bl[:, 2] *= 0.02
     hadec = NP.stack((rng.uniform(0, 360, 25), rng.uniform(-80, 40, 25)), axis=1)
-    NP.savez_compressed(os.path.join(OUT, "delays.npz"), bl=bl, altaz=altaz, hadec=hadec, latitude=lat,
+    if not ONLY or "delays" in ONLY:
+      NP.savez_compressed(os.path.join(OUT, "delays.npz"), bl=bl, altaz=altaz, hadec=hadec, latitude=lat,
                         tau_altaz=DLY.geometric_delay(bl, altaz, altaz=True, hadec=False),
                         tau_hadec=DLY.geometric_delay(bl, hadec, altaz=False, hadec=True, latitude=lat),
                         tau_dircos=DLY.geometric_delay(bl, altaz2dircos(altaz, "degrees"), altaz=False, hadec=False, dircos=True),
@@ -246,7 +251,7 @@ def main():
 
     # ---------------- InterferometerArray.observe / generate_noise / add_noise / delay_transform ----------------
     def run_observe(tag, telescope, src_shape=None, roi_radius=None, pb_info=None, nbl=12, nchan=32, nsrc0=150, nsnap=3,
-                    pointing_coords="hadec", roi_info_from_beam=False):
+                    pointing_coords="hadec", roi_info_from_beam=False, gradient_mode=None):
         bl = rng.normal(0, 60.0, (nbl, 3)); bl[:, 2] *= 0.02
         bl[0] = [14.6, 0.0, 0.0]
         chans = 150e6 + (NP.arange(nchan) - nchan // 2) * 100e3
@@ -281,9 +286,20 @@ def main():
                 rec["roi_ind_{0}".format(j)] = ind
                 rec["roi_pbeam_{0}".format(j)] = pbt.astype(NP.float32)
             ia.observe(TimeObj(2451545.0 + j * 0.01, lsts[j]), Tsysinfo, bandpass, pointing, sky, t_acc[j], pb_info=pb_info,
-                       roi_radius=roi_radius, **kw)
+                       roi_radius=roi_radius, gradient_mode=gradient_mode, **kw)
             rec["hadec_{0}".format(j)] = hadec_j
             rec["m2_{0}".format(j)] = NP.asarray(ia.obs_catalog_indices[-1]) if len(ia.obs_catalog_indices) > j else NP.zeros(0, dtype=int)
+        if gradient_mode is not None:
+            # visibility gradient w.r.t. baseline vectors (interferometry.py:6312-6343, :6384-6394) and the first-order
+            # perturbed visibilities apply_gradients() builds from it (:6726-6819)
+            pert = rng.normal(0, 0.02, (2, 3, nbl))
+            # apply_gradients reads self.labels.size / self.lst.size (:6816), i.e. it expects the array attributes of an
+            # object re-loaded from disk; observe() leaves them as lists
+            keep = ia.labels, ia.lst
+            ia.labels, ia.lst = NP.arange(nbl), NP.asarray(ia.lst)          # one label per baseline (a record array in the reference)
+            delta = ia.apply_gradients(gradient_mode="baseline", perturbations={"baseline": pert.copy()})
+            ia.labels, ia.lst = keep
+            rec.update(gradient_baseline=ia.gradient["baseline"], perturbations=pert, delta_skyvis_freq=delta)
         NP.random.seed(1234 + len(tag))
         ia.generate_noise()
         ia.add_noise()
@@ -299,8 +315,9 @@ def main():
         rec["skyvis_lag_pad0"] = ia.skyvis_lag
         ia.delay_transform(pad=0.5, freq_wts=window, verbose=False)
         rec["skyvis_lag_pad05"] = ia.skyvis_lag
-        NP.savez_compressed(os.path.join(OUT, "observe_{0}.npz".format(tag)), **rec)
-        if tag == "hera":
+        if not ONLY or tag in ONLY:
+            NP.savez_compressed(os.path.join(OUT, "observe_{0}.npz".format(tag)), **rec)
+        if tag == "hera" and (not ONLY or "rotate_hera" in ONLY):
             # rotate_visibilities = phase_centering + project_baselines (interferometry.py:7655-7995), twice:
             # to a fixed HA/Dec, then to an RA/Dec that differs per snapshot
             rot = {}
@@ -323,6 +340,9 @@ def main():
                                            "groundplane": None}, pointing_coords="altaz", nsnap=2)
     run_observe("mwa_dipole", {"id": "mwa_dipole", "shape": "dipole", "size": 0.74, "orientation": NP.asarray([1.0, 0.0, 0.0]),
                                "ocoords": "dircos", "groundplane": 0.3}, nsnap=2)
+    # gradient_mode='baseline' only runs in the reference when the sky model has src_shape: the direction cosines it
+    # multiplies by are assigned inside the taper branch (interferometry.py:6263) and are unbound otherwise (:6343)
+    run_observe("hera_taper_gradient", hera, src_shape=0.6, gradient_mode="baseline", nsnap=2)
     print("golden vectors written to", OUT)
 
 

@@ -46,12 +46,29 @@ def test_observe_noise_delay_against_reference_golden(tag):
         if "roi_ind_{0}".format(j) in g.files:
             kw["roi_info"] = {"ind": g["roi_ind_{0}".format(j)], "pbeam": g["roi_pbeam_{0}".format(j)]}
         ia.observe(SimpleTime(2451545.0 + j * 0.01, float(g["lsts"][j])), Tsysinfo, g["bandpass"], g["pointing"], SkyModel(init_parms=parms),
-                   float(g["t_acc"][j]), roi_radius=case.get("roi_radius", None), **kw)
+                   float(g["t_acc"][j]), roi_radius=case.get("roi_radius", None),
+                   gradient_mode="baseline" if "gradient_baseline" in g.files else None, **kw)
         assert NP.array_equal(ia.obs_catalog_indices[j], g["m2_{0}".format(j)])
     assert ia.n_acc == int(g["n_acc"]) and NP.isclose(ia.t_obs, float(g["t_obs"]))
     assert NP.allclose(ia.pointing_center, g["pointing_center"])
     assert rel_err(ia.skyvis_freq, g["skyvis_freq"]) <= TOL
     assert NP.allclose(ia.Tsys, g["Tsys"]) and NP.allclose(ia.bp, g["bp"])
+    if "gradient_baseline" in g.files:       # gradient_mode='baseline' (:6312-6343) and apply_gradients (:6726-6819)
+        G = ia.gradient["baseline"]
+        assert G.shape == g["gradient_baseline"].shape and ia.gradient_mode == "baseline"
+        for i in range(3):
+            assert rel_err(G[i], g["gradient_baseline"][i]) <= TOL
+        dV = ia.apply_gradients(perturbations={"baseline": g["perturbations"].copy()})
+        assert dV.shape == g["delta_skyvis_freq"].shape
+        assert rel_err(dV.reshape((-1,) + dV.shape[2:]), g["delta_skyvis_freq"].reshape((-1,) + dV.shape[2:])) <= TOL
+        with pytest.raises(KeyError):
+            ia.apply_gradients(gradient_mode="baseline", perturbations={"skypos": NP.zeros((3, nbl))})
+        with pytest.raises(ValueError):
+            ia.apply_gradients(perturbations={"baseline": NP.zeros((3, nbl + 1))})
+    else:
+        assert ia.gradient == {}
+        with pytest.raises(AttributeError):
+            ia.apply_gradients(perturbations={"baseline": NP.zeros((3, nbl))})
     ia.generate_noise()
     ia.add_noise()
     assert NP.allclose(ia.vis_rms_freq, g["vis_rms_freq"], rtol=1e-12)
@@ -75,6 +92,45 @@ def test_observe_noise_delay_against_reference_golden(tag):
     res2 = ds.delay_transform(pad=1.0, freq_wts=g["window"], downsample=False, verbose=False)
     assert res2["skyvis_lag"].shape[1] == 2 * nchan and res2["lags"].size == 2 * nchan
     assert rel_err(res2["skyvis_lag"][:, ::2], g["skyvis_lag"]) <= TOL
+
+
+def test_gradient_point_sources_vs_oracle_and_finite_difference():
+    """gradient_mode='baseline' on a point-source sky (the reference's own branch is unreachable there, :6263/:6343):
+    against the oracle, and against a finite difference of the GPU visibilities themselves."""
+    from prisim_b200 import synthetic as S
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    cfg = S.config1(nsnap=1)
+    mk = lambda bl: InterferometerArray(cfg["labels"], bl, cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
+                                        skycoords="radec", pointing_coords="hadec", device=0)
+    args = (SimpleTime(2451545.0, 0.0), {"Tnet": 300.0}, NP.ones(cfg["channels"].size), cfg["pointing_hadec"], cfg["skymodel"], cfg["t_acc"])
+    ia = mk(cfg["baselines"])
+    ia.precision = "fp64"
+    ia.observe(*args, gradient_mode="baseline")
+    G = ia.gradient["baseline"][..., 0]
+    sm = cfg["skymodel"]
+    hadec = NP.stack(((0.0 - sm.location[:, 0]) % 360.0, sm.location[:, 1]), axis=1)
+    sp = sm.spec_parms
+    (Vo, Go), _ = O.observe_snapshot(cfg["baselines"], cfg["channels"], hadec, "hadec", cfg["latitude"], cfg["pointing_hadec"], "hadec",
+                                     dict(cfg["telescope"]), sp["flux-scale"], sp["power-law-index"], sp["freq-ref"], gradient=True)
+    assert rel_err(ia.skyvis_freq[..., 0], Vo) <= 1e-9
+    for i in range(3):
+        assert rel_err(G[i], Go[i]) <= 1e-9
+    # fp32 path within tolerance of the fp64 one
+    ib = mk(cfg["baselines"])
+    ib.observe(*args, gradient_mode="baseline")
+    for i in range(3):
+        assert rel_err(ib.gradient["baseline"][i, ..., 0], Go[i]) <= TOL
+    # finite difference along east: V(b + h e_x) - V(b - h e_x) = 2 dV, the phase-centre (zenith) term does not move with b_x
+    h = 1e-3
+    dbl = NP.zeros_like(cfg["baselines"]); dbl[:, 0] = h
+    Vp, Vm = mk(cfg["baselines"] + dbl), mk(cfg["baselines"] - dbl)
+    for a in (Vp, Vm):
+        a.precision = "fp64"
+        a.observe(*args)
+    pert = NP.zeros((1, 3, cfg["baselines"].shape[0])); pert[0, 0, :] = h
+    dV = ia.apply_gradients(perturbations={"baseline": pert})[0, :, :, 0]
+    fd = 0.5 * (Vp.skyvis_freq[..., 0] - Vm.skyvis_freq[..., 0])
+    assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
 def test_config1_observing_run_vs_oracle():

@@ -25,6 +25,7 @@ TELESCOPES = {
 OBSERVE_CASES = {
     "hera": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
     "hera_taper": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
+    "hera_taper_gradient": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
     "hera_roi20": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}, roi_radius=20.0),
     "hera_roiinfo": dict(telescope={"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}),
     "gaussian_altazpointing": dict(telescope={"shape": "gaussian", "size": 10.0, "ocoords": "altaz", "orientation": NP.asarray([90.0, 270.0]), "groundplane": None},
@@ -172,3 +173,38 @@ def test_rotate_visibilities_matches_reference():
     s_new = new1[0] - cur[0]
     expect = V_direct * NP.exp(+2j * NP.pi * (g["bl"] @ s_new)[:, None] * g["chans"][None, :] / 299792458.0)
     assert NP.abs(pbf_free - expect).max() <= 1e-9 * scale
+
+
+def test_gradient_matches_reference():
+    """gradient_mode='baseline' (interferometry.py:6312-6343, :6384-6394) and apply_gradients (:6726-6819) executed by the
+    reference's own code (tapered sky: the only case in which the reference's gradient branch runs, :6263 vs :6343)."""
+    g = _load("observe_hera_taper_gradient.npz")
+    case = OBSERVE_CASES["hera_taper_gradient"]
+    lat = float(g["latitude"])
+    grads = []
+    for j in range(int(g["n_acc"])):
+        (V, G), m2 = O.observe_snapshot(g["bl"], g["chans"], g["hadec_{0}".format(j)], "hadec", lat, g["pointing"], "hadec",
+                                        dict(case["telescope"]), g["flux"], g["spindex"], 150e6, src_shape=g["src_shape"],
+                                        lst=float(g["lsts"][j]), gradient=True)
+        assert NP.abs(V - g["skyvis_freq"][:, :, j]).max() <= 1e-11 * NP.sqrt(NP.mean(NP.abs(g["skyvis_freq"]) ** 2))
+        grads.append(G)
+    grad = NP.stack(grads, axis=3)
+    ref = g["gradient_baseline"]
+    assert grad.shape == ref.shape
+    assert NP.abs(grad - ref).max() <= 1e-11 * NP.sqrt(NP.mean(NP.abs(ref) ** 2))
+    dV = O.apply_gradients(ref, g["perturbations"], g["chans"])
+    assert dV.shape == g["delta_skyvis_freq"].shape
+    assert NP.abs(dV - g["delta_skyvis_freq"]).max() <= 1e-12 * NP.abs(g["delta_skyvis_freq"]).max()
+    # first-order consistency: V(b + db) - V(b) = dV + O(db^2) on the oracle itself
+    j = 0
+    db = g["perturbations"][0].T * 0.05                                  # [nbl,3], ~1 mm
+    kw = dict(src_shape=g["src_shape"], lst=float(g["lsts"][j]))
+    V1, _ = O.observe_snapshot(g["bl"] + db, g["chans"], g["hadec_0"], "hadec", lat, g["pointing"], "hadec", dict(case["telescope"]),
+                               g["flux"], g["spindex"], 150e6, **kw)
+    V0 = g["skyvis_freq"][:, :, 0]
+    lin = O.apply_gradients(ref[:, :, :, :1], db.T[NP.newaxis], g["chans"])[0, :, :, 0]
+    # the gradient covers the fringe term exp(-2 pi i f b.s/c) only; observe() also re-references the phase to the
+    # (zenith) phase centre with the perturbed baseline, d/db of exp(+2 pi i f b.s_pc/c), and the taper moves slightly
+    wl = 299792458.0 / g["chans"]
+    full = lin + 1j * 2.0 * NP.pi / wl[NP.newaxis, :] * db[:, 2:3] * V0
+    assert NP.abs((V1 - V0) - full).max() <= 0.02 * NP.abs(full).max()
