@@ -556,6 +556,41 @@ def skyvis_snapshot(baselines_enu, skypos_altaz_roi, pbfluxes, channels, pc_alta
     return (skyvis, grad) if gradient else skyvis
 
 
+def duplicate_counts(labels, blgroups):
+    """Index logic of InterferometerArray.duplicate_measurements, interferometry.py:6852-6889.
+    labels: sequence of (A2, A1) label tuples of the simulated (unique) baselines; blgroups: dict
+    key tuple -> sequence of label tuples redundant with it.  A key found only reversed in `labels` is
+    used reversed (:6861-6864); a key missing from its own group is prepended (:6866-6870); a label
+    without a group counts once (:6883-6885); a label in two groups raises ValueError (:6880-6882).
+    Returns (num_list [nbl] ints, expanded list of label tuples), or (None, labels) when the groups
+    hold no more baselines than `labels` (:6852-6857: nothing to do)."""
+    labels = [tuple(l) for l in labels]
+    groups = {tuple(k): [tuple(l) for l in v] for k, v in blgroups.items()}
+    if len(labels) >= sum(len(v) for v in groups.values()):
+        return None, labels
+    for key in list(groups):
+        use = key
+        if key not in labels:
+            if tuple(reversed(key)) not in labels:
+                raise KeyError("Input label {0} not found in attribute labels".format(key))
+            use = tuple(reversed(key))
+            groups.setdefault(use, groups[key])         # the reference looks the reversed key up in blgroups (KeyError there)
+        if use not in groups[use]:
+            groups[use] = [use] + groups[use]
+    num_list, out = [], []
+    for label in labels:
+        if label in groups:
+            num_list.append(len(groups[label]))
+            for lbl in groups[label]:
+                if lbl in out:
+                    raise ValueError("Label {0} repeated in more than one baseline group".format(lbl))
+                out.append(lbl)
+        else:
+            num_list.append(1)
+            out.append(label)
+    return NP.asarray(num_list, dtype=NP.int64), out
+
+
 def apply_gradients(gradient_baseline, perturbations, channels):
     """First-order perturbed visibilities, interferometry.py:6811-6819:
     dV = -i 2 pi / lambda * sum_i db[..., i, b] G[i, b, f, t].  gradient_baseline [3,nbl,nchan,nsnap],

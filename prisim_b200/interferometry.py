@@ -875,6 +875,72 @@ class InterferometerArray(object):
         if verbose:
             print("delay_transform() completed successfully.")
 
+    # ------------------------------------------------------------------ redundant baselines
+    def duplicate_measurements(self, blgroups=None):
+        """Expand the simulated (unique) baselines into their redundant sets, same call as interferometry.py:6823-6907:
+        every per-baseline product is repeated ``len(group)`` times along the baseline axis (one device row gather per
+        snapshot), labels / baselines / lengths / projected baselines / per-baseline A_eff, eff_Q, Tsys, bandpass
+        follow, and noise is regenerated for the expanded set (:6905-6906).  ``blgroups``: {label tuple: sequence of
+        label tuples redundant with it}; a key missing from its own group is prepended, labels without a group are
+        kept once, a label in two groups raises ValueError.  Nothing happens when the groups hold no more baselines
+        than are present (:6852-6857)."""
+        if blgroups is None:
+            blgroups = self.blgroups
+        if not isinstance(blgroups, dict):
+            raise TypeError("Input blgroups must be a dictionary")
+        labels = [tuple(l) for l in (self.labels.tolist() if isinstance(self.labels, NP.ndarray) else self.labels)]
+        groups = {tuple(k): [tuple(l) for l in (v.tolist() if isinstance(v, NP.ndarray) else v)] for k, v in blgroups.items()}
+        nbl_new = len(self.bl_reversemap) if self.bl_reversemap is not None else sum(len(v) for v in groups.values())
+        if len(labels) >= nbl_new:
+            return
+        for key in list(groups):
+            use = key
+            if key not in labels:
+                if tuple(reversed(key)) not in labels:
+                    raise KeyError("Input label {0} not found in attribute labels".format(key))
+                use = tuple(reversed(key))
+                groups.setdefault(use, groups[key])
+            if use not in groups[use]:
+                groups[use] = [use] + groups[use]
+        num_list, out = [], []
+        for label in labels:
+            if label in groups:
+                num_list.append(len(groups[label]))
+                for lbl in groups[label]:
+                    if lbl in out:
+                        raise ValueError("Label {0} repeated in more than one baseline group".format(lbl))
+                    out.append(lbl)
+            else:
+                num_list.append(1)
+                out.append(label)
+        num = NP.asarray(num_list, dtype=NP.int64)
+        nbl_old = len(labels)
+        idx = torch.repeat_interleave(torch.arange(nbl_old, device=self._dev_str()), torch.as_tensor(num, device=self._dev_str()))
+        rep = lambda t: t.index_select(0, idx) if (t.dim() == 2 and t.shape[0] == nbl_old) else t      # [nchan] rows are shared
+        self._skyvis = [t.index_select(0, idx) for t in self._skyvis]                    # :6887-6888
+        self._gradient = [t.index_select(1, idx) for t in self._gradient]                # :6889-6890
+        self._bp = [rep(t) for t in self._bp]
+        self._Tsys = [rep(t) for t in self._Tsys]
+        if isinstance(self.labels, NP.ndarray) and self.labels.dtype.names:
+            self.labels = NP.asarray(out, dtype=self.labels.dtype)                       # :6892
+        else:
+            self.labels = out
+        self.baselines = NP.repeat(self.baselines, num, axis=0)
+        if self.projected_baselines is not None:
+            self.projected_baselines = NP.repeat(self.projected_baselines, num, axis=0)
+        self.baseline_lengths = NP.repeat(self.baseline_lengths, num)
+        self.baseline_orientations = NP.repeat(self.baseline_orientations, num)
+        self.eff_Q = NP.repeat(self.eff_Q, num, axis=0)
+        self.A_eff = NP.repeat(self.A_eff, num, axis=0)
+        if self._d_bl is not None:
+            self._d_bl = self._d_bl.index_select(0, idx).contiguous()
+        self._d_aeff = self._d_effq = None
+        self._lag = {}
+        self._vis, self._noise, self._rms = [], [], []
+        self.nbl_total = self.baselines.shape[0] if self.nbl_total == nbl_old else self.nbl_total
+        self.generate_noise()                                                            # :6905-6906
+        self.add_noise()
+
     # ------------------------------------------------------------------ bounded-memory streaming
     def drain(self, sink, noise=True, delay_transform=None):
         """Stream the resident snapshots out and free their device memory (a 1000-snapshot HERA-350 run is

@@ -169,6 +169,8 @@ def load_reference(name):
     src = open(path).read()
     src = re.sub(r"^(\s*)print '([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)      # primary_beams.py:2027
     src = src.replace(".iteritems()", ".items()")                                       # interferometry.py:6405
+    src = src.replace("NP.asarray(blgroups.keys(), dtype=self.labels.dtype)",           # interferometry.py:6858 (dict view)
+                      "NP.asarray(list(blgroups.keys()), dtype=self.labels.dtype)")
     mod = types.ModuleType(name)
     mod.__file__ = path
     mod.__dict__["xrange"] = range
@@ -343,6 +345,45 @@ def main():
     # gradient_mode='baseline' only runs in the reference when the sky model has src_shape: the direction cosines it
     # multiplies by are assigned inside the taper branch (interferometry.py:6263) and are unbound otherwise (:6343)
     run_observe("hera_taper_gradient", hera, src_shape=0.6, gradient_mode="baseline", nsnap=2)
+    # ---------------- duplicate_measurements (interferometry.py:6823-6907): unique baselines -> redundant sets ----------------
+    ant = NP.asarray([[0.0, 0.0, 0.0], [14.6, 0.0, 0.0], [29.2, 0.0, 0.0], [43.8, 0.0, 0.0], [0.0, 14.6, 0.0]])
+    antl = NP.asarray(["0", "1", "2", "3", "4"])
+    dt = [("A2", antl.dtype), ("A1", antl.dtype)]
+    ulabels = NP.asarray([("1", "0"), ("2", "0"), ("3", "0"), ("4", "0")], dtype=dt)
+    ubl = NP.asarray([[14.6, 0.0, 0.0], [29.2, 0.0, 0.0], [43.8, 0.0, 0.0], [0.0, 14.6, 0.0]])
+    blgroups = {("1", "0"): NP.asarray([("1", "0"), ("2", "1"), ("3", "2")], dtype=dt),      # key listed in its own group
+                ("2", "0"): NP.asarray([("3", "1")], dtype=dt),                              # key missing: prepended (:6866-6870)
+                ("3", "0"): NP.asarray([("3", "0")], dtype=dt)}                              # singleton; ("4","0") has no group at all
+    nchan, nsrc0 = 16, 80
+    chans = 150e6 + (NP.arange(nchan) - nchan // 2) * 100e3
+    ia = RI.InterferometerArray(ulabels, ubl, chans, telescope=dict(hera), eff_Q=0.96, latitude=lat, longitude=21.4278, altitude=0.0,
+                                skycoords="hadec", A_eff=154.0 * 0.65, pointing_coords="hadec", baseline_coords="localenu", freq_scale="Hz",
+                                layout={"positions": ant, "labels": antl, "ids": NP.arange(5), "coords": "ENU"},
+                                blgroupinfo={"groups": blgroups, "reversemap": None})
+    ra = rng.uniform(0, 360, nsrc0); dec = NP.degrees(NP.arcsin(rng.uniform(-1, 0.5, nsrc0)))
+    flux = 10 ** rng.uniform(-1, 1.5, nsrc0); spindex = rng.normal(-0.83, 0.2, nsrc0)
+    rec = dict(bl=ubl, chans=chans, flux=flux, spindex=spindex, latitude=lat, lsts=NP.asarray([0.0, 20.0]),
+               ulabels=NP.asarray([list(l) for l in ulabels.tolist()]),
+               group_keys=NP.asarray([list(k) for k in blgroups]),
+               group_0=NP.asarray([list(l) for l in blgroups[("1", "0")].tolist()]),
+               group_1=NP.asarray([list(l) for l in blgroups[("2", "0")].tolist()]),
+               group_2=NP.asarray([list(l) for l in blgroups[("3", "0")].tolist()]))
+    for j, lst_j in enumerate((0.0, 20.0)):
+        hadec_j = NP.stack(((lst_j - ra) % 360.0, dec), axis=1)
+        rec["hadec_{0}".format(j)] = hadec_j
+        ia.observe(TimeObj(2451545.0 + j * 0.01, lst_j), {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None},
+                   NP.ones(nchan), NP.asarray([0.0, lat]), SkyModel(hadec_j, flux, spindex, NP.full(nsrc0, 150e6)), 10.7)
+    rec["skyvis_unique"] = ia.skyvis_freq.copy()
+    # duplicate_measurements repeats projected_baselines too (:6894), which only exist after project_baselines (:7916-7995)
+    ia.project_baselines(ref_point={"location": NP.asarray([[0.0, lat]]), "coords": "hadec"})
+    rec["projected_unique"] = ia.projected_baselines.copy()
+    NP.random.seed(99)
+    ia.duplicate_measurements()
+    rec.update(labels_out=NP.asarray([list(l) for l in ia.labels.tolist()]), baselines_out=ia.baselines, skyvis_out=ia.skyvis_freq,
+               baseline_lengths_out=ia.baseline_lengths, projected_out=ia.projected_baselines, Tsys_out=ia.Tsys, vis_rms_out=ia.vis_rms_freq, bp_out=ia.bp,
+               vis_noise_shape=NP.asarray(ia.vis_noise_freq.shape), vis_minus_noise=ia.vis_freq - ia.vis_noise_freq)
+    if not ONLY or "duplicate" in ONLY:
+        NP.savez_compressed(os.path.join(OUT, "duplicate.npz"), **rec)
     print("golden vectors written to", OUT)
 
 

@@ -133,6 +133,51 @@ def test_gradient_point_sources_vs_oracle_and_finite_difference():
     assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
+def test_duplicate_measurements_against_reference_golden():
+    """Unique baselines -> redundant sets (interferometry.py:6823-6907), replaying the reference's own run."""
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    from tests.test_oracle_golden import _dup_groups
+    g = NP.load(os.path.join(GOLD, "duplicate.npz"))
+    dt = [("A2", "U1"), ("A1", "U1")]
+    labels = NP.asarray([tuple(l) for l in g["ulabels"].tolist()], dtype=dt)
+    groups = {k: NP.asarray(v, dtype=dt) for k, v in _dup_groups(g).items()}
+    hera = {"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}
+    lat = float(g["latitude"])
+    ia = InterferometerArray(labels, g["bl"], g["chans"], telescope=hera, eff_Q=0.96, latitude=lat, longitude=21.4278, skycoords="hadec",
+                             A_eff=154.0 * 0.65, pointing_coords="hadec", freq_scale="Hz", blgroupinfo={"groups": groups, "reversemap": None},
+                             device=0, noise_seed=3)
+    nsrc0, nchan = g["flux"].size, g["chans"].size
+    for j in range(2):
+        parms = {"location": g["hadec_{0}".format(j)], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+                 "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": g["spindex"], "freq-ref": NP.full(nsrc0, 150e6),
+                                "flux-scale": g["flux"]}}
+        ia.observe(SimpleTime(2451545.0 + j * 0.01, float(g["lsts"][j])), {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None},
+                   NP.ones(nchan), NP.asarray([0.0, lat]), SkyModel(init_parms=parms), 10.7, gradient_mode="baseline")
+    assert rel_err(ia.skyvis_freq, g["skyvis_unique"]) <= TOL
+    ia.project_baselines(ref_point={"location": NP.asarray([[0.0, lat]]), "coords": "hadec"})
+    assert NP.allclose(ia.projected_baselines, g["projected_unique"], atol=1e-9)
+    unique = ia.skyvis_freq.copy()
+    grad_unique = ia.gradient["baseline"].copy()
+    ia.duplicate_measurements()
+    assert [tuple(l) for l in ia.labels.tolist()] == [tuple(l) for l in g["labels_out"].tolist()]
+    assert NP.array_equal(ia.baselines, g["baselines_out"]) and NP.allclose(ia.baseline_lengths, g["baseline_lengths_out"])
+    assert NP.allclose(ia.projected_baselines, g["projected_out"], atol=1e-9)
+    num = [3, 2, 1, 1]
+    assert NP.array_equal(ia.skyvis_freq, NP.repeat(unique, num, axis=0)) and rel_err(ia.skyvis_freq, g["skyvis_out"]) <= TOL
+    assert NP.array_equal(ia.gradient["baseline"], NP.repeat(grad_unique, num, axis=1))
+    assert NP.allclose(ia.Tsys, g["Tsys_out"]) and NP.allclose(ia.bp, g["bp_out"])
+    assert NP.allclose(ia.vis_rms_freq, g["vis_rms_out"], rtol=1e-12)
+    assert ia.vis_noise_freq.shape == tuple(g["vis_noise_shape"]) and NP.allclose(ia.vis_freq - ia.vis_noise_freq, ia.skyvis_freq)
+    # redundant copies share the sky signal but not the noise
+    assert NP.abs(ia.vis_noise_freq[0] - ia.vis_noise_freq[1]).min() > 0
+    # the delay transform runs on the expanded set
+    ia.delay_transform(pad=1.0, verbose=False)
+    assert ia.skyvis_lag.shape == (7, nchan, 2)
+    ia.duplicate_measurements()                                                        # complete now: no-op (:6852-6857)
+    assert ia.baselines.shape[0] == 7
+
+
 def test_config1_observing_run_vs_oracle():
     """BASELINE config 1 in full through observing_run (drift scan, 10 snapshots)."""
     from prisim_b200 import synthetic as S

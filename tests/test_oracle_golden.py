@@ -208,3 +208,28 @@ def test_gradient_matches_reference():
     wl = 299792458.0 / g["chans"]
     full = lin + 1j * 2.0 * NP.pi / wl[NP.newaxis, :] * db[:, 2:3] * V0
     assert NP.abs((V1 - V0) - full).max() <= 0.02 * NP.abs(full).max()
+
+
+def _dup_groups(g):
+    keys = [tuple(k) for k in g["group_keys"].tolist()]
+    return {keys[i]: [tuple(l) for l in g["group_{0}".format(i)].tolist()] for i in range(len(keys))}
+
+
+def test_duplicate_measurements_index_logic_matches_reference():
+    """interferometry.py:6823-6907 executed by the reference: label expansion and row repeats."""
+    g = _load("duplicate.npz")
+    labels = [tuple(l) for l in g["ulabels"].tolist()]
+    num, out = O.duplicate_counts(labels, _dup_groups(g))
+    assert out == [tuple(l) for l in g["labels_out"].tolist()]
+    assert NP.array_equal(NP.repeat(g["bl"], num, axis=0), g["baselines_out"])
+    assert NP.array_equal(NP.repeat(g["skyvis_unique"], num, axis=0), g["skyvis_out"])
+    assert NP.array_equal(NP.repeat(g["projected_unique"], num, axis=0), g["projected_out"])
+    assert NP.allclose(g["vis_minus_noise"], g["skyvis_out"])                       # noise regenerated on the expanded set
+    assert tuple(g["vis_noise_shape"]) == g["skyvis_out"].shape
+    # a label in two groups is an error; a key absent from labels (either order) too; complete groups are a no-op
+    bad = _dup_groups(g); bad[("3", "0")] = [("3", "0"), ("2", "1")]
+    with pytest.raises(ValueError):
+        O.duplicate_counts(labels, bad)
+    with pytest.raises(KeyError):
+        O.duplicate_counts(labels, {("9", "8"): [("9", "8"), ("7", "6"), ("5", "4"), ("3", "2"), ("1", "0")]})
+    assert O.duplicate_counts(labels, {("1", "0"): [("1", "0")]})[0] is None
