@@ -777,6 +777,61 @@ def delay_transform(vis_freq, bp, bp_wts, freq_resolution, pad=1.0, downsample=T
     return out, lags
 
 
+def window_N2width(shape="rect"):
+    """DSP.window_N2width(n_window=None, shape) [AU-memory]: width of the equivalent rectangular window as a fraction
+    of the window length, sum(w / max w) / N on a long window (rect 1, bhw 0.35875, bnw 0.3635819)."""
+    w = windowing(1000000, shape=shape.lower())
+    return NP.sum(w / w.max()) / w.size
+
+
+def multi_window_weights(channels, bw_eff, freq_center=None, shape=None):
+    """The sub-band windows of multi_window_delay_transform, interferometry.py:8199-8265: [nwin, nchan].
+    n_window = round(bw_eff / (frac_width * df)) samples (:8236-8238) of the window shape, centred on the channel
+    nearest each frequency centre (LKP.find_1NN within df/2 [AU-memory], sorted by channel :8246-8251), clipped to
+    the band and zero elsewhere (:8253-8265)."""
+    channels = NP.asarray(channels, dtype=NP.float64)
+    df = channels[1] - channels[0]
+    bw_eff = NP.asarray(bw_eff, dtype=NP.float64).reshape(-1)
+    if NP.any(bw_eff <= 0.0):
+        raise ValueError("All values in effective bandwidth must be strictly positive")
+    if freq_center is None:
+        freq_center = NP.asarray(channels[int(0.5 * channels.size)]).reshape(-1)        # :8210
+    else:
+        freq_center = NP.asarray(freq_center, dtype=NP.float64).reshape(-1)
+        if NP.any((freq_center <= channels.min()) | (freq_center >= channels.max())):
+            raise ValueError("Frequency centers must lie strictly inside the observing band")
+    if bw_eff.size == 1 and freq_center.size > 1:
+        bw_eff = NP.repeat(bw_eff, freq_center.size)
+    elif bw_eff.size > 1 and freq_center.size == 1:
+        freq_center = NP.repeat(freq_center, bw_eff.size)
+    elif bw_eff.size != freq_center.size:
+        raise ValueError("Effective bandwidth(s) and frequency center(s) must have same number of elements")
+    shape = "rect" if shape is None else shape
+    if shape not in ["rect", "bhw", "bnw", "RECT", "BHW", "BNW"]:
+        raise ValueError("Invalid value for window shape specified.")
+    n_window = NP.round(bw_eff / window_N2width(shape) / df).astype(int)               # :8236-8238
+    ind_channels = NP.rint((freq_center - channels[0]) / df).astype(int)                # nearest channel (within df/2)
+    order = NP.argsort(ind_channels, kind="stable")                                     # :8247-8251
+    ind_channels, n_window = ind_channels[order], n_window[order]
+    freq_wts = NP.zeros((ind_channels.size, channels.size))
+    for i, ic in enumerate(ind_channels):
+        window = windowing(int(n_window[i]), shape=shape.lower(), centering=True)       # :8254
+        chan_idx = ic + NP.arange(int(n_window[i])) - int(n_window[i] / 2)              # :8255
+        ok = (chan_idx >= 0) & (chan_idx < channels.size)                               # :8256-8262 (out-of-band part dropped)
+        freq_wts[i, chan_idx[ok]] = window[ok]
+    return freq_wts
+
+
+def multi_window_delay_transform(vis_freq, bp, freq_wts, freq_resolution, pad=1.0):
+    """interferometry.py:8267-8287 for one product: [nbl, nchan, nsnap] -> [nbl, nwin, nchan, nsnap]; also the
+    delay-sample correlation length nchan / sum(window) (:8287)."""
+    out = []
+    for i in range(freq_wts.shape[0]):
+        lag, _ = delay_transform(vis_freq, bp, freq_wts[i][NP.newaxis, :, NP.newaxis], freq_resolution, pad=pad)
+        out.append(lag)
+    return NP.stack(out, axis=1), vis_freq.shape[1] / NP.sum(freq_wts, axis=1)
+
+
 # --------------------------------------------------------------------------------------------
 # phase centring / projected baselines (interferometry.py:7712-7995)
 # --------------------------------------------------------------------------------------------

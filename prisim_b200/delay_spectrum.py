@@ -38,6 +38,15 @@ def windowing(N, shape="rect", pad_width=0, centering=True, area_normalize=False
     return win
 
 
+def window_N2width(n_window=None, shape="rect", fftpow=1.0):
+    """Width of the equivalent rectangular window as a fraction of the window length (``DSP.window_N2width`` of the
+    un-vendored astroutils, used at interferometry.py:8236): sum(w / max w) / N, evaluated on a long window when
+    n_window is None (rect 1.0, bhw 0.35875, bnw 0.3635819)."""
+    n = 1000000 if n_window is None else int(n_window)
+    w = windowing(n, shape=shape.lower()) ** fftpow
+    return float(NP.sum(w / w.max()) / n)
+
+
 class DelaySpectrum(object):
     def __init__(self, interferometer_array=None, init_file=None):
         if init_file is not None:

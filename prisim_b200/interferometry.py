@@ -875,6 +875,85 @@ class InterferometerArray(object):
         if verbose:
             print("delay_transform() completed successfully.")
 
+    # ------------------------------------------------------------------ sub-band delay transforms
+    def subband_windows(self, bw_eff, freq_center=None, shape=None):
+        """The [nwin, nchan] sub-band weights multi_window_delay_transform builds (interferometry.py:8199-8265): for
+        every (effective bandwidth, centre frequency) a window of round(bw_eff / (w_frac df)) samples of `shape`
+        ('rect' | 'bhw' | 'bnw'; w_frac = its equivalent-rectangle width fraction) centred on the nearest channel,
+        clipped to the band, ordered by centre channel."""
+        if not isinstance(bw_eff, (int, float, list, NP.ndarray)):
+            raise TypeError("Effective bandwidth must be a scalar, list or numpy array")
+        bw = NP.asarray(bw_eff, dtype=NP.float64).reshape(-1)
+        if NP.any(bw <= 0.0):
+            raise ValueError("All values in effective bandwidth must be strictly positive")
+        f, df = self.channels, self.freq_resolution
+        if freq_center is None:
+            fc = NP.asarray(f[int(0.5 * f.size)]).reshape(-1)
+        elif isinstance(freq_center, (int, float, list, NP.ndarray)):
+            fc = NP.asarray(freq_center, dtype=NP.float64).reshape(-1)
+            if NP.any((fc <= f.min()) | (fc >= f.max())):
+                raise ValueError("Frequency centers must lie strictly inside the observing band")
+        else:
+            raise TypeError("Frequency center(s) must be scalar, list or numpy array")
+        if bw.size == 1 and fc.size > 1:
+            bw = NP.repeat(bw, fc.size)
+        elif bw.size > 1 and fc.size == 1:
+            fc = NP.repeat(fc, bw.size)
+        elif bw.size != fc.size:
+            raise ValueError("Effective bandwidth(s) and frequency center(s) must have same number of elements")
+        if shape is not None:
+            if not isinstance(shape, str):
+                raise TypeError("Window shape must be a string")
+            if shape not in ["rect", "bhw", "bnw", "RECT", "BHW", "BNW"]:
+                raise ValueError("Invalid value for window shape specified.")
+        else:
+            shape = "rect"
+        from .delay_spectrum import windowing, window_N2width
+        nwin = NP.round(bw / window_N2width(shape=shape) / df).astype(int)              # :8236-8238
+        centre = NP.rint((fc - f[0]) / df).astype(int)                                  # nearest channel, :8246
+        order = NP.argsort(centre, kind="stable")
+        wts = NP.zeros((fc.size, f.size))
+        for row, (c, n) in enumerate(zip(centre[order], nwin[order])):
+            w = windowing(int(n), shape=shape.lower(), centering=True)
+            k = c + NP.arange(int(n)) - int(n / 2)                                      # :8255
+            inside = (k >= 0) & (k < f.size)
+            wts[row, k[inside]] = w[inside]
+        return wts
+
+    def multi_window_delay_transform(self, bw_eff, freq_center=None, shape=None, pad=1.0, verbose=True):
+        """Delay transforms over several sub-bands, same call and products as interferometry.py:8141-8287: returns
+        {'skyvis_lag', 'vis_noise_lag', 'lag_kernel'} of shape [nbl, nwin, nchan, nsnap] and 'lag_corr_length' [nwin].
+        Each (window, snapshot) is one launch of the delay-transform kernel with the window as its weights."""
+        wts_host = self.subband_windows(bw_eff, freq_center=freq_center, shape=shape)
+        if not isinstance(pad, (int, float)):
+            raise TypeError("pad fraction must be a scalar value.")
+        if pad < 0.0:
+            pad = 0.0
+            if verbose:
+                warnings.warn("\tPad fraction found to be negative. Resetting to 0.0 (no padding will be applied).")
+        nbl, nchan, nsnap = self.baselines.shape[0], self.channels.size, len(self._skyvis)
+        wts_dev = engine._f64(wts_host, self.device)
+        nout = engine.delay_nout(nchan, pad, True)
+        out = {}
+        for key, lst in (("skyvis_lag", self._skyvis), ("vis_noise_lag", self._noise), ("lag_kernel", None)):
+            if lst is not None and not lst:
+                continue                                                                 # product not generated (yet)
+            res = torch.empty((nbl, wts_host.shape[0], nout, nsnap), dtype=torch.complex128, device=self._dev_str())
+            for t in range(nsnap):
+                for i in range(wts_host.shape[0]):
+                    if lst is None:
+                        kern = engine.delay_transform(None, self._bp[t], wts_dev[i], self.freq_resolution, pad=pad, downsample=True,
+                                                      nrows=nbl if self._bp[t].ndim == 2 else 1, nchan=nchan, device=self.device)
+                        res[:, i, :, t] = kern
+                    else:
+                        res[:, i, :, t] = engine.delay_transform(lst[t], self._bp[t], wts_dev[i], self.freq_resolution, pad=pad,
+                                                                 downsample=True)
+            out[key] = res.cpu().numpy()
+        out["lag_corr_length"] = nchan / NP.sum(wts_host, axis=1)                        # :8287
+        if verbose:
+            print("multi_window_delay_transform() completed successfully.")
+        return out
+
     # ------------------------------------------------------------------ redundant baselines (SURVEY 8f-4)
     def duplicate_measurements(self, blgroups=None):
         """Expand the simulated (unique) baselines into their redundant sets, same call as interferometry.py:6823-6907:

@@ -119,6 +119,41 @@ def downsampler(inp, factor, axis=-1, verbose=True, method="interp", kind="linea
     return f(NP.arange(0, n, factor))
 
 
+def windowing(N, shape="rect", pad_width=0, centering=True, area_normalize=False, peak=1.0, power_normalize=False):
+    """DSP.windowing [AU-memory]: rect / 4-term Blackman-Harris / Blackman-Nuttall over n/(N-1); peak 1 unless normalised."""
+    n = NP.arange(N)
+    if shape.lower() == "rect":
+        win = NP.ones(N)
+    else:
+        a = {"bhw": (0.35875, 0.48829, 0.14128, 0.01168), "bnw": (0.3635819, 0.4891775, 0.1365995, 0.0106411)}[shape.lower()]
+        x = 2 * NP.pi * n / (N - 1)
+        win = a[0] - a[1] * NP.cos(x) + a[2] * NP.cos(2 * x) - a[3] * NP.cos(3 * x)
+    if area_normalize:
+        return win / NP.sum(win)
+    if power_normalize:
+        return win / NP.sqrt(NP.sum(win ** 2))
+    return win * peak / NP.amax(win)
+
+
+def window_N2width(n_window=None, shape="rect", area_normalize=True, power_normalize=False, fftpow=1.0):
+    """DSP.window_N2width [AU-memory]: width of the equivalent rectangular window as a fraction of the window length,
+    sum(w / max w) / N on a long window (rect 1.0, bhw 0.35875, bnw 0.3635819)."""
+    n = 1000000 if n_window is None else int(n_window)
+    w = windowing(n, shape=shape) ** fftpow
+    return NP.sum(w / w.max()) / n
+
+
+def find_1NN(ref, inp, distance_ULIM=NP.inf, remove_oob=True):
+    """LKP.find_1NN [AU-memory]: nearest reference point of every input point; returns (input index, reference index,
+    distance) of the inputs that have one within distance_ULIM."""
+    ref = NP.asarray(ref, dtype=float).reshape(len(ref), -1); inp = NP.asarray(inp, dtype=float).reshape(len(inp), -1)
+    d = NP.sqrt(((inp[:, None, :] - ref[None, :, :]) ** 2).sum(axis=2))
+    j = NP.argmin(d, axis=1)
+    dist = d[NP.arange(inp.shape[0]), j]
+    ok = dist <= distance_ULIM
+    return NP.arange(inp.shape[0])[ok], j[ok], dist[ok]
+
+
 class SkyModel(object):
     """catalog.SkyModel stand-in: power-law ('func') spectra only."""
 
@@ -138,11 +173,13 @@ def install_stubs():
     au = _mod("astroutils", __githash__="stub")
     au.geometry = _mod("astroutils.geometry", altaz2dircos=altaz2dircos, dircos2altaz=dircos2altaz, hadec2altaz=hadec2altaz,
                        altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu, enu2xyz=enu2xyz)
-    au.DSP_modules = _mod("astroutils.DSP_modules", FT1D=FT1D, spectral_axis=spectral_axis, downsampler=downsampler)
+    au.DSP_modules = _mod("astroutils.DSP_modules", FT1D=FT1D, spectral_axis=spectral_axis, downsampler=downsampler,
+                          windowing=windowing, window_N2width=window_N2width)
     au.catalog = _mod("astroutils.catalog", SkyModel=SkyModel)
     au.constants = _mod("astroutils.constants", Jy=1.0e-26, sday=0.99726958, rest_freq_HI=1420405751.77)
     for name in ("gridding_modules", "lookup_operations", "nonmathops", "mathops", "ephemeris_timing", "mpi_modules"):
         setattr(au, name, _mod("astroutils." + name))
+    au.lookup_operations.find_1NN = find_1NN
 
     class _Any(object):
         def __init__(self, *a, **k):
@@ -169,6 +206,7 @@ def load_reference(name):
     src = open(path).read()
     src = re.sub(r"^(\s*)print '([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)      # primary_beams.py:2027
     src = src.replace(".iteritems()", ".items()")                                       # interferometry.py:6405
+    src = src.replace(".astype(NP.int)", ".astype(int)")                                # numpy >= 1.24 (interferometry.py:8238)
     src = src.replace("NP.asarray(blgroups.keys(), dtype=self.labels.dtype)",           # interferometry.py:6858 (dict view)
                       "NP.asarray(list(blgroups.keys()), dtype=self.labels.dtype)")
     mod = types.ModuleType(name)
@@ -319,6 +357,18 @@ def main():
         rec["skyvis_lag_pad05"] = ia.skyvis_lag
         if not ONLY or tag in ONLY:
             NP.savez_compressed(os.path.join(OUT, "observe_{0}.npz".format(tag)), **rec)
+        if tag == "hera" and (not ONLY or "multiwin_hera" in ONLY):
+            # multi_window_delay_transform (interferometry.py:8141-8287): three sub-bands, Blackman-Harris, pad 1.0 and 0.0
+            mw = {}
+            bw_eff = NP.asarray([0.8e6, 1.0e6, 0.6e6]); fc = NP.asarray([chans[8], chans[16], chans[25]])
+            for pad_mw, sfx in ((1.0, "pad1"), (0.0, "pad0")):
+                res = ia.multi_window_delay_transform(bw_eff, freq_center=fc, shape="bhw", pad=pad_mw, verbose=False)
+                for k in ("skyvis_lag", "vis_noise_lag", "lag_kernel", "lag_corr_length"):
+                    mw["{0}_{1}".format(k, sfx)] = res[k]
+            res = ia.multi_window_delay_transform(1.2e6, shape="rect", pad=1.0, verbose=False)      # defaults: centre channel
+            mw.update(skyvis_lag_rect=res["skyvis_lag"], lag_corr_length_rect=res["lag_corr_length"], bw_eff=bw_eff, freq_center=fc,
+                      vis_noise_freq=ia.vis_noise_freq)
+            NP.savez_compressed(os.path.join(OUT, "multiwin_hera.npz"), **mw)
         if tag == "hera" and (not ONLY or "rotate_hera" in ONLY):
             # rotate_visibilities = phase_centering + project_baselines (interferometry.py:7655-7995), twice:
             # to a fixed HA/Dec, then to an RA/Dec that differs per snapshot

@@ -133,6 +133,50 @@ def test_gradient_point_sources_vs_oracle_and_finite_difference():
     assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
+def test_multi_window_delay_transform_against_reference_golden():
+    """Sub-band delay transforms (interferometry.py:8141-8287) replaying the reference's own run on the 'hera' case."""
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    g = NP.load(os.path.join(GOLD, "observe_hera.npz"))
+    m = NP.load(os.path.join(GOLD, "multiwin_hera.npz"))
+    nbl, nchan, nsnap = g["skyvis_freq"].shape
+    ia = InterferometerArray([("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)], g["bl"], g["chans"], telescope=dict(OBSERVE_CASES["hera"]["telescope"]),
+                             eff_Q=0.96, latitude=float(g["latitude"]), longitude=21.4278, skycoords="hadec", A_eff=154.0 * 0.65,
+                             pointing_coords="hadec", freq_scale="Hz", device=0, noise_seed=5)
+    nsrc0 = g["flux"].size
+    for j in range(nsnap):
+        parms = {"location": g["hadec_{0}".format(j)], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+                 "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": g["spindex"], "freq-ref": NP.full(nsrc0, 150e6),
+                                "flux-scale": g["flux"]}}
+        ia.observe(SimpleTime(2451545.0 + j * 0.01, float(g["lsts"][j])), {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None},
+                   g["bandpass"], g["pointing"], SkyModel(init_parms=parms), float(g["t_acc"][j]))
+    res0 = ia.multi_window_delay_transform(m["bw_eff"], freq_center=m["freq_center"], shape="bhw", verbose=False)   # before noise exists
+    assert set(res0) == {"skyvis_lag", "lag_kernel", "lag_corr_length"}
+    ia.generate_noise()
+    df = g["chans"][1] - g["chans"][0]
+    for shape, bw, fc, sfx, pad in (("bhw", m["bw_eff"], m["freq_center"], "pad1", 1.0), ("bhw", m["bw_eff"], m["freq_center"], "pad0", 0.0),
+                                    ("rect", 1.2e6, None, "rect", 1.0)):
+        res = ia.multi_window_delay_transform(bw, freq_center=fc, shape=shape, pad=pad, verbose=False)
+        assert res["skyvis_lag"].shape == m["skyvis_lag_" + sfx].shape
+        nw = res["skyvis_lag"].shape[1]
+        for i in range(nw):
+            assert rel_err(res["skyvis_lag"][:, i], m["skyvis_lag_" + sfx][:, i]) <= TOL
+        assert NP.allclose(res["lag_corr_length"], m["lag_corr_length_" + sfx], rtol=1e-12)
+        assert NP.array_equal(ia.subband_windows(bw, fc, shape), O.multi_window_weights(g["chans"], bw, fc, shape))
+        if sfx != "rect":
+            assert NP.abs(res["lag_kernel"] - m["lag_kernel_" + sfx]).max() <= 1e-10 * NP.abs(m["lag_kernel_" + sfx]).max()
+            nz_o, _ = O.multi_window_delay_transform(ia.vis_noise_freq, g["bp"], O.multi_window_weights(g["chans"], bw, fc, shape), df, pad=pad)
+            assert NP.abs(res["vis_noise_lag"] - nz_o).max() <= 1e-10 * NP.abs(nz_o).max()
+    with pytest.raises(ValueError):
+        ia.multi_window_delay_transform(-1.0)
+    with pytest.raises(ValueError):
+        ia.multi_window_delay_transform(1e6, freq_center=g["chans"][-1])
+    with pytest.raises(ValueError):
+        ia.multi_window_delay_transform(1e6, shape="hann")
+    with pytest.raises(TypeError):
+        ia.multi_window_delay_transform("wide")
+
+
 def test_duplicate_measurements_against_reference_golden():
     """Unique baselines -> redundant sets (interferometry.py:6823-6907), replaying the reference's own run."""
     from prisim_b200.interferometry import InterferometerArray, SimpleTime

@@ -233,3 +233,28 @@ def test_duplicate_measurements_index_logic_matches_reference():
     with pytest.raises(KeyError):
         O.duplicate_counts(labels, {("9", "8"): [("9", "8"), ("7", "6"), ("5", "4"), ("3", "2"), ("1", "0")]})
     assert O.duplicate_counts(labels, {("1", "0"): [("1", "0")]})[0] is None
+
+
+def test_multi_window_delay_transform_matches_reference():
+    """interferometry.py:8141-8287 run by the reference (window helpers of astroutils stubbed, [AU-memory])."""
+    g = _load("observe_hera.npz")
+    m = _load("multiwin_hera.npz")
+    df = g["chans"][1] - g["chans"][0]
+    for shape, bw, fc, sfx, pad in (("bhw", m["bw_eff"], m["freq_center"], "pad1", 1.0), ("bhw", m["bw_eff"], m["freq_center"], "pad0", 0.0),
+                                    ("rect", 1.2e6, None, "rect", 1.0)):
+        wts = O.multi_window_weights(g["chans"], bw, fc, shape)
+        lag, corr = O.multi_window_delay_transform(g["skyvis_freq"], g["bp"], wts, df, pad=pad)
+        ref = m["skyvis_lag_" + sfx]
+        assert lag.shape == ref.shape
+        assert NP.abs(lag - ref).max() <= 1e-12 * NP.abs(ref).max()
+        assert NP.allclose(corr, m["lag_corr_length_" + sfx], rtol=1e-12)
+        if sfx != "rect":
+            nz, _ = O.multi_window_delay_transform(m["vis_noise_freq"], g["bp"], wts, df, pad=pad)
+            assert NP.abs(nz - m["vis_noise_lag_" + sfx]).max() <= 1e-12 * NP.abs(m["vis_noise_lag_" + sfx]).max()
+            kern, _ = O.multi_window_delay_transform(NP.ones_like(g["bp"]), g["bp"], wts, df, pad=pad)
+            assert NP.abs(kern - m["lag_kernel_" + sfx]).max() <= 1e-12 * NP.abs(m["lag_kernel_" + sfx]).max()
+    assert abs(O.window_N2width("bhw") - 0.35875) < 1e-5 and O.window_N2width("rect") == 1.0
+    with pytest.raises(ValueError):
+        O.multi_window_weights(g["chans"], [1e6, 2e6], [150e6, 150.5e6, 151e6])
+    with pytest.raises(ValueError):
+        O.multi_window_weights(g["chans"], 1e6, g["chans"][0])
