@@ -556,6 +556,69 @@ def skyvis_snapshot(baselines_enu, skypos_altaz_roi, pbfluxes, channels, pc_alta
     return (skyvis, grad) if gradient else skyvis
 
 
+def roi_append_settings(skypos, skycoords, latitude, freq, telescope, roi_info, pinfo=None, lst=None):
+    """One call of ROI_parameters.append_settings, interferometry.py:4221-4617, for sky positions in 'hadec',
+    'altaz' or 'dircos' (degrees).  Returns (ind, pbeam [n_roi, nchan], radius, center_altaz [1,2] or None).
+    * 'ind' given (:4451-4453): used as is; 'pbeam' given with it: cast to float32 (:4466).
+    * otherwise radius clamped to [0, 90], default 90 (:4497-4501); centre default zenith, converted to alt-az
+      (:4503-4523); zenith-centred (within 1e-2 deg, :4546-4547) selects alt >= 90 - radius (:4551), else
+      GEOM.spherematch within radius of the centre (:4549) [AU-memory], called with (alt, az) in the (lon, lat) slots.
+    * beam: primary_beam_generator at the ROI positions for all channels if roi_info['pbeam_chromaticity'], else at
+      pbeam_reffreq (default centre channel) broadcast over the channels (:4578-4615)."""
+    freq = NP.asarray(freq, dtype=NP.float64).ravel()
+    skypos = NP.asarray(skypos, dtype=NP.float64)
+    altaz = {"hadec": lambda: hadec2altaz(skypos, latitude, units="degrees"), "altaz": lambda: skypos,
+             "dircos": lambda: dircos2altaz(skypos, units="degrees")}[skycoords]()
+    roi_info = dict(roi_info)
+    radius, center = None, None
+    if roi_info.get("ind", None) is not None:
+        ind = NP.asarray(roi_info["ind"])
+        radius = roi_info.get("radius", None)
+        if roi_info.get("pbeam", None) is not None and ind.size > 0:
+            pb = NP.asarray(roi_info["pbeam"]).reshape(-1, freq.size)
+            if ind.size != pb.shape[0]:
+                raise ValueError('Number of elements in values in key "ind" and number of rows of values in key "pbeam" must be identical.')
+            return ind, pb.astype(NP.float32), radius, center
+    else:
+        radius = 90.0 if roi_info.get("radius", None) is None else max(0.0, min(roi_info["radius"], 90.0))
+        if roi_info.get("center", None) is None:
+            center = NP.asarray([90.0, 270.0]).reshape(1, -1)
+        else:
+            c = NP.asarray(roi_info["center"], dtype=NP.float64).reshape(1, -1)
+            cc = roi_info["center_coords"]
+            if cc == "dircos":
+                center = dircos2altaz(c, units="degrees")
+            elif cc == "altaz":
+                center = c
+            elif cc == "hadec":
+                center = hadec2altaz(c, latitude, units="degrees")
+            elif cc == "radec":
+                if lst is None:
+                    raise KeyError("LST not provided for coordinate conversion")
+                center = hadec2altaz(NP.asarray([lst - c[0, 0], c[0, 1]]).reshape(1, -1), latitude, units="degrees")
+            else:
+                raise ValueError("Invalid coordinate system specified for center")
+        if sphdist(center[0, 1], center[0, 0], 270.0, 90.0) > 1e-2:
+            # the reference hands (alt, az) to spherematch(lon1, lat1, lon2, lat2, ...) in that order (:4549), i.e. the
+            # altitude plays the longitude; reproduced as written
+            ind = NP.where(sphdist(center[0, 0], center[0, 1], altaz[:, 0], altaz[:, 1]) <= radius)[0]
+        else:
+            ind = NP.where(altaz[:, 0] >= 90.0 - radius)[0]
+    if ind.size == 0:
+        return ind, NP.asarray([]), radius, center
+    pinfo = dict(pinfo) if pinfo is not None else None
+    if pinfo is None:
+        raise ValueError("Pointing info dictionary pinfo must be specified.")
+    if pinfo.get("pointing_coords", "altaz") == "radec":
+        pc = NP.asarray(pinfo["pointing_center"], dtype=NP.float64).reshape(1, -1)
+        pinfo["pointing_center"] = hadec2altaz(NP.asarray([lst - pc[0, 0], pc[0, 1]]).reshape(1, -1), latitude, units="degrees")
+        pinfo["pointing_coords"] = "altaz"
+    reffreq = roi_info.get("pbeam_reffreq", freq[freq.size // 2])
+    fcomp = freq if roi_info.get("pbeam_chromaticity", False) else NP.asarray(reffreq, dtype=NP.float64).reshape(-1)
+    pbeam = primary_beam_generator(altaz[ind, :], fcomp, telescope, freq_scale="Hz", skyunits="altaz", pointing_info=pinfo)
+    return ind, pbeam.astype(NP.float64) * NP.ones(freq.size).reshape(1, -1), radius, center
+
+
 def duplicate_counts(labels, blgroups):
     """Index logic of InterferometerArray.duplicate_measurements, interferometry.py:6852-6889.
     labels: sequence of (A2, A1) label tuples of the simulated (unique) baselines; blgroups: dict

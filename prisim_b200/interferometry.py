@@ -156,6 +156,160 @@ def _validate_2d(name, val, nbl, nchan):
     raise ValueError("{0} incompatible with the number of interferometers and/or frequency channels.".format(name))
 
 
+class ROI_parameters(object):
+    """Drop-in for ``prisim.interferometry.ROI_parameters`` (interferometry.py:3905-4617) in memory: per snapshot the
+    catalogue indices inside the region of interest and the primary-beam table [n_roi, nchan] that
+    ``InterferometerArray.observe(roi_info={'ind', 'pbeam'})`` consumes.  The beam is evaluated on the GPU
+    (``primary_beam_generator`` -> ``pb200_amp_table``); FITS save / init_file are out of scope."""
+
+    def __init__(self, init_file=None, device=None):
+        if init_file is not None:
+            raise NotImplementedError("FITS interchange of ROI parameters is outside the hot-path scope (SURVEY.md section 8f)")
+        self.skymodel = None
+        self.freq = None
+        self.freq_scale = None
+        self.telescope = None
+        self.info = {"radius": [], "center": [], "ind": [], "pbeam": [], "center_coords": None}     # :4170-4176
+        self.pinfo = []
+        self.device = device
+
+    def _altaz(self, skymodel, lst):
+        coords = getattr(skymodel, "coords", None)
+        loc = NP.asarray(skymodel.location, dtype=NP.float64)
+        if coords in ("radec", "hadec") and self.telescope.get("latitude", None) is None:
+            raise ValueError("Latitude of the observatory must be provided.")
+        if coords == "radec":          # HA = LST - RA (same deviation from the astropy route as observe(), DESIGN.md section 6)
+            if lst is None:
+                raise ValueError("LST must be provided.")
+            return GEOM.hadec2altaz(NP.stack(((lst - loc[:, 0]), loc[:, 1]), axis=1), self.telescope["latitude"], units="degrees")
+        if coords == "hadec":
+            return GEOM.hadec2altaz(loc, self.telescope["latitude"], units="degrees")
+        if coords == "dircos":
+            return GEOM.dircos2altaz(loc, units="degrees")
+        if coords == "altaz":
+            return loc
+        raise KeyError("skycoords invalid or unspecified in skymodel")
+
+    def append_settings(self, skymodel, freq, pinfo=None, lst=None, time_jd=None, roi_info=None, telescope=None, freq_scale="GHz"):
+        """Same call as interferometry.py:4221-4224."""
+        from .skymodel import SkyModel
+        if self.freq is None:                                                          # :4396-4414
+            if freq is None:
+                raise ValueError("freq must be specified using a numpy array")
+            if not isinstance(freq, NP.ndarray):
+                raise TypeError("freq must be specified using a numpy array")
+            scale = {None: 1.0, "hz": 1.0, "ghz": 1.0e9, "mhz": 1.0e6, "khz": 1.0e3}
+            key = freq_scale.lower() if isinstance(freq_scale, str) else freq_scale
+            if key not in scale:
+                raise ValueError('Frequency units must be "GHz", "MHz", "kHz" or "Hz". If not set, it defaults to "Hz"')
+            self.freq = NP.asarray(freq, dtype=NP.float64).ravel() * scale[key]
+            self.freq_scale = "Hz"
+        if self.telescope is None:                                                     # :4416-4420
+            if not isinstance(telescope, dict):
+                raise TypeError("Input telescope must be a dictionary.")
+            self.telescope = telescope
+        if skymodel is None:                                                           # :4422-4425
+            self.info["pbeam"] += [NP.asarray([])]
+            self.info["ind"] += [NP.asarray([])]
+            self.pinfo += [None]
+            return
+        if not isinstance(skymodel, SkyModel):
+            raise TypeError("skymodel should be an instance of class SkyModel.")
+        self.skymodel = skymodel
+        if roi_info is None:
+            raise ValueError("roi_info dictionary must be set.")
+        pbeam_input = False
+        skypos_altaz = None
+        if roi_info.get("ind", None) is not None:                                      # :4451-4495
+            ind = NP.asarray(roi_info["ind"])
+            self.info["ind"] += [ind]
+            if ind.size > 0:
+                if roi_info.get("pbeam", None) is not None:
+                    try:
+                        pb = NP.asarray(roi_info["pbeam"]).reshape(-1, self.freq.size)
+                    except ValueError:
+                        raise ValueError('Number of columns of primary beam in key "pbeam" of dictionary roi_info must be equal to number of frequency channels.')
+                    if ind.size != pb.shape[0]:
+                        raise ValueError('Number of elements in values in key "ind" and number of rows of values in key "pbeam" must be identical.')
+                    self.info["pbeam"] += [NP.asarray(roi_info["pbeam"]).astype(NP.float32)]
+                    pbeam_input = True
+                if not pbeam_input:
+                    skypos_altaz = self._altaz(skymodel, lst)
+            if "radius" in roi_info:
+                self.info["radius"] += [roi_info["radius"]]
+            if "center" in roi_info:
+                self.info["center"] += [roi_info["center"]]
+        else:                                                                          # :4496-4552
+            radius = 90.0 if roi_info.get("radius", None) is None else max(0.0, min(roi_info["radius"], 90.0))
+            self.info["radius"] += [radius]
+            lat = self.telescope.get("latitude", None)
+            if roi_info.get("center", None) is None:
+                self.info["center"] += [NP.asarray([90.0, 270.0]).reshape(1, -1)]
+            else:
+                c = NP.asarray(roi_info["center"], dtype=NP.float64).reshape(1, -1)
+                cc = roi_info.get("center_coords", None)
+                if cc == "dircos":
+                    self.info["center"] += [GEOM.dircos2altaz(c, units="degrees")]
+                elif cc == "altaz":
+                    self.info["center"] += [c]
+                elif cc == "hadec":
+                    self.info["center"] += [GEOM.hadec2altaz(c, lat, units="degrees")]
+                elif cc == "radec":
+                    if lst is None:
+                        raise KeyError("LST not provided for coordinate conversion")
+                    self.info["center"] += [GEOM.hadec2altaz(NP.asarray([lst - c[0, 0], c[0, 1]]).reshape(1, -1), lat, units="degrees")]
+                else:
+                    raise ValueError("Invalid coordinate system specified for center")
+            skypos_altaz = self._altaz(skymodel, lst)
+            centre = self.info["center"][-1]
+            if _sphdist(centre[0, 1], centre[0, 0], 270.0, 90.0) > 1e-2:             # :4546-4549 ROI centre is not the zenith
+                # the reference hands (alt, az) to spherematch in its (lon, lat) slots; kept as written for parity
+                ind = NP.where(_sphdist(centre[0, 0], centre[0, 1], skypos_altaz[:, 0], skypos_altaz[:, 1]) <= radius)[0]
+            else:
+                ind = NP.where(skypos_altaz[:, 0] >= 90.0 - radius)[0]                 # :4551
+            self.info["ind"] += [ind]
+        if self.info["center_coords"] is None and roi_info.get("center_coords", None) in ("altaz", "dircos", "hadec", "radec"):
+            self.info["center_coords"] = roi_info["center_coords"]                     # :4554-4557
+        if pbeam_input:
+            return
+        if pinfo is None:                                                              # :4559-4576
+            raise ValueError("Pointing info dictionary pinfo must be specified.")
+        pinfo = dict(pinfo)
+        self.pinfo += [pinfo]
+        pcoords = pinfo.get("pointing_coords", None)
+        if pcoords is not None and pcoords not in ("dircos", "altaz"):
+            if self.telescope.get("latitude", None) is None:
+                raise ValueError("Latitude of the observatory must be provided.")
+            pc = NP.asarray(pinfo["pointing_center"], dtype=NP.float64).reshape(1, -1)
+            if pcoords == "radec":
+                if lst is None:
+                    raise ValueError("LST must be provided.")
+                pc = NP.asarray([lst - pc[0, 0], pc[0, 1]]).reshape(1, -1)
+            elif pcoords != "hadec":
+                raise ValueError('pointing_coords in dictionary pinfo must be "dircos", "altaz", "hadec" or "radec".')
+            pinfo["pointing_center"] = GEOM.hadec2altaz(pc, self.telescope["latitude"], units="degrees")
+            pinfo["pointing_coords"] = "altaz"
+        ind = self.info["ind"][-1]
+        if ind.size == 0:
+            self.info["pbeam"] += [NP.asarray([])]
+            return
+        reffreq = roi_info.get("pbeam_reffreq", self.freq[self.freq.size // 2])        # :4578-4588
+        fcomp = self.freq if roi_info.get("pbeam_chromaticity", False) else NP.asarray(reffreq, dtype=NP.float64).reshape(-1)
+        if self.telescope.get("id", None) == "mwa_tools":
+            raise NotImplementedError("the external MWA_Tools beam is not on the hot path")
+        pbeam = PB.primary_beam_generator(skypos_altaz[ind, :], fcomp, self.telescope, freq_scale="Hz", skyunits="altaz",
+                                          pointing_info=pinfo, device=self.device)
+        self.info["pbeam"] += [pbeam.astype(NP.float64) * NP.ones(self.freq.size).reshape(1, -1)]   # :4615
+
+
+def _sphdist(lon1, lat1, lon2, lat2):
+    """Great-circle separation in degrees (``GEOM.sphdist`` of astroutils), haversine form."""
+    lon1, lat1, lon2, lat2 = [NP.radians(NP.asarray(v, dtype=NP.float64)) for v in (lon1, lat1, lon2, lat2)]
+    a = NP.sin(0.5 * (lat2 - lat1)) ** 2 + NP.cos(lat1) * NP.cos(lat2) * NP.sin(0.5 * (lon2 - lon1)) ** 2
+    with NP.errstate(invalid="ignore"):        # "latitudes" beyond 90 deg (the alt/az swap above) can make a < 0: NaN, never matched
+        return NP.degrees(2.0 * NP.arcsin(NP.minimum(1.0, NP.sqrt(a))))
+
+
 class InterferometerArray(object):
     """Drop-in for ``prisim.interferometry.InterferometerArray`` on the visibility hot path."""
 

@@ -90,6 +90,15 @@ def sphdist(lon1, lat1, lon2, lat2):
     return NP.degrees(2 * NP.arcsin(NP.minimum(1.0, NP.sqrt(a))))
 
 
+def spherematch(lon1, lat1, lon2, lat2, matchrad=None, nnearest=0, maxmatches=-1):
+    """GEOM.spherematch [AU-memory] as used at interferometry.py:4549 / :6213 (one centre against many points,
+    maxmatches=0): indices of the points within matchrad (great-circle, degrees) of the centre."""
+    d = sphdist(NP.asarray(lon1, dtype=float).reshape(-1, 1), NP.asarray(lat1, dtype=float).reshape(-1, 1),
+                NP.asarray(lon2, dtype=float).reshape(1, -1), NP.asarray(lat2, dtype=float).reshape(1, -1))
+    m1, m2 = NP.where(d <= matchrad)
+    return m1, m2, d[m1, m2]
+
+
 def enu2xyz(enu, latitude, units=None):
     enu = NP.asarray(enu, dtype=float).reshape(-1, 3)
     lat = NP.radians(latitude) if units == "degrees" else latitude
@@ -162,6 +171,7 @@ class SkyModel(object):
         self.flux_scale, self.spindex, self.freq_ref = map(lambda v: NP.asarray(v, dtype=float), (flux_scale, spindex, freq_ref))
         self.src_shape = src_shape
         self.epoch = epoch
+        self.coords = "hadec"
 
     def generate_spectrum(self, ind=None, frequency=None, interp_method="pchip"):
         ind = NP.arange(self.location.shape[0]) if ind is None else NP.asarray(ind)
@@ -172,7 +182,7 @@ class SkyModel(object):
 def install_stubs():
     au = _mod("astroutils", __githash__="stub")
     au.geometry = _mod("astroutils.geometry", altaz2dircos=altaz2dircos, dircos2altaz=dircos2altaz, hadec2altaz=hadec2altaz,
-                       altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu, enu2xyz=enu2xyz)
+                       altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu, enu2xyz=enu2xyz, spherematch=spherematch)
     au.DSP_modules = _mod("astroutils.DSP_modules", FT1D=FT1D, spectral_axis=spectral_axis, downsampler=downsampler,
                           windowing=windowing, window_N2width=window_N2width)
     au.catalog = _mod("astroutils.catalog", SkyModel=SkyModel)
@@ -434,6 +444,33 @@ def main():
                vis_noise_shape=NP.asarray(ia.vis_noise_freq.shape), vis_minus_noise=ia.vis_freq - ia.vis_noise_freq)
     if not ONLY or "duplicate" in ONLY:
         NP.savez_compressed(os.path.join(OUT, "duplicate.npz"), **rec)
+    # ---------------- ROI_parameters.append_settings (interferometry.py:4221-4617): per-snapshot ROI indices + beam table ----------------
+    nsrc0 = 300
+    hadec0 = NP.stack((rng.uniform(0, 360, nsrc0), NP.degrees(NP.arcsin(rng.uniform(-1, 0.6, nsrc0)))), axis=1)
+    roi_sky = SkyModel(hadec0, NP.ones(nsrc0), NP.zeros(nsrc0), NP.full(nsrc0, 150e6))
+    roi_freq = 150e6 + (NP.arange(24) - 12) * 250e3
+    roirec = dict(hadec=hadec0, freq=roi_freq, latitude=lat)
+    tel_roi = dict(hera); tel_roi.update(latitude=lat, longitude=21.4278, altitude=0.0)
+    cases = [("zenith_achromatic", {"radius": None, "center": None, "center_coords": None}),
+             ("zenith_r30_chromatic", {"radius": 30.0, "center": None, "center_coords": None, "pbeam_chromaticity": True}),
+             ("offzenith_altaz_reffreq", {"radius": 25.0, "center": NP.asarray([60.0, 140.0]), "center_coords": "altaz", "pbeam_reffreq": 151.3e6}),
+             ("offzenith_hadec", {"radius": 40.0, "center": NP.asarray([20.0, -10.0]), "center_coords": "hadec"}),
+             ("given_ind", {"ind": NP.asarray([3, 17, 44, 120, 250]), "radius": 90.0}),
+             ("given_ind_pbeam", {"ind": NP.asarray([5, 6, 7]), "pbeam": rng.uniform(0, 1, (3, 24))})]
+    roi = RI.ROI_parameters()
+    for name, ri in cases:
+        roi.append_settings(roi_sky, roi_freq, pinfo={"pointing_center": NP.asarray([[90.0, 270.0]]), "pointing_coords": "altaz"},
+                            lst=10.0, time_jd=2451545.0, roi_info=dict(ri), telescope=tel_roi, freq_scale="Hz")
+        roirec["ind_" + name] = NP.asarray(roi.info["ind"][-1]); roirec["pbeam_" + name] = NP.asarray(roi.info["pbeam"][-1])
+        if "radius" in ri and len(roi.info["radius"]):
+            roirec["radius_" + name] = NP.asarray(roi.info["radius"][-1], dtype=float)
+        if "pbeam" in ri:
+            roirec["pbeam_in_" + name] = ri["pbeam"]
+    roi.append_settings(None, roi_freq, pinfo=None, roi_info=None, telescope=tel_roi, freq_scale="Hz")
+    roirec["n_entries"] = len(roi.info["ind"]); roirec["center_coords"] = str(roi.info["center_coords"])
+    roirec["centers"] = NP.concatenate([NP.asarray(c, dtype=float).reshape(1, 2) for c in roi.info["center"]], axis=0)
+    if not ONLY or "roi_parameters" in ONLY:
+        NP.savez_compressed(os.path.join(OUT, "roi_parameters.npz"), **roirec)
     print("golden vectors written to", OUT)
 
 

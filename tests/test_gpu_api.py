@@ -133,6 +133,49 @@ def test_gradient_point_sources_vs_oracle_and_finite_difference():
     assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
+def test_roi_parameters_against_reference_golden():
+    """ROI_parameters.append_settings (interferometry.py:4221-4617) replaying the reference's own run; the tables then
+    feed observe(roi_info=...) and give the same visibilities as the internal ROI + beam path."""
+    from prisim_b200.interferometry import ROI_parameters, InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    from tests.test_oracle_golden import ROI_CASES, ROI_TELESCOPE
+    g = NP.load(os.path.join(GOLD, "roi_parameters.npz"))
+    lat = float(g["latitude"])
+    nsrc0 = g["hadec"].shape[0]
+    sky = SkyModel(init_parms={"location": g["hadec"], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+                               "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": NP.zeros(nsrc0),
+                                              "freq-ref": NP.full(nsrc0, 150e6), "flux-scale": NP.ones(nsrc0)}})
+    tel = dict(ROI_TELESCOPE); tel.update(latitude=lat, longitude=21.4278, altitude=0.0)
+    roi = ROI_parameters(device=0)
+    for name, ri in ROI_CASES:
+        ri = dict(ri)
+        if name == "given_ind_pbeam":
+            ri["pbeam"] = g["pbeam_in_" + name]
+        roi.append_settings(sky, g["freq"], pinfo={"pointing_center": NP.asarray([[90.0, 270.0]]), "pointing_coords": "altaz"}, lst=10.0,
+                            time_jd=2451545.0, roi_info=ri, telescope=tel, freq_scale="Hz")
+        assert NP.array_equal(roi.info["ind"][-1], g["ind_" + name]), name
+        pb = roi.info["pbeam"][-1]
+        assert pb.shape == g["pbeam_" + name].shape and pb.dtype == g["pbeam_" + name].dtype, name
+        assert NP.abs(pb - g["pbeam_" + name]).max() <= 2e-7, name                     # device beam table is fp32
+    roi.append_settings(None, g["freq"], telescope=tel, freq_scale="Hz")
+    assert len(roi.info["ind"]) == int(g["n_entries"]) and roi.info["center_coords"] == str(g["center_coords"])
+    assert NP.allclose(NP.concatenate([NP.asarray(c, dtype=float).reshape(1, 2) for c in roi.info["center"]]), g["centers"])
+    with pytest.raises(ValueError):
+        roi.append_settings(sky, g["freq"], pinfo=None, roi_info={"radius": 10.0, "center": None}, telescope=tel)
+    with pytest.raises(ValueError):
+        roi.append_settings(sky, g["freq"], roi_info={"ind": NP.arange(4), "pbeam": NP.ones((3, g["freq"].size))}, telescope=tel)
+    # the tables drive observe(): same visibilities as the internal cull + beam (zenith ROI, chromatic table)
+    bl = NP.asarray([[14.6, 0.0, 0.0], [0.0, 29.2, 0.0], [43.8, 14.6, 0.0]])
+    mk = lambda: InterferometerArray(["a", "b", "c"], bl, g["freq"], telescope=dict(ROI_TELESCOPE), latitude=lat, skycoords="hadec",
+                                     pointing_coords="altaz", freq_scale="Hz", device=0)
+    args = (SimpleTime(2451545.0, 10.0), {"Tnet": 100.0}, NP.ones(g["freq"].size), NP.asarray([90.0, 270.0]), sky, 10.0)
+    ia, ib = mk(), mk()
+    ia.observe(*args, roi_radius=30.0)
+    ib.observe(*args, roi_info={"ind": roi.info["ind"][1], "pbeam": roi.info["pbeam"][1]})
+    assert NP.array_equal(ia.obs_catalog_indices[0], ib.obs_catalog_indices[0])
+    assert rel_err(ib.skyvis_freq, ia.skyvis_freq) <= 1e-6
+
+
 def test_multi_window_delay_transform_against_reference_golden():
     """Sub-band delay transforms (interferometry.py:8141-8287) replaying the reference's own run on the 'hera' case."""
     from prisim_b200.interferometry import InterferometerArray, SimpleTime

@@ -258,3 +258,30 @@ def test_multi_window_delay_transform_matches_reference():
         O.multi_window_weights(g["chans"], [1e6, 2e6], [150e6, 150.5e6, 151e6])
     with pytest.raises(ValueError):
         O.multi_window_weights(g["chans"], 1e6, g["chans"][0])
+
+
+ROI_CASES = [("zenith_achromatic", {"radius": None, "center": None, "center_coords": None}),
+             ("zenith_r30_chromatic", {"radius": 30.0, "center": None, "center_coords": None, "pbeam_chromaticity": True}),
+             ("offzenith_altaz_reffreq", {"radius": 25.0, "center": NP.asarray([60.0, 140.0]), "center_coords": "altaz", "pbeam_reffreq": 151.3e6}),
+             ("offzenith_hadec", {"radius": 40.0, "center": NP.asarray([20.0, -10.0]), "center_coords": "hadec"}),
+             ("given_ind", {"ind": NP.asarray([3, 17, 44, 120, 250]), "radius": 90.0}),
+             ("given_ind_pbeam", {"ind": NP.asarray([5, 6, 7])})]
+ROI_TELESCOPE = {"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "groundplane": None}
+
+
+def test_roi_parameters_append_settings_matches_reference():
+    """ROI_parameters.append_settings (interferometry.py:4221-4617) run by the reference: indices and beam tables."""
+    g = _load("roi_parameters.npz")
+    lat = float(g["latitude"])
+    pinfo = {"pointing_center": NP.asarray([[90.0, 270.0]]), "pointing_coords": "altaz"}
+    for name, ri in ROI_CASES:
+        ri = dict(ri)
+        if name == "given_ind_pbeam":
+            ri["pbeam"] = g["pbeam_in_" + name]
+        ind, pbeam, radius, center = O.roi_append_settings(g["hadec"], "hadec", lat, g["freq"], dict(ROI_TELESCOPE), ri, pinfo=pinfo, lst=10.0)
+        assert NP.array_equal(ind, g["ind_" + name]), name
+        assert pbeam.shape == g["pbeam_" + name].shape and pbeam.dtype == g["pbeam_" + name].dtype, name
+        assert NP.allclose(pbeam, g["pbeam_" + name], rtol=1e-11, atol=1e-14), name
+        if "radius_" + name in g.files and radius is not None:
+            assert float(g["radius_" + name]) == radius
+    assert int(g["n_entries"]) == len(ROI_CASES) + 1 and str(g["center_coords"]) == "altaz"
