@@ -44,11 +44,15 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
 #ifndef PB_LIFT_MAX_ANGLE
 #define PB_LIFT_MAX_ANGLE 2.0   // rad per two-channel step; tan(1) = 1.56 keeps the shear intermediates below 2.6
 #endif
+#ifndef PB_SRC_UNROLL
+#define PB_SRC_UNROLL 4    // sources in flight per thread in the channel loop (measured: 1 -> 4.34, 4 -> 4.42 Tterms/s at the time)
+#endif
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
 #define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
 #endif
 constexpr int FLUSH_TILES = PB_FLUSH_TILES;                // fp32 -> fp64 flush cadence (512 sources); measured max error at C2 / speed: 6.3e-6 / 4.42 @32, 5.5e-6 @16, 4.7e-6 / 4.29 @8
 constexpr int NSTAGE = 2;
+constexpr int SRC_UNROLL = PB_SRC_UNROLL;
 constexpr int STAGGER = PB_STAGGER;                     // source-loop chunks per tile between which the warps of a scheduler take turns precomputing
 // CTA shape: SPC slabs (SPC*128 channels) x WB baseline groups, SPC*WCS*WB = 16 warps.  A wider
 // channel extent shares each (source, baseline) delay/rotation among more warps (less per-tile
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
 #pragma unroll 1
     for (int chunk = 0; chunk < STAGGER; ++chunk) {
     if (chunk == (warp >> 2) % STAGGER && tile + 1 < ntiles && !((PB_ABLATE & 1) && tile > 0)) precompute(tile + 1);
-#pragma unroll 4
+#pragma unroll SRC_UNROLL
     for (int s = chunk * (T / STAGGER); s < (chunk + 1) * (T / STAGGER); ++s) {
       const float2 p0 = p_next, q0 = q_next, r = r_next;
       const int sn = (s + 1 < T) ? s + 1 : s;
