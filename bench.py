@@ -354,8 +354,9 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per k_skyvis launch at the headline size, from the
 # committed ncu capture (profiles/); None until that capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 21.88e9   # profiles/skyvis_headline_r01_ncu.txt: 20.45 GB read + 1.43 GB written (0.13 % of HBM bandwidth over 2.57 s;
-                                      # the amplitude table is re-streamed once per wave of CTAs, 26 waves x 0.73 GB)
+TRAFFIC_BYTES_PER_LAUNCH = 29.70e9   # profiles/skyvis_headline_r01_ncu.txt: 22.86 GB read + 6.84 GB written (0.19 % of HBM bandwidth over 2.44 s;
+                                      # the amplitude table is re-streamed once per wave of CTAs, 26 waves x 0.73 GB; the staggered fp64
+                                      # flushes keep less of the 1 GB running-sum scratch resident in L2 than the synchronous ones did)
 
 if __name__ == "__main__":
     main()
