@@ -16,6 +16,7 @@
 // HBM-bound: algorithmic bytes per row = nchan*(16 + 8 + 8) read + nout*16 written.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -130,12 +131,30 @@ template <> __device__ __forceinline__ void ifft_small<8>(double2 (&v)[8]) {
   for (int i = 0; i < 4; ++i) { v[2 * i] = a[i]; v[2 * i + 1] = b[i]; }
 }
 
+// w^1 .. w^(R-1) from ONE table load: the kernel is bound by L1/TEX requests (21 twiddle loads per thread were a
+// quarter of them) while the FP64 pipe idles at 16 %, so the powers are formed by 6 complex multiplications
+// (squares where possible; error <= 3 ulp)
+template <int R> struct TwiddlePowers {
+  double2 w[R];
+  __device__ __forceinline__ explicit TwiddlePowers(const double2 w1) {
+    w[0] = make_double2(1.0, 0.0);
+    if (R > 1) w[1] = w1;
+    if (R > 2) w[2] = cmul(w1, w1);
+    if (R > 3) w[3] = cmul(w[2], w1);
+    if (R > 4) w[4] = cmul(w[2], w[2]);
+    if (R > 5) w[5] = cmul(w[4], w1);
+    if (R > 6) w[6] = cmul(w[3], w[3]);
+    if (R > 7) w[7] = cmul(w[6], w1);
+  }
+};
+
 // branch-free loader (all loads of a butterfly in flight together): bp / wts always valid pointers
 // (the host substitutes a broadcast "ones" row), index clamped for the zero-padded tail
 template <bool HAS_X>
 __device__ __forceinline__ double2 load_in_nb(const DelayParams& P, int row, int n) {
   const int nc = n < P.nchan ? n : P.nchan - 1;
-  const double w = P.bp[(size_t)row * P.bp_stride + nc] * P.wts[(size_t)row * P.wts_stride + nc];
+  double w = P.bp[(size_t)row * P.bp_stride + nc];
+  if (P.wts) w *= P.wts[(size_t)row * P.wts_stride + nc];                 // uniform predicate; null = already folded into bp
   double2 v = make_double2(1.0, 0.0);
   if (HAS_X) v = P.x[(size_t)row * P.nchan + nc];
   const double m = n < P.nchan ? w : 0.0;
@@ -160,9 +179,9 @@ __device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, boo
         for (int r = 0; r < R; ++r) v[r] = first ? load_in_nb<HAS_X>(P, row, j + r * NR) : buf[padi(j + r * NR)];
         const int k = j & (Ns - 1);
         if (Ns > 1) {
-          const int tstep = k * (N / (Ns * R));
+          const TwiddlePowers<R> tw(__ldg(&P.twiddle[(k * (N / (Ns * R))) & (N - 1)]));
 #pragma unroll
-          for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(&P.twiddle[(r * tstep) & (N - 1)]));
+          for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw.w[r]);
         }
         ifft_small<R>(v);
         const int j0 = (j - k) * R + k;
@@ -185,9 +204,9 @@ __device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, boo
   if (active) {
     const int k = j & (Ns - 1);
     if (Ns > 1) {
-      const int tstep = k * (N / (Ns * R));
+      const TwiddlePowers<R> tw(__ldg(&P.twiddle[(k * (N / (Ns * R))) & (N - 1)]));
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(&P.twiddle[(r * tstep) & (N - 1)]));
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw.w[r]);
     }
     ifft_small<R>(v);
     const int j0 = (j - k) * R + k;
@@ -197,8 +216,11 @@ __device__ __forceinline__ void stockham_pass(const DelayParams& P, int row, boo
   __syncthreads();                              // outputs visible to the next pass
 }
 
+#ifndef PB_DT_MINBLOCKS     // resident CTAs per SM asked of ptxas: 2 -> 128 registers, no spills (0.67 ms at C2 size); 3 / 4 -> 80 / 64
+#define PB_DT_MINBLOCKS 2   // registers with 600-850 bytes of spills, 1.35 / 1.32 ms
+#endif
 template <bool HAS_X>
-__global__ void __launch_bounds__(256) k_delay_fft_r8(const DelayParams P, int T, int rows_per_cta) {
+__global__ void __launch_bounds__(256, PB_DT_MINBLOCKS) k_delay_fft_r8(const DelayParams P, int T, int rows_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.nfft;
   const int lrow = threadIdx.x / T, t = threadIdx.x % T;
@@ -253,6 +275,11 @@ __global__ void __launch_bounds__(FFT_THREADS) k_delay_dft(const DelayParams P) 
     }
     P.out[(size_t)row * P.nout + i] = make_double2(o.x * P.scale, o.y * P.scale);
   }
+}
+
+__global__ void k_mul_rows(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i];
 }
 
 __global__ void k_fill_ones(double* p, int n) {
@@ -326,15 +353,23 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
     const int T = pl.nfft / 8;                         // one radix-8 butterfly per thread and pass
     const int rows_per_cta = 256 / T;
     const size_t smem = sizeof(double2) * (size_t)(pl.nfft + (pl.nfft >> 3)) * rows_per_cta;
-    // bp / wts default to a broadcast row of ones so the loader needs no null checks
-    if (!P.bp || !P.wts) {
-      void* ones;
-      int rc1 = pb_scratch(ctx, 6, sizeof(double) * (size_t)nchan, &ones);
+    // one weight vector where possible (every load is an L1/TEX request, the unit this kernel is bound by): a missing
+    // factor is dropped, two broadcast rows are multiplied once into scratch; only per-row bp AND wts keep two loads
+    {
+      void* tmp;
+      int rc1 = pb_scratch(ctx, 6, sizeof(double) * (size_t)nchan, &tmp);
       if (rc1) return rc1;
-      k_fill_ones<<<pb_div_up(nchan, 256), 256, 0, stream>>>((double*)ones, nchan);
-      PB_CHECK_LAUNCH(ctx, "k_fill_ones");
-      if (!P.bp) { P.bp = (const double*)ones; P.bp_stride = 0; }
-      if (!P.wts) { P.wts = (const double*)ones; P.wts_stride = 0; }
+      if (!P.bp && !P.wts) {
+        k_fill_ones<<<pb_div_up(nchan, 256), 256, 0, stream>>>((double*)tmp, nchan);
+        PB_CHECK_LAUNCH(ctx, "k_fill_ones");
+        P.bp = (const double*)tmp; P.bp_stride = 0;
+      } else if (!P.bp) {
+        P.bp = P.wts; P.bp_stride = P.wts_stride; P.wts = nullptr;
+      } else if (P.wts && P.bp_stride == 0 && P.wts_stride == 0) {
+        k_mul_rows<<<pb_div_up(nchan, 256), 256, 0, stream>>>(P.bp, P.wts, (double*)tmp, nchan);
+        PB_CHECK_LAUNCH(ctx, "k_mul_rows");
+        P.bp = (const double*)tmp; P.wts = nullptr;
+      }
     }
     if (P.x) {
       PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_r8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
