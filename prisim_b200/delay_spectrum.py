@@ -57,7 +57,7 @@ class DelaySpectrum(object):
         self.f = self.ia.channels
         self.df = self.ia.freq_resolution
         self.n_acc = self.ia.n_acc
-        self.horizon_delay_limits = None
+        self.horizon_delay_limits = self.get_horizon_delay_limits() if self.ia.n_acc > 0 else None   # :1183
         self.pad = None
         self.lags = None
         self.bp_wts = None
@@ -66,6 +66,83 @@ class DelaySpectrum(object):
     @property
     def bp(self):
         return self.ia.bp
+
+    def get_horizon_delay_limits(self, phase_center=None, phase_center_coords=None):
+        """delay_spectrum.py:2976-3030: [n_phase_centres, nbl, 2] minimum / maximum horizon delay of every baseline."""
+        from . import baseline_delay_horizon as DLY
+        from . import geometry as GEOM
+        if phase_center is None:
+            phase_center = self.ia.phase_center
+            phase_center_coords = self.ia.phase_center_coords
+        if phase_center_coords not in ["hadec", "altaz", "dircos"]:
+            raise ValueError('Phase center coordinates must be "altaz", "hadec" or "dircos"')
+        if phase_center_coords == "hadec":
+            pc_dircos = GEOM.altaz2dircos(GEOM.hadec2altaz(phase_center, self.ia.latitude, units="degrees"), units="degrees")
+        elif phase_center_coords == "altaz":
+            pc_dircos = GEOM.altaz2dircos(phase_center, units="degrees")
+        else:
+            pc_dircos = phase_center
+        return DLY.horizon_delay_limits(self.ia.baselines, pc_dircos, units="mks")
+
+    def delay_transform_allruns(self, vis, pad=1.0, freq_wts=None, downsample=True, verbose=True):
+        """delay_spectrum.py:1475-1618: delay-transform external visibilities of shape (..., nbl, nchan, ntimes) (several
+        runs / realisations) with this object's bandpass; returns {'freq_wts', 'pad', 'lags', 'vis_lag', 'lag_kernel'}
+        with the reference's shapes.  Every (run, snapshot) slice is one launch of the delay-transform kernel."""
+        if not isinstance(vis, NP.ndarray):
+            raise TypeError("Input vis must be a numpy array")
+        ia = self.ia
+        nbl, nchan, nt = ia.baselines.shape[0], self.f.size, self.n_acc
+        if vis.ndim < 3:
+            raise ValueError("Input vis must be at least 3-dimensional")
+        if vis.shape[-3:] != (nbl, nchan, nt):
+            raise ValueError("Input vis does not have compatible shape")
+        if vis.ndim == 3:
+            vis = vis.reshape((1,) + vis.shape)
+        if not isinstance(pad, (int, float)):
+            raise TypeError("pad fraction must be a scalar value.")
+        if pad < 0.0:
+            pad = 0.0
+        if not isinstance(downsample, bool):
+            raise TypeError("Input downsample must be of boolean type")
+        lead = vis.shape[:-3]
+        ones = (1,) * len(lead)
+        if freq_wts is not None:                                                          # :1541-1551
+            freq_wts = NP.asarray(freq_wts)
+            if freq_wts.shape == self.f.shape:
+                wts_full = freq_wts.reshape(ones + (1, -1, 1))
+            elif freq_wts.shape == (nchan, nt):
+                wts_full = freq_wts.reshape(ones + (1, nchan, nt))
+            elif freq_wts.shape == (nbl, nchan):
+                wts_full = freq_wts.reshape(ones + (nbl, nchan, 1))
+            elif freq_wts.shape == (nbl, nchan, nt):
+                wts_full = freq_wts.reshape(ones + (nbl, nchan, nt))
+            elif freq_wts.shape == vis.shape:
+                raise NotImplementedError("per-run frequency weights are not on the device path")
+            else:
+                raise ValueError("window shape dimensions incompatible with number of channels and/or number of tiemstamps.")
+            getter = ia._freq_wts_getter(freq_wts)
+        else:                                                                             # :1552-1553 the stored weights
+            stored = self.bp_wts if self.bp_wts is not None else ia.bp_wts
+            wts_full = NP.asarray(stored).reshape(ones + NP.asarray(stored).shape)
+            getter = ia._bp_wts if self.bp_wts is None else ia._freq_wts_getter(self.bp_wts)
+        nout = engine.delay_nout(nchan, pad, downsample)
+        flat = vis.reshape((-1, nbl, nchan, nt))
+        out = NP.empty((flat.shape[0], nbl, nout, nt), dtype=NP.complex128)
+        kern = NP.empty((nbl, nout, nt), dtype=NP.complex128)
+        for t in range(nt):
+            bp = ia._bp[t]
+            wts = None if getter is None else getter(t)
+            krows = nbl if (bp.ndim == 2 or (wts is not None and wts.ndim == 2)) else 1
+            k = engine.delay_transform(None, bp, wts, self.df, pad=pad, downsample=downsample, nrows=krows, nchan=nchan, device=ia.device)
+            kern[:, :, t] = k.cpu().numpy()
+            for r in range(flat.shape[0]):
+                x = engine._c128(NP.ascontiguousarray(flat[r, :, :, t]), ia.device)
+                out[r, :, :, t] = engine.delay_transform(x, bp, wts, self.df, pad=pad, downsample=downsample).cpu().numpy()
+        lags = NP.fft.fftshift(NP.fft.fftfreq(int(nchan * (1 + pad)), d=self.df))           # :1575
+        if downsample and pad > 0.0:                                                          # :1596
+            lags = NP.interp(NP.arange(0, lags.size, 1 + pad), NP.arange(lags.size), lags)
+        return {"freq_wts": wts_full, "pad": pad, "lags": lags.flatten(), "vis_lag": out.reshape(lead + (nbl, nout, nt)),
+                "lag_kernel": kern.reshape(ones + (nbl, nout, nt))}
 
     def delay_transform(self, pad=1.0, freq_wts=None, downsample=True, action=None, verbose=True):
         """delay_spectrum.py:1224-1342."""

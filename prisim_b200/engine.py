@@ -29,6 +29,13 @@ def _f64(x, device):
     return torch.as_tensor(NP.ascontiguousarray(x, dtype=NP.float64)).to("cuda:{0}".format(device))
 
 
+def _c128(x, device):
+    """Host array-like or tensor -> contiguous complex128 CUDA tensor on `device`."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda:{0}".format(device), dtype=torch.complex128).contiguous()
+    return torch.as_tensor(NP.ascontiguousarray(x, dtype=NP.complex128)).to("cuda:{0}".format(device))
+
+
 def _h64(x):
     return NP.ascontiguousarray(NP.asarray(x, dtype=NP.float64))
 

@@ -246,6 +246,20 @@ def main():
     DLY = load_reference("baseline_delay_horizon")
     PB = load_reference("primary_beams")
     RI = load_reference("interferometry")
+    # delay_spectrum.py imports its siblings through the package and a few more third-party names at module level
+    pr = sys.modules["prisim"]
+    pr.primary_beams, pr.interferometry, pr.baseline_delay_horizon = PB, RI, DLY
+    sys.modules.update({"prisim.primary_beams": PB, "prisim.interferometry": RI, "prisim.baseline_delay_horizon": DLY})
+
+    class _Cosmo(object):
+        H0, h = 67.7, 0.677
+
+        def clone(self, **kw):
+            return self
+    sys.modules["astropy"].cosmology = _mod("astropy.cosmology", Planck15=_Cosmo(), WMAP9=_Cosmo())
+    _mod("healpy")
+    sys.modules["astroutils"].writer_module = _mod("astroutils.writer_module")
+    DSM = load_reference("delay_spectrum")
     rng = NP.random.default_rng(20261017)
     lat = -30.7224
 
@@ -367,6 +381,21 @@ def main():
         rec["skyvis_lag_pad05"] = ia.skyvis_lag
         if not ONLY or tag in ONLY:
             NP.savez_compressed(os.path.join(OUT, "observe_{0}.npz".format(tag)), **rec)
+        if tag == "hera" and (not ONLY or "allruns_hera" in ONLY):
+            # DelaySpectrum.delay_transform / delay_transform_allruns (delay_spectrum.py:1224-1342, :1475-1618) on the same object
+            ds = DSM.DelaySpectrum(interferometer_array=ia)
+            runs = NP.stack((ia.vis_freq, 0.5 * ia.skyvis_freq, 1j * ia.vis_noise_freq), axis=0).reshape(3, 1, nbl, nchan, nsnap)
+            ar = {"runs": runs, "horizon_delay_limits": ds.horizon_delay_limits}
+            r = ds.delay_transform_allruns(runs, pad=1.0, freq_wts=window, downsample=True, verbose=False)
+            ar.update(vis_lag_pad1=r["vis_lag"], lag_kernel_pad1=r["lag_kernel"], lags_pad1=r["lags"])
+            r = ds.delay_transform_allruns(ia.skyvis_freq, pad=0.5, freq_wts=None, downsample=False, verbose=False)
+            ar.update(vis_lag_pad05_full=r["vis_lag"], lag_kernel_pad05_full=r["lag_kernel"], lags_pad05_full=r["lags"])
+            wts2 = NP.outer(window, [1.0, 0.5, 0.25][:nsnap])                  # [nchan, nsnap] form of freq_wts
+            r = ds.delay_transform_allruns(ia.skyvis_freq, pad=0.0, freq_wts=wts2, downsample=True, verbose=False)
+            ar.update(vis_lag_pad0_w2=r["vis_lag"], wts2=wts2)
+            r = ds.delay_transform(pad=1.0, freq_wts=window, downsample=True, action="return", verbose=False)
+            ar.update(ds_skyvis_lag=r["skyvis_lag"], ds_vis_lag=r["vis_lag"], ds_lags=r["lags"], ds_lag_kernel=r["lag_kernel"])
+            NP.savez_compressed(os.path.join(OUT, "allruns_hera.npz"), **ar)
         if tag == "hera" and (not ONLY or "multiwin_hera" in ONLY):
             # multi_window_delay_transform (interferometry.py:8141-8287): three sub-bands, Blackman-Harris, pad 1.0 and 0.0
             mw = {}

@@ -133,6 +133,53 @@ def test_gradient_point_sources_vs_oracle_and_finite_difference():
     assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
+def test_delay_spectrum_allruns_against_reference_golden():
+    """DelaySpectrum.delay_transform / delay_transform_allruns / horizon limits (delay_spectrum.py:1224-1342, :1475-1618,
+    :2976-3030) replaying the reference's own DelaySpectrum on the 'hera' case."""
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    from prisim_b200.delay_spectrum import DelaySpectrum
+    g = NP.load(os.path.join(GOLD, "observe_hera.npz"))
+    a = NP.load(os.path.join(GOLD, "allruns_hera.npz"))
+    nbl, nchan, nsnap = g["skyvis_freq"].shape
+    ia = InterferometerArray([("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)], g["bl"], g["chans"], telescope=dict(OBSERVE_CASES["hera"]["telescope"]),
+                             eff_Q=0.96, latitude=float(g["latitude"]), longitude=21.4278, skycoords="hadec", A_eff=154.0 * 0.65,
+                             pointing_coords="hadec", freq_scale="Hz", device=0, noise_seed=5)
+    nsrc0 = g["flux"].size
+    for j in range(nsnap):
+        parms = {"location": g["hadec_{0}".format(j)], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+                 "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": g["spindex"], "freq-ref": NP.full(nsrc0, 150e6),
+                                "flux-scale": g["flux"]}}
+        ia.observe(SimpleTime(2451545.0 + j * 0.01, float(g["lsts"][j])), {"Trx": 50.0, "Tant": {"T0": 200.0, "f0": 150e6, "spindex": -2.55}, "Tnet": None},
+                   g["bandpass"], g["pointing"], SkyModel(init_parms=parms), float(g["t_acc"][j]))
+    ia.generate_noise(); ia.add_noise()
+    ia.delay_transform(pad=1.0, freq_wts=g["window"], verbose=False)     # as in the golden run: leaves the window in ia.bp_wts
+    ds = DelaySpectrum(interferometer_array=ia)
+    assert NP.allclose(ds.horizon_delay_limits, a["horizon_delay_limits"], rtol=1e-12, atol=1e-20)
+    # external runs (the golden file's own arrays), vector window, pad 1 + downsample
+    r = ds.delay_transform_allruns(a["runs"], pad=1.0, freq_wts=g["window"], downsample=True, verbose=False)
+    assert r["vis_lag"].shape == a["vis_lag_pad1"].shape and r["lag_kernel"].shape == a["lag_kernel_pad1"].shape
+    assert NP.abs(r["vis_lag"] - a["vis_lag_pad1"]).max() <= 1e-10 * NP.abs(a["vis_lag_pad1"]).max()
+    assert NP.abs(r["lag_kernel"] - a["lag_kernel_pad1"]).max() <= 1e-10 * NP.abs(a["lag_kernel_pad1"]).max()
+    assert NP.allclose(r["lags"], a["lags_pad1"]) and r["pad"] == 1.0 and r["freq_wts"].shape == (1, 1, 1, nchan, 1)
+    # [nchan, nsnap] window, no padding
+    r = ds.delay_transform_allruns(g["skyvis_freq"], pad=0.0, freq_wts=a["wts2"], verbose=False)
+    assert NP.abs(r["vis_lag"] - a["vis_lag_pad0_w2"]).max() <= 1e-10 * NP.abs(a["vis_lag_pad0_w2"]).max()
+    # freq_wts=None -> the weights stored by the last ia.delay_transform; pad 0.5 without downsampling (48-point transform)
+    r = ds.delay_transform_allruns(g["skyvis_freq"], pad=0.5, freq_wts=None, downsample=False, verbose=False)
+    assert r["vis_lag"].shape == a["vis_lag_pad05_full"].shape and NP.allclose(r["lags"], a["lags_pad05_full"])
+    assert NP.abs(r["vis_lag"] - a["vis_lag_pad05_full"]).max() <= 1e-10 * NP.abs(a["vis_lag_pad05_full"]).max()
+    assert NP.abs(r["lag_kernel"] - a["lag_kernel_pad05_full"]).max() <= 1e-10 * NP.abs(a["lag_kernel_pad05_full"]).max()
+    # the object's own products
+    r = ds.delay_transform(pad=1.0, freq_wts=g["window"], downsample=True, action="return", verbose=False)
+    assert rel_err(r["skyvis_lag"], a["ds_skyvis_lag"]) <= TOL and NP.allclose(r["lags"], a["ds_lags"])
+    assert NP.abs(r["lag_kernel"] - a["ds_lag_kernel"]).max() <= 1e-10 * NP.abs(a["ds_lag_kernel"]).max()
+    with pytest.raises(ValueError):
+        ds.delay_transform_allruns(g["skyvis_freq"][:, :-1, :])
+    with pytest.raises(TypeError):
+        ds.delay_transform_allruns([1, 2, 3])
+
+
 def test_roi_parameters_against_reference_golden():
     """ROI_parameters.append_settings (interferometry.py:4221-4617) replaying the reference's own run; the tables then
     feed observe(roi_info=...) and give the same visibilities as the internal ROI + beam path."""
