@@ -10,7 +10,8 @@
 //                 integer m and nchan is even, decimating the m*nchan-point padded transform by m
 //                 is exactly the nchan-point transform, so that one is computed (default pad=1).
 //   k_delay_fft   radix-2 in-smem inverse FFT with linear-interpolated decimation on store: the
-//                 remaining power-of-two cases (non-integer decimation, N < 64, N >= 4096).
+//                 remaining power-of-two cases (non-integer decimation, N < 64, N >= 4096) and
+//                 lengths 3 * 2^k (pad = 0.5): three interleaved 2^k-point transforms + radix-3 combine.
 //   k_delay_dft   direct evaluation of just the output samples needed (any length, any pad):
 //                 O(nout * nchan) per row, twiddles from an exact integer-indexed table.
 // HBM-bound: algorithmic bytes per row = nchan*(16 + 8 + 8) read + nout*16 written.
@@ -30,6 +31,7 @@ struct DelayParams {
   double2* out;              // [nrows, nout]
   const double2* twiddle;    // exp(+2 pi i j / nfft), j < nfft
   int nrows, nchan, nfft, log2n, nout;
+  int radix3;                // nfft = 3 * 2^log2n (k_delay_fft only): three interleaved 2^log2n-point transforms + a radix-3 combine
   int shift;                 // (nfft+1)/2: fftshift(X)[j] = X[(j + shift) % nfft]
   double scale;              // df  ( = (1/nfft) * nfft * df )
   double factor;             // decimation step in units of the nfft grid (1 = none)
@@ -54,22 +56,42 @@ __global__ void __launch_bounds__(FFT_THREADS) k_delay_fft(const DelayParams P) 
   double2* buf = reinterpret_cast<double2*>(smem_raw);
   const int row = blockIdx.x;
   const int N = P.nfft;
-  // bit-reversed load
+  const int NSUB = P.radix3 ? 3 : 1;            // interleaved sub-sequences x[NSUB m + r], each M = N / NSUB = 2^log2n points
+  const int M = N / NSUB;
+  // decimation in time: sub-sequence r goes to buf[r M ...] in bit-reversed order
   for (int n = threadIdx.x; n < N; n += FFT_THREADS) {
-    int r = (int)(__brev((unsigned)n) >> (32 - P.log2n));
-    buf[r] = load_in(P, row, n);
+    const int r = n % NSUB, m = n / NSUB;
+    const int br = P.log2n > 0 ? (int)(__brev((unsigned)m) >> (32 - P.log2n)) : 0;
+    buf[r * M + br] = load_in(P, row, n);
   }
   __syncthreads();
   for (int st = 1; st <= P.log2n; ++st) {
     const int half = 1 << (st - 1);
-    const int tstride = N >> st;
+    const int tstride = NSUB * (M >> st);        // exp(+2 pi i j / 2^st) = twiddle[j * N / 2^st]
     for (int i = threadIdx.x; i < N / 2; i += FFT_THREADS) {
-      int j = i & (half - 1);
-      int base = ((i - j) << 1) + j;
+      const int sub = i / (M / 2), ii = i - sub * (M / 2);
+      int j = ii & (half - 1);
+      int base = sub * M + ((ii - j) << 1) + j;
       double2 w = P.twiddle[j * tstride];
       double2 a = buf[base], bb = cmul(buf[base + half], w);
       buf[base] = make_double2(a.x + bb.x, a.y + bb.y);
       buf[base + half] = make_double2(a.x - bb.x, a.y - bb.y);
+    }
+    __syncthreads();
+  }
+  if (P.radix3) {
+    // X[k + s M] = Y0[k] + w3^s W^k Y1[k] + w3^(2s) W^(2k) Y2[k],  W = exp(+2 pi i / N), w3 = exp(+2 pi i / 3); in place per k
+    const double hs = 0.86602540378443864676;    // sin(2 pi / 3)
+    for (int k = threadIdx.x; k < M; k += FFT_THREADS) {
+      const double2 a = buf[k];
+      const double2 b = cmul(buf[M + k], P.twiddle[k]);
+      const double2 c = cmul(buf[2 * M + k], P.twiddle[(2 * k) % N]);
+      const double2 sum = make_double2(b.x + c.x, b.y + c.y), dif = make_double2(b.x - c.x, b.y - c.y);
+      const double2 re = make_double2(a.x - 0.5 * sum.x, a.y - 0.5 * sum.y);           // a + (b + c) cos(2 pi/3)
+      const double2 im = make_double2(-hs * dif.y, hs * dif.x);                         // i sin(2 pi/3) (b - c)
+      buf[k] = make_double2(a.x + sum.x, a.y + sum.y);
+      buf[M + k] = make_double2(re.x + im.x, re.y + im.y);
+      buf[2 * M + k] = make_double2(re.x - im.x, re.y - im.y);
     }
     __syncthreads();
   }
@@ -296,7 +318,7 @@ __global__ void k_twiddle(double2* tw, int n) {
   tw[j] = make_double2(cs, sn);
 }
 
-struct Plan { int nfft, nout; double factor; bool pow2; int log2n; };
+struct Plan { int nfft, nout; double factor; bool pow2; int log2n; bool three_pow2; };
 
 Plan make_plan(int nchan, double pad, int downsample) {
   Plan p;
@@ -313,6 +335,16 @@ Plan make_plan(int nchan, double pad, int downsample) {
   p.pow2 = (p.nfft & (p.nfft - 1)) == 0 && p.nfft >= 2 && p.nfft <= 8192;
   p.log2n = 0;
   while ((1 << p.log2n) < p.nfft) ++p.log2n;
+  // 3 * 2^k (e.g. pad = 0.5 on a power-of-two band): three interleaved 2^k-point transforms and a radix-3 combine
+  p.three_pow2 = false;
+  if (!p.pow2 && p.nfft % 3 == 0) {
+    const int m = p.nfft / 3;
+    if ((m & (m - 1)) == 0 && m >= 1 && p.nfft <= 12288) {
+      p.three_pow2 = true;
+      p.log2n = 0;
+      while ((1 << p.log2n) < m) ++p.log2n;
+    }
+  }
   return p;
 }
 
@@ -349,6 +381,7 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
   P.nrows = nrows; P.nchan = nchan; P.nfft = pl.nfft; P.log2n = pl.log2n; P.nout = pl.nout;
   P.shift = (pl.nfft + 1) / 2;
   P.scale = df; P.factor = pl.factor;
+  P.radix3 = pl.three_pow2 ? 1 : 0;
   if (pl.pow2 && pl.factor == 1.0 && pl.nfft >= 64 && pl.nfft <= 2048) {
     const int T = pl.nfft / 8;                         // one radix-8 butterfly per thread and pass
     const int rows_per_cta = 256 / T;
@@ -379,7 +412,7 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
       k_delay_fft_r8<false><<<pb_div_up(nrows, rows_per_cta), 256, smem, stream>>>(P, T, rows_per_cta);
     }
     PB_CHECK_LAUNCH(ctx, "k_delay_fft_r8");
-  } else if (pl.pow2) {
+  } else if (pl.pow2 || pl.three_pow2) {
     size_t smem = sizeof(double2) * (size_t)pl.nfft;
     PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_delay_fft<<<nrows, FFT_THREADS, smem, stream>>>(P);
