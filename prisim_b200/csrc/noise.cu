@@ -4,7 +4,7 @@
 //
 // The reference draws from numpy's global Mersenne Twister (:6693), which makes the result depend
 // on call order and on how the work is split; here the deviates come from Philox4x32-10 keyed by
-// (seed, global element index), so any sharding of baselines over GPUs reproduces the same noise.
+// (seed, global row = snapshot x baseline, channel), so any sharding of baselines over GPUs reproduces the same noise.
 // HBM-bound elementwise kernel: algorithmic bytes per element = 16 (skyvis) + 8 (Tsys) + 8 (A_eff)
 // + 8 (eff_Q) read, 8 (rms) + 16 (noise) + 16 (vis) written = 80 B.
 #include "common.cuh"
@@ -37,50 +37,75 @@ struct NoiseParams {
   double scale;            // 2k/sqrt(df t)/Jy  or 1/sqrt(df t)
   int flux_unit_k;
   unsigned long long seed;
-  long long elem_offset;   // (snapshot*nbl_total + bl_offset)*nchan
-  long long n;
+  long long row_offset;    // snapshot*nbl_total + bl_offset: global row of this shard's first baseline
+  long long nrows;
   long long st[6];         // element strides (row, col) of tsys, aeff, effq
   int nchan;
   int add_only;
 };
 
+// One standard complex normal pair (N + iN) from two 32-bit words: Box-Muller in fp32 (accurate logf / sincospif, on
+// the otherwise idle FP32 pipe) -- the deviates carry 24 significant bits and reach 6.7 sigma, the thermal rms and the
+// scaling stay fp64.  An fp64 Box-Muller on 53-bit uniforms (the first version of this kernel) made it FP64-issue
+// bound at 3.9 TB/s; noise parity with the reference is statistical by construction (different generator).
+__device__ __forceinline__ float2 normal_pair(uint32_t w0, uint32_t w1) {
+  const float u1 = (float)(((double)w0 + 0.5) * (1.0 / 4294967296.0));      // (0, 1]
+  const float u2 = (float)w1 * (1.0f / 4294967296.0f);                       // [0, 1]: sincospi is periodic
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(rad * cs, rad * sn);
+}
+
+// Thread = the two elements (row, c) and (row, c + H) of one row, H = ceil(nchan / 2): they share ONE generator call,
+// Philox(counter = global_row * H + c, key = seed), words 0-1 for the first and 2-3 for the second, and every access
+// of a warp is a contiguous run (lanes = consecutive c).  The counter depends on the global row only, so any sharding
+// of the baselines (rows) reproduces the same numbers.
 __global__ void __launch_bounds__(256) k_noise(const NoiseParams P) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n) return;
+  const int H = (P.nchan + 1) >> 1;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.nrows * (long long)H) return;
+  long long row; int c;
+  if (P.nrows * (long long)H < (1ll << 31)) { const unsigned u = (unsigned)t; row = u / (unsigned)H; c = (int)(u - (unsigned)row * (unsigned)H); }
+  else { row = t / H; c = (int)(t - row * H); }
+  const int ne = (c + H < P.nchan) ? 2 : 1;
   if (P.add_only) {                                             // vis = gains*skyvis + noise (:6722)
-    double2 v = P.skyvis[i], nzi = P.noise[i];
-    if (P.gains) {
-      double2 gn = P.gains[i];
-      v = make_double2(gn.x * v.x - gn.y * v.y, gn.x * v.y + gn.y * v.x);
+    for (int e = 0; e < ne; ++e) {
+      const long long i = row * P.nchan + c + e * H;
+      double2 v = P.skyvis[i], nzi = P.noise[i];
+      if (P.gains) {
+        double2 gn = P.gains[i];
+        v = make_double2(gn.x * v.x - gn.y * v.y, gn.x * v.y + gn.y * v.x);
+      }
+      P.vis[i] = make_double2(v.x + nzi.x, v.y + nzi.y);
     }
-    P.vis[i] = make_double2(v.x + nzi.x, v.y + nzi.y);
     return;
   }
-  const long long row = i / P.nchan, col = i - row * P.nchan;
-  const double tsys = P.tsys[row * P.st[0] + col * P.st[1]];
-  const double effq = P.effq[row * P.st[4] + col * P.st[5]];
-  // interferometry.py:6687 / :6689
-  double rms = P.flux_unit_k ? P.scale * tsys / effq : P.scale * (tsys / P.aeff[row * P.st[2] + col * P.st[3]] / effq);
-  unsigned long long g = (unsigned long long)(P.elem_offset + i);
   uint32_t r[4];
-  philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0u, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r);
-  // two uniforms in (0,1) with 53 / 32 significant bits, Box-Muller -> two independent N(0,1)
-  double u1 = ((double)(((unsigned long long)r[0] << 21) ^ (unsigned long long)(r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
-  double u2 = ((double)(((unsigned long long)r[2] << 21) ^ (unsigned long long)(r[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
-  double rad = sqrt(-2.0 * log(u1));
-  double sn, cs;
-  sincospi(2.0 * u2, &sn, &cs);
-  const double a = rms * 0.70710678118654752440;               // rms/sqrt(2) (:6693)
-  double2 nz = make_double2(a * rad * cs, a * rad * sn);
-  if (P.rms) P.rms[i] = rms;
-  if (P.noise) P.noise[i] = nz;
-  if (P.vis) {
-    double2 v = P.skyvis[i];
-    if (P.gains) {                                              // gains * skyvis (:6722)
-      double2 gn = P.gains[i];
-      v = make_double2(gn.x * v.x - gn.y * v.y, gn.x * v.y + gn.y * v.x);
+  const unsigned long long ctr = (unsigned long long)(P.row_offset + row) * (unsigned long long)H + (unsigned long long)c;
+  philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (e >= ne) break;
+    const int col = c + e * H;
+    const long long i = row * P.nchan + col;
+    const double tsys = P.tsys[row * P.st[0] + col * P.st[1]];
+    const double effq = P.effq[row * P.st[4] + col * P.st[5]];
+    // interferometry.py:6687 / :6689
+    const double rms = P.flux_unit_k ? P.scale * tsys / effq : P.scale * (tsys / P.aeff[row * P.st[2] + col * P.st[3]] / effq);
+    const float2 z = e ? normal_pair(r[2], r[3]) : normal_pair(r[0], r[1]);
+    const double a = rms * 0.70710678118654752440;               // rms/sqrt(2) (:6693)
+    const double2 nz = make_double2(a * (double)z.x, a * (double)z.y);
+    if (P.rms) P.rms[i] = rms;
+    if (P.noise) P.noise[i] = nz;
+    if (P.vis) {
+      double2 v = P.skyvis[i];
+      if (P.gains) {                                              // gains * skyvis (:6722)
+        double2 gn = P.gains[i];
+        v = make_double2(gn.x * v.x - gn.y * v.y, gn.x * v.y + gn.y * v.x);
+      }
+      P.vis[i] = make_double2(v.x + nz.x, v.y + nz.y);
     }
-    P.vis[i] = make_double2(v.x + nz.x, v.y + nz.y);
   }
 }
 
@@ -109,9 +134,9 @@ extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d
   P.nchan = nchan; P.add_only = add_only;
   P.flux_unit_k = flux_unit_k;
   P.seed = seed;
-  P.elem_offset = ((long long)snapshot * nbl_total + bl_offset) * (long long)nchan;
-  P.n = (long long)nbl * nchan;
-  k_noise<<<pb_div_up(P.n, 256), 256, 0, stream>>>(P);
+  P.row_offset = (long long)snapshot * nbl_total + bl_offset;
+  P.nrows = nbl;
+  k_noise<<<pb_div_up((long long)nbl * ((nchan + 1) / 2), 256), 256, 0, stream>>>(P);
   PB_CHECK_LAUNCH(ctx, "k_noise");
   return PB200_OK;
 }

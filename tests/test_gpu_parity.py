@@ -311,6 +311,16 @@ def test_noise_rms_statistics_and_sharding_invariance(eng):
     _, nzs, _ = eng.noise(None, tsys, aeff[100:250].contiguous(), effq, 1e5, 10.7, seed=99, nbl=150, nchan=nchan, snapshot=3,
                           bl_offset=100, nbl_total=nbl, want=("noise",))
     assert torch.equal(nzs, nz[100:250])
+    # odd channel count and odd shard offsets: Philox word pairs straddle rows and shard boundaries
+    nco = 127
+    tso, aeo = eng._f64(Tsys[:nco], 0), eng._f64(NP.full((nbl, nco), 100.1), 0)
+    _, nzo, _ = eng.noise(None, tso, aeo, effq, 1e5, 10.7, seed=7, nbl=nbl, nchan=nco, snapshot=1, want=("noise",))
+    for lo, hi in ((0, 1), (1, 2), (37, 154), (299, 300)):
+        _, part, _ = eng.noise(None, tso, aeo[lo:hi].contiguous(), effq, 1e5, 10.7, seed=7, nbl=hi - lo, nchan=nco, snapshot=1,
+                               bl_offset=lo, nbl_total=nbl, want=("noise",))
+        assert torch.equal(part, nzo[lo:hi])
+    zo = (nzo / nzo.abs().pow(2).mean().sqrt()).cpu().numpy()
+    assert abs(NP.mean(zo.real[:, 1:] * zo.real[:, :-1])) < 5 / NP.sqrt(zo.size) and abs(NP.mean(zo.real * zo.imag)) < 5 / NP.sqrt(zo.size)
     # K units (interferometry.py:6689)
     rmsk, _, _ = eng.noise(None, tsys, None, effq, 1e5, 10.7, seed=1, nbl=nbl, nchan=nchan, flux_unit_k=True, want=("rms",))
     assert NP.abs(rmsk.cpu().numpy() - Tsys[None, :] / 0.96 / NP.sqrt(10.7e5)).max() < 1e-12
