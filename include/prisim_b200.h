@@ -169,11 +169,11 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
 #define PB200_SKYVIS_DIRECT     2
 #define PB200_SKYVIS_RECURRENCE_SCALAR 3   /* same algorithm with scalar FFMA instead of packed FFMA2 (A/B measurement) */
 #define PB200_SKYVIS_FP64       4           /* recurrence with every product and sum in fp64 (strongly cancelling skies) */
-#define PB200_SKYVIS_RECURRENCE_3TERM_SCALAR 7   /* the same with scalar FFMA */
-#define PB200_SKYVIS_RECURRENCE_3TERM 6    /* packed three-term recurrence Z_{j+1} = 2cos(2phi) Z_j - Z_{j-1} in 16-channel half blocks */
 #define PB200_SKYVIS_RECURRENCE_LIFT 5     /* packed recurrence with the 3-op lifted (shear) rotation on CTA rows of short baselines
                                               (A/B measurement: fewer FFMA2 and more accurate, but slower -- the loop is bound by
                                               register-file operand bandwidth, not by the FMA pipe) */
+#define PB200_SKYVIS_RECURRENCE_3TERM 6    /* packed three-term recurrence Z_{j+1} = 2cos(2phi) Z_j - Z_{j-1} in 16-channel half blocks (A/B) */
+#define PB200_SKYVIS_RECURRENCE_3TERM_SCALAR 7   /* the same with scalar FFMA (A/B) */
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                  const double* d_src_fwhm_deg, void* d_vis, int method, void* stream);
@@ -185,9 +185,10 @@ int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int 
  * One snapshot, logical shape [nbl,nchan].  d_tsys / d_aeff / d_effq are fp64 with element
  * strides (row, col) given in `strides[6]` = {tsys_row, tsys_col, aeff_row, aeff_col, effq_row,
  * effq_col}; a zero stride broadcasts (a [nchan] Tsys is {0,1}, a scalar is {0,0}).
- * Normal deviates come from Philox4x32-10 keyed by (seed, global element index =
- * (snapshot*nbl_total + bl_offset + b)*nchan + f), so a result does not depend on how baselines
- * are sharded across GPUs.  d_gains (complex128 [nbl,nchan]) may be NULL (unity).  Any of d_rms /
+ * Normal deviates come from Philox4x32-10 keyed by seed with counter (snapshot*nbl_total + bl_offset + b) *
+ * ceil(nchan/2) + (f mod ceil(nchan/2)) -- words 0-1 serve channel f < ceil(nchan/2), words 2-3 channel f +
+ * ceil(nchan/2) -- so a result does not depend on how baselines are sharded across GPUs.  Box-Muller in fp32 (24-bit
+ * deviates), rms and scaling in fp64.  d_gains (complex128 [nbl,nchan]) may be NULL (unity).  Any of d_rms /
  * d_noise / d_vis may be NULL to skip that output.
  * add_only != 0: d_noise is an INPUT and only d_vis = gains*skyvis + noise is written (:6722).
  */
