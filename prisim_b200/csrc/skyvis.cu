@@ -675,15 +675,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
         pr *= w0; pi *= w0; rr *= g0; ri *= g0;
       }
       const AMP* arow = &ti.amp[s][wc * KT64];
+      if (TAPER) {
 #pragma unroll
-      for (int k = 0; k < KT64; ++k) {
-        const double a = (double)arow[k];
-        acc_re[k] = fma(a, pr, acc_re[k]);
-        acc_im[k] = fma(a, pi, acc_im[k]);
-        const double nr = fma(-pi, ri, pr * rr);
-        const double ni = fma(pi, rr, pr * ri);
-        pr = nr; pi = ni;
-        if (TAPER) { rr = fma(rr, hm1, rr); ri = fma(ri, hm1, ri); }
+        for (int k = 0; k < KT64; ++k) {
+          const double a = (double)arow[k];
+          acc_re[k] = fma(a, pr, acc_re[k]);
+          acc_im[k] = fma(a, pi, acc_im[k]);
+          const double nr = fma(-pi, ri, pr * rr);
+          const double ni = fma(pi, rr, pr * ri);
+          pr = nr; pi = ni;
+          rr = fma(rr, hm1, rr); ri = fma(ri, hm1, ri);
+        }
+      } else {
+        // unit phasors: three-term recurrence z_{k+1} = 2 cos(phi) z_k - z_{k-1} (one DFMA per component instead of a
+        // complex multiplication; over 16 channels in fp64 the error growth, steps^2/2 ulp, is 1e-14)
+        double qr = fma(-pi, ri, pr * rr), qi = fma(pi, rr, pr * ri);          // z_1 = z_0 r
+        const double C = 2.0 * rr;
+        {
+          const double a0 = (double)arow[0], a1 = (double)arow[1];
+          acc_re[0] = fma(a0, pr, acc_re[0]); acc_im[0] = fma(a0, pi, acc_im[0]);
+          acc_re[1] = fma(a1, qr, acc_re[1]); acc_im[1] = fma(a1, qi, acc_im[1]);
+        }
+#pragma unroll
+        for (int k = 2; k < KT64; k += 2) {
+          pr = fma(C, qr, -pr); pi = fma(C, qi, -pi);                           // z_k     (overwrites z_{k-2})
+          qr = fma(C, pr, -qr); qi = fma(C, pi, -qi);                           // z_{k+1} (overwrites z_{k-1})
+          const double a0 = (double)arow[k], a1 = (double)arow[k + 1];
+          acc_re[k] = fma(a0, pr, acc_re[k]); acc_im[k] = fma(a0, pi, acc_im[k]);
+          acc_re[k + 1] = fma(a1, qr, acc_re[k + 1]); acc_im[k + 1] = fma(a1, qi, acc_im[k + 1]);
+        }
       }
     }
     __syncthreads();
