@@ -586,6 +586,7 @@ struct __align__(16) TilePre64 {
   double tau[T][BL64];
   double2 rot[T][BL64];
   double kap[T][BL64];
+  float hm1[T][BL64];      // taper: h - 1 = expm1(-2 kap dF^2 ln2), the same for every channel block (fp32: it only scales R by 1 + hm1)
 };
 template <typename AMP> struct __align__(16) TileIn64 {
   AMP amp[T][PB200_SLAB];
@@ -645,7 +646,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
       sincospi(2.0 * frac_turns(tau * df), &sn, &cs);
       tpre[stage].tau[s][bcol] = tau;
       tpre[stage].rot[s][bcol] = make_double2(cs, -sn);
-      if (TAPER) tpre[stage].kap[s][bcol] = g.w * fmax(G.blen2 - tau_g * tau_g, 0.0);
+      if (TAPER) {
+        const double kap = g.w * fmax(G.blen2 - tau_g * tau_g, 0.0);
+        tpre[stage].kap[s][bcol] = kap;
+        tpre[stage].hm1[s][bcol] = (float)expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
+      }
     }
   };
   double acc_re[KT64], acc_im[KT64];
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
         // phasor (q = p w) and the rotation (R_k = r g_k, R_{k+1} = R_k + R_k (h - 1))
         const double kap = tp.kap[s][bcol];
         const double w0 = exp2(-kap * tF0 * tF0), g0 = exp2(-kap * tdF * (2.0 * tF0 + tdF));
-        hm1 = expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
+        hm1 = (double)tp.hm1[s][bcol];
         pr *= w0; pi *= w0; rr *= g0; ri *= g0;
       }
       const AMP* arow = &ti.amp[s][wc * KT64];
