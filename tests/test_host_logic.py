@@ -155,3 +155,78 @@ def test_interferometer_array_validation_without_gpu():
     ia = InterferometerArray(["a", "b", "c"], bl[:, :2], ch / 1e6, freq_scale="MHz", A_eff=[1.0, 2.0, 3.0])
     assert ia.baselines.shape == (3, 3) and NP.allclose(ia.channels, ch) and ia.A_eff.shape == (3, 4)
     assert NP.isclose(ia.freq_resolution, 1e5) and ia.n_acc == 0 and ia.skyvis_freq is None
+
+
+def test_subband_windows_and_window_helpers_match_oracle():
+    """Host-only parts of multi_window_delay_transform (interferometry.py:8199-8265): no GPU needed."""
+    from prisim_b200.interferometry import InterferometerArray
+    from prisim_b200.delay_spectrum import window_N2width, windowing
+    from oracle import prisim_oracle as O
+    ch = 150e6 + (NP.arange(96) - 48) * 1e5
+    ia = InterferometerArray(["a", "b"], NP.zeros((2, 3)), ch)
+    for shape in ("rect", "bhw", "bnw", "BHW"):
+        assert abs(window_N2width(shape=shape) - O.window_N2width(shape)) < 1e-15
+        assert NP.array_equal(windowing(37, shape=shape.lower()), O.windowing(37, shape=shape.lower()))
+        for bw, fc in ((1.0e6, None), ([0.8e6, 2.5e6, 1.1e6], [ch[70], ch[5], ch[40]]), (3.0e6, [ch[2], ch[93]]), ([1e6, 2e6], ch[50])):
+            w = ia.subband_windows(bw, freq_center=fc, shape=shape)
+            assert NP.array_equal(w, O.multi_window_weights(ch, bw, fc, shape))
+            assert w.shape[1] == ch.size and NP.all(w >= 0.0) and NP.all(w.max(axis=1) <= 1.0 + 1e-15)
+    w = ia.subband_windows([1e6, 1e6], freq_center=[ch[80], ch[10]], shape="bhw")
+    assert NP.argmax(w[0]) < NP.argmax(w[1])                                     # ordered by centre channel (:8247-8251)
+    w = ia.subband_windows(4.0e6, freq_center=ch[1], shape="rect")               # clipped at the band edge, not wrapped
+    assert w[0, 0] == 1.0 and w[0, -1] == 0.0
+    for bad in (dict(bw_eff=0.0), dict(bw_eff=[1e6, 2e6], freq_center=[ch[3], ch[4], ch[5]]), dict(bw_eff=1e6, freq_center=ch[-1]),
+                dict(bw_eff=1e6, shape="hann")):
+        with pytest.raises(ValueError):
+            ia.subband_windows(**bad)
+    with pytest.raises(TypeError):
+        ia.subband_windows("1 MHz")
+    with pytest.raises(TypeError):
+        ia.subband_windows(1e6, shape=3)
+
+
+def test_roi_parameters_host_paths_without_gpu():
+    """ROI_parameters.append_settings (interferometry.py:4221-4617): the branches that need no beam evaluation."""
+    from prisim_b200.interferometry import ROI_parameters
+    from prisim_b200.skymodel import SkyModel
+    n = 20
+    sky = SkyModel(init_parms={"location": NP.stack((NP.linspace(0, 340, n), NP.linspace(-80, 20, n)), axis=1), "coords": "hadec",
+                               "spec_type": "func", "frequency": [150e6],
+                               "spec_parms": {"name": NP.repeat("power-law", n), "power-law-index": NP.zeros(n), "freq-ref": NP.full(n, 150e6),
+                                              "flux-scale": NP.ones(n)}})
+    freq = 0.15 + NP.arange(8) * 1e-4                                            # GHz (the reference's default freq_scale)
+    tel = {"id": "hera", "shape": "dish", "size": 14.0, "orientation": NP.asarray([90.0, 270.0]), "ocoords": "altaz", "latitude": -30.7}
+    roi = ROI_parameters()
+    pb = NP.random.default_rng(0).uniform(0, 1, (3, 8))
+    roi.append_settings(sky, freq, roi_info={"ind": NP.asarray([1, 5, 9]), "pbeam": pb, "radius": 90.0}, telescope=tel)
+    assert NP.allclose(roi.freq, freq * 1e9) and roi.freq_scale == "Hz"
+    assert roi.info["pbeam"][0].dtype == NP.float32 and NP.array_equal(roi.info["pbeam"][0], pb.astype(NP.float32))
+    assert NP.array_equal(roi.info["ind"][0], [1, 5, 9]) and roi.info["radius"] == [90.0] and roi.pinfo == []
+    roi.append_settings(None, freq, telescope=tel)
+    assert roi.info["ind"][1].size == 0 and roi.info["pbeam"][1].size == 0 and roi.pinfo == [None]
+    with pytest.raises(ValueError):
+        roi.append_settings(sky, freq, roi_info=None)
+    with pytest.raises(ValueError):
+        roi.append_settings(sky, freq, roi_info={"ind": NP.arange(4), "pbeam": NP.ones((3, 8))})
+    with pytest.raises(ValueError):
+        roi.append_settings(sky, freq, roi_info={"ind": NP.arange(3), "pbeam": NP.ones((3, 7))})
+    with pytest.raises(TypeError):
+        roi.append_settings("sky", freq, roi_info={"radius": 10.0})
+    with pytest.raises(ValueError):                                              # ROI by radius needs the pointing info for the beam
+        roi.append_settings(sky, freq, pinfo=None, roi_info={"radius": 30.0, "center": None})
+    with pytest.raises(TypeError):
+        ROI_parameters().append_settings(sky, freq, roi_info={"radius": 10.0}, telescope=None)
+    with pytest.raises(NotImplementedError):
+        ROI_parameters(init_file="roi.fits")
+
+
+def test_gradient_and_duplicate_argument_errors_without_gpu():
+    from prisim_b200.interferometry import InterferometerArray
+    ia = InterferometerArray(["a", "b"], NP.zeros((2, 3)), 150e6 + NP.arange(4) * 1e5)
+    assert ia.gradient == {} and ia.gradient_mode is None
+    with pytest.raises(AttributeError):                                          # interferometry.py:6765-6769
+        ia.apply_gradients(perturbations={"baseline": NP.zeros((3, 2))})
+    with pytest.raises(TypeError):                                               # :6849-6850
+        ia.duplicate_measurements(blgroups=[("a", "b")])
+    ia.duplicate_measurements(blgroups={"a": ["a"], "b": ["b"]})                 # nothing to expand: no-op (:6852-6857)
+    assert ia.baselines.shape[0] == 2
