@@ -133,6 +133,33 @@ def test_gradient_point_sources_vs_oracle_and_finite_difference():
     assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
+def test_roi_about_the_pointing_centre_vs_oracle():
+    """observe(roi_center='pointing_center', roi_radius=r) (interferometry.py:6212-6213): sources within r of an off-zenith
+    pointing; the reference takes that branch through astropy coordinates, so the oracle gets the index list explicitly."""
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    g = NP.load(os.path.join(GOLD, "observe_gaussian_altazpointing.npz"))
+    case = OBSERVE_CASES["gaussian_altazpointing"]
+    nbl, nchan, _ = g["skyvis_freq"].shape
+    lat = float(g["latitude"])
+    ia = InterferometerArray([("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)], g["bl"], g["chans"], telescope=dict(case["telescope"]),
+                             latitude=lat, skycoords="hadec", pointing_coords="altaz", freq_scale="Hz", device=0)
+    nsrc0 = g["flux"].size
+    parms = {"location": g["hadec_0"], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+             "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": g["spindex"], "freq-ref": NP.full(nsrc0, 150e6),
+                            "flux-scale": g["flux"]}}
+    radius = 35.0
+    ia.observe(SimpleTime(2451545.0, float(g["lsts"][0])), {"Tnet": 100.0}, NP.ones(nchan), g["pointing"], SkyModel(init_parms=parms), 10.0,
+               roi_radius=radius, roi_center="pointing_center")
+    altaz = O.hadec2altaz(g["hadec_0"], lat, units="degrees")
+    m2 = NP.where(O.sphdist(g["pointing"][1], g["pointing"][0], altaz[:, 1], altaz[:, 0]) <= radius)[0]
+    assert 0 < m2.size < NP.sum(altaz[:, 0] >= 0) and NP.array_equal(ia.obs_catalog_indices[0], m2)
+    pb = O.primary_beam_generator(altaz[m2], g["chans"] / 1e9, dict(case["telescope"]), skyunits="altaz", freq_scale="GHz", pointing_center=g["pointing"])
+    Vo, _ = O.observe_snapshot(g["bl"], g["chans"], g["hadec_0"], "hadec", lat, g["pointing"], "altaz", dict(case["telescope"]), g["flux"], g["spindex"],
+                               150e6, roi_info={"ind": m2, "pbeam": pb})
+    assert rel_err(ia.skyvis_freq[..., 0], Vo) <= TOL
+
+
 def test_delay_spectrum_allruns_against_reference_golden():
     """DelaySpectrum.delay_transform / delay_transform_allruns / horizon limits (delay_spectrum.py:1224-1342, :1475-1618,
     :2976-3030) replaying the reference's own DelaySpectrum on the 'hera' case."""
