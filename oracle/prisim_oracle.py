@@ -619,6 +619,37 @@ def roi_append_settings(skypos, skycoords, latitude, freq, telescope, roi_info, 
     return ind, pbeam.astype(NP.float64) * NP.ones(freq.size).reshape(1, -1), radius, center
 
 
+def uniq_baselines(baseline_locations, redundant=None):
+    """interferometry.py:1373-1463: unique baselines by (length to 0.01 m, zenith angle and orientation folded into
+    [0, 180) deg to 0.001 arcsec), keyed as formatted strings and ordered as NP.unique orders those strings (:1432-1434).
+    redundant=None: all unique baselines; True: those occurring more than once; False: exactly once.  Returns
+    (baselines [nu,3], first-occurrence indices, counts, list of index lists of all occurrences)
+    (the last via NMO.find_all_occurrences_list1_in_list2 [AU-memory])."""
+    bl = NP.asarray(baseline_locations, dtype=NP.float64)
+    if bl.shape[1] > 3:
+        bl = bl[:, :3]
+    elif bl.shape[1] < 3:
+        bl = NP.hstack((bl, NP.zeros((bl.shape[0], 3 - bl.shape[1]))))
+    blo = NP.angle(bl[:, 0] + 1j * bl[:, 1], deg=True)
+    blo[blo >= 180.0] -= 180.0
+    blo[blo < 0.0] += 180.0
+    bll = NP.sqrt(NP.sum(bl ** 2, axis=1))
+    blza = NP.degrees(NP.arccos(bl[:, 2] / bll))
+    blstr = ["{0[0]:.2f}_{0[1]:.3f}_{0[2]:.3f}".format(lo) for lo in zip(bll, 3.6e3 * blza, 3.6e3 * blo)]   # :1432
+    uniq, ind, invind = NP.unique(blstr, return_index=True, return_inverse=True)
+    counts = NP.asarray([blstr.count(u) for u in uniq])
+    if redundant is None:
+        sel = NP.arange(uniq.size)
+    elif redundant:
+        sel = NP.where(counts > 1)[0]
+    else:
+        sel = NP.where(counts == 1)[0]
+    retind = ind[sel]
+    cnt = counts[sel] if redundant is None or redundant else NP.ones(retind.size)
+    occ = [NP.where(invind == invind[i])[0].tolist() for i in retind]
+    return bl[retind, :], retind, cnt, occ
+
+
 def duplicate_counts(labels, blgroups):
     """Index logic of InterferometerArray.duplicate_measurements, interferometry.py:6852-6889.
     labels: sequence of (A2, A1) label tuples of the simulated (unique) baselines; blgroups: dict

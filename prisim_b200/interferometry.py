@@ -133,14 +133,46 @@ def orient_and_sort_baselines(bl, labels=None):
     return bl[order], (None if labels is None else labels[order]), order
 
 
-def uniq_baselines(bl, precision=1e-3):
-    """Unique baselines up to `precision` metres in length/orientation (redundant arrays,
-    cf. interferometry.py:1373-1463); returns (unique baselines, first-occurrence indices, counts)."""
-    bl = NP.asarray(bl, dtype=NP.float64)
-    keys = NP.round(bl / precision).astype(NP.int64)
-    _, first, counts = NP.unique(keys, axis=0, return_index=True, return_counts=True)
-    order = NP.argsort(first)
-    return bl[first[order]], first[order], counts[order]
+def uniq_baselines(baseline_locations, redundant=None):
+    """Same call and 4-tuple as interferometry.py:1373-1463: (selected baselines [nu,3], their first-occurrence indices,
+    counts, list of the indices of all occurrences of each).  Two baselines are the same when length (0.01 m), zenith
+    angle and orientation folded into [0, 180) degrees (0.001 arcsec) agree -- b and -b are one baseline -- and the
+    result is ordered like the reference orders its formatted keys.  redundant=None: every unique baseline; True:
+    only those occurring more than once; False: only those occurring once."""
+    if not isinstance(baseline_locations, NP.ndarray):
+        raise TypeError("baseline_locations must be a numpy array")
+    if redundant is not None and not isinstance(redundant, bool):
+        raise TypeError('keyword "redundant" must be set to None or a boolean value')
+    b3 = NP.zeros((baseline_locations.shape[0], 3))
+    ncol = min(3, baseline_locations.shape[1])
+    b3[:, :ncol] = baseline_locations[:, :ncol]
+    length = NP.linalg.norm(b3, axis=1)
+    za_arcsec = 3.6e3 * NP.degrees(NP.arccos(b3[:, 2] / length))
+    orient = NP.degrees(NP.arctan2(b3[:, 1], b3[:, 0]))
+    orient = NP.where(orient >= 180.0, orient - 180.0, NP.where(orient < 0.0, orient + 180.0, orient))
+    keys = NP.asarray(["%.2f_%.3f_%.3f" % t for t in zip(length, za_arcsec, 3.6e3 * orient)])
+    _, first, inverse, count = NP.unique(keys, return_index=True, return_inverse=True, return_counts=True)
+    pick = NP.arange(first.size) if redundant is None else NP.flatnonzero(count > 1 if redundant else count == 1)
+    occurrences = [NP.flatnonzero(inverse == g).tolist() for g in pick]
+    counts = count[pick] if redundant is not False else NP.ones(pick.size)
+    return b3[first[pick], :], first[pick], counts, occurrences
+
+
+def baseline_groups(labels, baseline_locations):
+    """Unique baselines of a (redundant) array with the bookkeeping ``duplicate_measurements`` needs, in the dictionary
+    formats getBaselineInfo builds (interferometry.py:1999-2007): returns (unique labels, unique baselines [nu,3],
+    {'groups': {label tuple: labels of all baselines redundant with it}, 'reversemap': {label tuple: group key}})."""
+    labels = NP.asarray(labels)
+    ubl, first, _, occ = uniq_baselines(NP.asarray(baseline_locations, dtype=NP.float64))
+    order = NP.argsort(first, kind="stable")                          # keep the input order of first occurrences
+    groups, reverse = {}, {}
+    for g in order:
+        key = tuple(labels[first[g]].tolist()) if labels[first[g]].shape or labels.dtype.names else (labels[first[g]].item(),)
+        members = labels[NP.asarray(occ[g])]
+        groups[key] = members
+        for lbl in members:
+            reverse[tuple(lbl.tolist()) if (lbl.shape or labels.dtype.names) else (lbl.item(),)] = NP.asarray([labels[first[g]]], dtype=labels.dtype)
+    return labels[first[order]], ubl[order], {"groups": groups, "reversemap": reverse}
 
 
 ################################################################################

@@ -190,6 +190,8 @@ def install_stubs():
     for name in ("gridding_modules", "lookup_operations", "nonmathops", "mathops", "ephemeris_timing", "mpi_modules"):
         setattr(au, name, _mod("astroutils." + name))
     au.lookup_operations.find_1NN = find_1NN
+    # NMO.find_all_occurrences_list1_in_list2 [AU-memory]: for every element of list1 the indices of list2 equal to it
+    au.nonmathops.find_all_occurrences_list1_in_list2 = lambda l1, l2: [NP.where(NP.asarray(l2) == v)[0].tolist() for v in l1]
 
     class _Any(object):
         def __init__(self, *a, **k):
@@ -434,6 +436,21 @@ def main():
     # gradient_mode='baseline' only runs in the reference when the sky model has src_shape: the direction cosines it
     # multiplies by are assigned inside the taper branch (interferometry.py:6263) and are unbound otherwise (:6343)
     run_observe("hera_taper_gradient", hera, src_shape=0.6, gradient_mode="baseline", nsnap=2)
+    # ---------------- uniq_baselines (interferometry.py:1373-1463) on a redundant layout: no random numbers ----------------
+    if not ONLY or "uniq_baselines" in ONLY:
+        # 19-element hexagon, 14.6 m pitch (the reference's hexagon_generator needs Python 2's list-returning zip)
+        xy = NP.asarray([[14.6 * (q + 0.5 * r), 14.6 * NP.sqrt(3.0) / 2 * r] for r in range(-2, 3) for q in range(-2, 3) if abs(q + r) <= 2])
+        ants = NP.hstack((xy, NP.zeros((xy.shape[0], 1))))
+        ants = NP.vstack((ants, [[100.3, -40.2, 1.5], [-77.7, 12.9, 0.0]]))                    # two outriggers
+        ii, jj = NP.triu_indices(ants.shape[0], k=1)
+        blu = ants[jj] - ants[ii]
+        ub = {"bl": blu}
+        for key, red in (("all", None), ("red", True), ("nonred", False)):
+            sel, ind, cnt, occ = RI.uniq_baselines(blu, redundant=red)
+            ub.update({"sel_" + key: sel, "ind_" + key: NP.asarray(ind), "cnt_" + key: NP.asarray(cnt),
+                       "occ_len_" + key: NP.asarray([len(o) for o in occ]), "occ_flat_" + key: NP.concatenate([NP.asarray(o, dtype=int) for o in occ])})
+        NP.savez_compressed(os.path.join(OUT, "uniq_baselines.npz"), **ub)
+
     # ---------------- duplicate_measurements (interferometry.py:6823-6907): unique baselines -> redundant sets ----------------
     ant = NP.asarray([[0.0, 0.0, 0.0], [14.6, 0.0, 0.0], [29.2, 0.0, 0.0], [43.8, 0.0, 0.0], [0.0, 14.6, 0.0]])
     antl = NP.asarray(["0", "1", "2", "3", "4"])

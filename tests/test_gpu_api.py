@@ -372,8 +372,11 @@ def test_config1_observing_run_vs_oracle():
     assert rel_err(ia.skyvis_freq, Vo) <= TOL
     # redundant baselines see identical visibilities
     from prisim_b200.interferometry import uniq_baselines
-    ub, first, counts = uniq_baselines(cfg["baselines"])
+    ub, first, counts, occ = uniq_baselines(cfg["baselines"])
     assert ub.shape[0] == 30
+    grp = max(occ, key=len)                                        # b and -b share a group (conjugate visibilities): compare moduli
+    assert len(grp) > 1
+    assert NP.abs(NP.abs(ia.skyvis_freq[grp[1:]]) - NP.abs(ia.skyvis_freq[grp[0]])).max() <= 2e-5 * NP.abs(ia.skyvis_freq[grp[0]]).max()
     # track mode flips the bookkeeping to RA-Dec (interferometry.py:6620-6621)
     ib = InterferometerArray(cfg["labels"], cfg["baselines"], cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
                              skycoords="radec", pointing_coords="hadec", device=0)

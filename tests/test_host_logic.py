@@ -92,7 +92,7 @@ def test_hexagon_and_baselines():
     blo = NP.degrees(NP.angle(bls[:, 0] + 1j * bls[:, 1]))
     assert NP.all((blo > -67.5 - 1e-9) & (blo <= 112.5 + 1e-9))
     assert NP.all(NP.diff(NP.sqrt((bls ** 2).sum(1))) >= -1e-12)
-    ub, first, counts = uniq_baselines(bls)
+    ub, first, counts, occ = uniq_baselines(bls)
     assert ub.shape[0] == 30 and counts.sum() == 171                     # HERA-19: 30 unique baselines
     bla, _, _ = baseline_generator(ant, auto=True)
     assert bla.shape == (190, 3)
@@ -230,3 +230,34 @@ def test_gradient_and_duplicate_argument_errors_without_gpu():
         ia.duplicate_measurements(blgroups=[("a", "b")])
     ia.duplicate_measurements(blgroups={"a": ["a"], "b": ["b"]})                 # nothing to expand: no-op (:6852-6857)
     assert ia.baselines.shape[0] == 2
+
+
+def test_uniq_baselines_matches_reference_and_groups_feed_duplicate_measurements():
+    """uniq_baselines (interferometry.py:1373-1463) against the reference's own run, shim and oracle; baseline_groups builds
+    the blgroups / reversemap dictionaries of interferometry.py:1999-2007."""
+    from prisim_b200.interferometry import uniq_baselines, baseline_groups
+    from oracle import prisim_oracle as O
+    g = NP.load(os.path.join(ROOT, "tests", "golden", "uniq_baselines.npz"))
+    for key, red in (("all", None), ("red", True), ("nonred", False)):
+        for fn in (uniq_baselines, O.uniq_baselines):
+            sel, ind, cnt, occ = fn(g["bl"], redundant=red)
+            assert NP.array_equal(sel, g["sel_" + key]) and NP.array_equal(ind, g["ind_" + key]) and NP.array_equal(cnt, g["cnt_" + key])
+            assert [len(o) for o in occ] == g["occ_len_" + key].tolist()
+            assert NP.array_equal(NP.concatenate([NP.asarray(o, dtype=int) for o in occ]), g["occ_flat_" + key])
+    with pytest.raises(TypeError):
+        uniq_baselines(g["bl"].tolist())
+    with pytest.raises(TypeError):
+        uniq_baselines(g["bl"], redundant="yes")
+    assert uniq_baselines(g["bl"][:, :2])[0].shape[1] == 3                       # 2-column input is zero-filled (:1425-1426)
+    # groups: every baseline in exactly one group, keys are group members, reverse map points back to the key
+    dt = [("A2", "U4"), ("A1", "U4")]
+    labels = NP.asarray([("j{0}".format(i), "i{0}".format(i)) for i in range(g["bl"].shape[0])], dtype=dt)
+    ulab, ubl, info = baseline_groups(labels, g["bl"])
+    assert ubl.shape == (69, 3) and len(info["groups"]) == 69 and len(info["reversemap"]) == 210
+    members = [tuple(m) for v in info["groups"].values() for m in v.tolist()]
+    assert sorted(members) == sorted(tuple(l) for l in labels.tolist())
+    for key, v in info["groups"].items():
+        assert key in [tuple(m) for m in v.tolist()]
+        for m in v.tolist():
+            assert tuple(info["reversemap"][tuple(m)][0].tolist()) == key
+    assert [tuple(l) for l in ulab.tolist()] == list(info["groups"].keys())
