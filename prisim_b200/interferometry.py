@@ -50,41 +50,35 @@ class SimpleTime(object):
 ################################################################################
 
 def hexagon_generator(spacing, n_total=None, n_side=None, orientation=None, center=None):
-    """Hexagonal antenna layout, mirrors interferometry.py:857-989: rows above and below the
-    central row are appended pairwise (:960-966), then the centre row (:968-969); centred on the
-    mean (:979), rotated (:980-984), scaled (:986).  Returns (xy [n,2], labels)."""
+    """Hexagonal antenna layout with the call and the antenna ORDER of interferometry.py:857-989: for every offset
+    i = 1 .. n_side-1 the row above the centre line, then its mirror below, and the centre line last; centred on the
+    mean, rotated by `orientation` degrees, scaled by `spacing`, shifted by `center`.  Returns (xy [n,2], labels)."""
     if n_total is None and n_side is None:
         raise NameError("n_total or n_side must be provided")
     if n_side is None:
-        sqroots = NP.roots([3.0, -3.0, 1.0 - n_total])
-        valid = NP.logical_and(sqroots.real >= 1, sqroots.imag == 0.0)
-        if not NP.any(valid):
-            raise ValueError("No valid root found for the quadratic equation with the specified n_total")
-        n_side = int(NP.round(sqroots[valid].real)[0])
-        if 3 * n_side ** 2 - 3 * n_side + 1 != n_total:
+        # n_total = 3 n^2 - 3 n + 1  =>  n = (3 + sqrt(12 n_total - 3)) / 6
+        n_side = int(round((3.0 + NP.sqrt(12.0 * n_total - 3.0)) / 6.0))
+        if n_side < 1 or 3 * n_side ** 2 - 3 * n_side + 1 != n_total:
             raise ValueError("n_total is not a valid number for a hexagonal array")
     else:
-        if not isinstance(n_side, int):
+        if not isinstance(n_side, (int, NP.integer)):
             raise TypeError("n_side must be an integer")
         if n_side <= 0:
             raise ValueError("n_side must be positive")
         n_total = 3 * n_side ** 2 - 3 * n_side + 1
-    xref = NP.arange(2 * n_side - 1, dtype=float)
-    xloc, yloc = [], []
+    width = 2 * n_side - 1
+    dx, dy = NP.cos(NP.pi / 3), NP.sin(NP.pi / 3)          # the reference's own constants (0.5000000000000001, 0.866...)
+    blocks = []
     for i in range(1, n_side):
-        x = xref[:-i] + i * NP.cos(NP.pi / 3)
-        y = i * NP.sin(NP.pi / 3) * NP.ones(2 * n_side - 1 - i)
-        xloc += x.tolist() * 2
-        yloc += y.tolist()
-        yloc += (-y).tolist()
-    xloc += xref.tolist()
-    yloc += [0.0] * int(2 * n_side - 1)
-    xy = NP.asarray(list(zip(xloc, yloc)))
+        xs = NP.arange(width - i, dtype=NP.float64) + i * dx
+        ys = NP.full(width - i, i * dy)
+        blocks += [NP.column_stack((xs, ys)), NP.column_stack((xs, -ys))]
+    blocks.append(NP.column_stack((NP.arange(width, dtype=NP.float64), NP.zeros(width))))
+    xy = NP.concatenate(blocks, axis=0)
     xy = xy - NP.mean(xy, axis=0, keepdims=True)
     if orientation is not None:
-        angle = NP.radians(orientation)
-        rot = NP.asarray([[NP.cos(angle), -NP.sin(angle)], [NP.sin(angle), NP.cos(angle)]])
-        xy = NP.dot(xy, rot.T)
+        ang = NP.radians(orientation)
+        xy = NP.dot(xy, NP.asarray([[NP.cos(ang), -NP.sin(ang)], [NP.sin(ang), NP.cos(ang)]]).T)
     xy = xy * spacing
     if center is not None:
         xy = xy + center
@@ -101,7 +95,7 @@ def baseline_generator(antenna_locations, ant_label=None, ant_id=None, auto=Fals
         ant = NP.hstack((ant, NP.zeros((ant.shape[0], 3 - ant.shape[1]))))
     n = ant.shape[0]
     if ant_label is None:
-        ant_label = NP.asarray([str(i + 1) for i in range(n)])
+        ant_label = NP.asarray([str(i) for i in range(n)])                 # :1302
     ant_label = NP.asarray(ant_label)
     if ant_id is None:
         ant_id = NP.arange(n)

@@ -219,6 +219,8 @@ def load_reference(name):
     src = re.sub(r"^(\s*)print '([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)      # primary_beams.py:2027
     src = src.replace(".iteritems()", ".items()")                                       # interferometry.py:6405
     src = src.replace(".astype(NP.int)", ".astype(int)")                                # numpy >= 1.24 (interferometry.py:8238)
+    src = src.replace("dtype=NP.float)", "dtype=float)")                                # numpy >= 1.24 (interferometry.py:957)
+    src = src.replace("xy = zip(xloc, yloc)", "xy = list(zip(xloc, yloc))")             # interferometry.py:973 (zip is lazy in Py3)
     src = src.replace("NP.asarray(blgroups.keys(), dtype=self.labels.dtype)",           # interferometry.py:6858 (dict view)
                       "NP.asarray(list(blgroups.keys()), dtype=self.labels.dtype)")
     mod = types.ModuleType(name)
@@ -436,6 +438,21 @@ def main():
     # gradient_mode='baseline' only runs in the reference when the sky model has src_shape: the direction cosines it
     # multiplies by are assigned inside the taper branch (interferometry.py:6263) and are unbound otherwise (:6343)
     run_observe("hera_taper_gradient", hera, src_shape=0.6, gradient_mode="baseline", nsnap=2)
+    # ---------------- antenna layouts and baseline pairs (interferometry.py:857-989, :1184-1370): no random numbers ----------------
+    if not ONLY or "layouts" in ONLY:
+        lay = {}
+        for tag, kw in (("side3", dict(n_side=3)), ("side11", dict(n_side=11)), ("side4_rot", dict(n_side=4, orientation=30.0, center=NP.asarray([[5.0, -3.0]])))):
+            xy_ref, lab_ref = RI.hexagon_generator(14.6, **kw)
+            lay["hex_" + tag] = xy_ref
+            lay["hexlab_" + tag] = NP.asarray(list(lab_ref))
+        ant3 = NP.hstack((lay["hex_side3"], 0.1 * NP.arange(19).reshape(-1, 1)))
+        for tag, kw in (("plain", {}), ("auto", dict(auto=True)), ("conj", dict(conjugate=True))):
+            b_ref, l_ref, i_ref = RI.baseline_generator(ant3, **kw)
+            lay["bl_" + tag] = b_ref
+            lay["bllab_" + tag] = NP.asarray([[x.decode() if isinstance(x, bytes) else str(x) for x in row] for row in l_ref.tolist()])
+            lay["blid_" + tag] = NP.asarray([list(row) for row in i_ref.tolist()])
+        NP.savez_compressed(os.path.join(OUT, "layouts.npz"), **lay)
+
     # ---------------- uniq_baselines (interferometry.py:1373-1463) on a redundant layout: no random numbers ----------------
     if not ONLY or "uniq_baselines" in ONLY:
         # 19-element hexagon, 14.6 m pitch (the reference's hexagon_generator needs Python 2's list-returning zip)

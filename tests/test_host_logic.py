@@ -261,3 +261,21 @@ def test_uniq_baselines_matches_reference_and_groups_feed_duplicate_measurements
         for m in v.tolist():
             assert tuple(info["reversemap"][tuple(m)][0].tolist()) == key
     assert [tuple(l) for l in ulab.tolist()] == list(info["groups"].keys())
+
+
+def test_layouts_match_reference_golden():
+    """hexagon_generator / baseline_generator (interferometry.py:857-989, :1184-1370) against the reference's own run."""
+    from prisim_b200.interferometry import hexagon_generator, baseline_generator
+    g = NP.load(os.path.join(ROOT, "tests", "golden", "layouts.npz"))
+    for tag, kw in (("side3", dict(n_side=3)), ("side11", dict(n_side=11)), ("side4_rot", dict(n_side=4, orientation=30.0, center=NP.asarray([[5.0, -3.0]])))):
+        xy, lab = hexagon_generator(14.6, **kw)
+        assert NP.array_equal(xy, g["hex_" + tag]) and list(lab) == g["hexlab_" + tag].tolist()
+    assert NP.array_equal(hexagon_generator(14.6, n_total=331)[0], g["hex_side11"])     # the n_total route (a 1-element array index in the reference)
+    with pytest.raises(ValueError):
+        hexagon_generator(14.6, n_total=330)
+    ant = NP.hstack((g["hex_side3"], 0.1 * NP.arange(19).reshape(-1, 1)))
+    for tag, kw in (("plain", {}), ("auto", dict(auto=True)), ("conj", dict(conjugate=True))):
+        bl, lab, ids = baseline_generator(ant, **kw)
+        assert NP.array_equal(bl, g["bl_" + tag])
+        assert [[str(a), str(b)] for a, b in lab.tolist()] == g["bllab_" + tag].tolist()
+        assert [list(r) for r in ids.tolist()] == g["blid_" + tag].tolist()
