@@ -49,6 +49,64 @@ class SimpleTime(object):
 # Layout helpers (host-side input producers; O(N_ant^2))
 ################################################################################
 
+_BCAST_SHAPES = lambda nbl, nchan, ntimes: [(a, b, c) for a in (1, nbl) for b in (1, nchan) for c in (1, ntimes)]
+
+
+def _noise_input(name, val, nbl, nchan, ntimes):
+    if not isinstance(val, (int, float, list, NP.ndarray)):
+        raise TypeError("Input {0} must be a scalar, float, list or numpy array".format(name))
+    arr = NP.asarray(val, dtype=NP.float64).reshape(1, 1, 1) if isinstance(val, (int, float)) else NP.asarray(val, dtype=NP.float64)
+    if NP.any(arr < 0.0):
+        raise ValueError("Value(s) in {0} cannot be negative".format(name))
+    if arr.shape not in _BCAST_SHAPES(nbl, nchan, ntimes):
+        raise IndexError("{0} specified has incompatible dimensions".format(name))
+    return arr
+
+
+def thermalNoiseRMS(A_eff, df, dt, Tsys, nbl=1, nchan=1, ntimes=1, flux_unit="Jy", eff_Q=1.0):
+    """Thermal-noise rms of a complex visibility, same call as interferometry.py:89-230: 2 k Tsys / (A_eff eff_Q sqrt(df dt))
+    in Jy, or Tsys / (eff_Q sqrt(df dt)) in K; inputs are scalars or arrays broadcastable to (nbl, nchan, ntimes)."""
+    if not isinstance(df, (int, float)):
+        raise TypeError("Input channel resolution must be a scalar")
+    if not isinstance(dt, (int, float)):
+        raise TypeError("Input time resolution must be a scalar")
+    for name, val in (("nbl", nbl), ("nchan", nchan), ("ntimes", ntimes)):
+        if not isinstance(val, int):
+            raise TypeError("Input {0} must be an integer".format(name))
+        if val <= 0:
+            raise ValueError("Input {0} must be positive".format(name))
+    Tsys = _noise_input("Tsys", Tsys, nbl, nchan, ntimes)
+    A_eff = _noise_input("A_eff", A_eff, nbl, nchan, ntimes)
+    eff_Q = _noise_input("eff_Q", eff_Q, nbl, nchan, ntimes)
+    if not isinstance(flux_unit, str):
+        raise TypeError("Input flux_unit must be a string")
+    if flux_unit.lower() not in ["k", "jy"]:
+        raise ValueError("Input flux_unit must be set to K or Jy")
+    if flux_unit.lower() == "k":
+        return Tsys / eff_Q / NP.sqrt(float(dt) * float(df))
+    return 2.0 * FCNST.k / NP.sqrt(float(dt) * float(df)) * (Tsys / A_eff / eff_Q) / 1.0e-26
+
+
+def generateNoise(noiseRMS=None, A_eff=None, df=None, dt=None, Tsys=None, nbl=1, nchan=1, ntimes=1, flux_unit="Jy", eff_Q=1.0,
+                  seed=0, device=None):
+    """Complex thermal noise rms/sqrt(2) (N + iN) of shape (nbl, nchan, ntimes), same call as interferometry.py:236-329
+    plus `seed` / `device`: the deviates come from the device Philox generator (``pb200_noise``), one launch per time."""
+    if noiseRMS is None:
+        noiseRMS = thermalNoiseRMS(A_eff, df, dt, Tsys, nbl=nbl, nchan=nchan, ntimes=ntimes, flux_unit=flux_unit, eff_Q=eff_Q)
+    else:
+        noiseRMS = _noise_input("noiseRMS", noiseRMS, nbl, nchan, ntimes)
+    rms = NP.broadcast_to(noiseRMS, (nbl, nchan, ntimes))
+    dev = engine._dev(device)
+    one = engine._f64([1.0], dev)
+    out = NP.empty((nbl, nchan, ntimes), dtype=NP.complex128)
+    for t in range(ntimes):
+        # the K form of the kernel, rms = Tsys / eff_Q / sqrt(df dt), with Tsys := rms and unit eff_Q, df, dt
+        _, nz, _ = engine.noise(None, engine._f64(NP.ascontiguousarray(rms[:, :, t]), dev), None, one, 1.0, 1.0, int(seed), nbl, nchan,
+                                snapshot=t, flux_unit_k=True, want=("noise",), device=dev)
+        out[:, :, t] = nz.cpu().numpy()
+    return out
+
+
 def hexagon_generator(spacing, n_total=None, n_side=None, orientation=None, center=None):
     """Hexagonal antenna layout with the call and the antenna ORDER of interferometry.py:857-989: for every offset
     i = 1 .. n_side-1 the row above the centre line, then its mirror below, and the centre line last; centred on the

@@ -438,6 +438,18 @@ def main():
     # gradient_mode='baseline' only runs in the reference when the sky model has src_shape: the direction cosines it
     # multiplies by are assigned inside the taper branch (interferometry.py:6263) and are unbound otherwise (:6343)
     run_observe("hera_taper_gradient", hera, src_shape=0.6, gradient_mode="baseline", nsnap=2)
+    # ---------------- thermalNoiseRMS (interferometry.py:89-230): broadcast shapes, both flux units; no random numbers ----------------
+    if not ONLY or "thermal_rms" in ONLY:
+        nb_, nc_, nt_ = 3, 4, 2
+        Ts = 100.0 + NP.arange(nb_ * nc_ * nt_, dtype=float).reshape(nb_, nc_, nt_)
+        tr = {"Tsys": Ts}
+        tr["jy_full"] = RI.thermalNoiseRMS(12.5, 1e5, 10.7, Ts, nbl=nb_, nchan=nc_, ntimes=nt_, flux_unit="Jy", eff_Q=0.9)
+        tr["k_full"] = RI.thermalNoiseRMS(12.5, 1e5, 10.7, Ts, nbl=nb_, nchan=nc_, ntimes=nt_, flux_unit="K", eff_Q=0.9)
+        tr["jy_chan"] = RI.thermalNoiseRMS(NP.full((1, nc_, 1), 20.0), 1e5, 5.0, Ts[:1, :, :1], nbl=nb_, nchan=nc_, ntimes=nt_,
+                                           eff_Q=NP.linspace(0.5, 1.0, nb_).reshape(nb_, 1, 1))
+        tr["jy_scalar"] = RI.thermalNoiseRMS(100.0, 2e5, 1.0, 250.0)
+        NP.savez_compressed(os.path.join(OUT, "thermal_rms.npz"), **tr)
+
     # ---------------- antenna layouts and baseline pairs (interferometry.py:857-989, :1184-1370): no random numbers ----------------
     if not ONLY or "layouts" in ONLY:
         lay = {}

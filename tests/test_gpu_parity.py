@@ -283,6 +283,27 @@ def test_skyvis_full_size_config2_subset_parity(eng):
 
 
 # ------------------------------------------------------------------ noise
+def test_module_level_generate_noise(eng):
+    """generateNoise (interferometry.py:236-329): rms/sqrt2 (N + iN) of shape (nbl, nchan, ntimes) from given rms or from
+    the instrument parameters; device generator, reproducible by seed."""
+    from prisim_b200.interferometry import generateNoise, thermalNoiseRMS
+    nbl, nchan, nt = 64, 96, 3
+    rms = NP.linspace(1.0, 3.0, nchan).reshape(1, nchan, 1)
+    nz = generateNoise(noiseRMS=rms, nbl=nbl, nchan=nchan, ntimes=nt, seed=5, device=0)
+    assert nz.shape == (nbl, nchan, nt) and nz.dtype == NP.complex128
+    z = nz / (rms / NP.sqrt(2.0))
+    n = z.size
+    assert abs(z.real.std() - 1) < 5 / NP.sqrt(2 * n) and abs(z.imag.std() - 1) < 5 / NP.sqrt(2 * n) and abs(z.mean()) < 5 / NP.sqrt(n)
+    assert abs(NP.mean(z.real[..., 0] * z.real[..., 1])) < 5 / NP.sqrt(n / nt)           # time slices are independent
+    assert NP.array_equal(nz, generateNoise(noiseRMS=rms, nbl=nbl, nchan=nchan, ntimes=nt, seed=5, device=0))
+    assert not NP.array_equal(nz, generateNoise(noiseRMS=rms, nbl=nbl, nchan=nchan, ntimes=nt, seed=6, device=0))
+    nz2 = generateNoise(A_eff=100.0, df=1e5, dt=10.0, Tsys=200.0, nbl=nbl, nchan=nchan, ntimes=1, eff_Q=0.9, seed=1, device=0)
+    r0 = float(thermalNoiseRMS(100.0, 1e5, 10.0, 200.0, eff_Q=0.9)[0, 0, 0])
+    assert abs(NP.sqrt(NP.mean(NP.abs(nz2) ** 2)) / r0 - 1) < 5 / NP.sqrt(nz2.size)
+    with pytest.raises(IndexError):
+        generateNoise(noiseRMS=NP.ones((2, 5)), nbl=2, nchan=5, ntimes=1)
+
+
 def test_noise_rms_statistics_and_sharding_invariance(eng):
     nbl, nchan = 300, 128
     freqs = 150e6 + NP.arange(nchan) * 1e5

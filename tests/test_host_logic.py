@@ -279,3 +279,26 @@ def test_layouts_match_reference_golden():
         assert NP.array_equal(bl, g["bl_" + tag])
         assert [[str(a), str(b)] for a, b in lab.tolist()] == g["bllab_" + tag].tolist()
         assert [list(r) for r in ids.tolist()] == g["blid_" + tag].tolist()
+
+
+def test_thermal_noise_rms_matches_reference_golden():
+    """Module-level thermalNoiseRMS (interferometry.py:89-230) against the reference's own run."""
+    from prisim_b200.interferometry import thermalNoiseRMS
+    g = NP.load(os.path.join(ROOT, "tests", "golden", "thermal_rms.npz"))
+    Ts = g["Tsys"]
+    nb, nc, nt = Ts.shape
+    assert NP.allclose(thermalNoiseRMS(12.5, 1e5, 10.7, Ts, nbl=nb, nchan=nc, ntimes=nt, flux_unit="Jy", eff_Q=0.9), g["jy_full"], rtol=1e-14)
+    assert NP.allclose(thermalNoiseRMS(12.5, 1e5, 10.7, Ts, nbl=nb, nchan=nc, ntimes=nt, flux_unit="K", eff_Q=0.9), g["k_full"], rtol=1e-14)
+    r = thermalNoiseRMS(NP.full((1, nc, 1), 20.0), 1e5, 5.0, Ts[:1, :, :1], nbl=nb, nchan=nc, ntimes=nt, eff_Q=NP.linspace(0.5, 1.0, nb).reshape(nb, 1, 1))
+    assert r.shape == g["jy_chan"].shape and NP.allclose(r, g["jy_chan"], rtol=1e-14)
+    assert NP.allclose(thermalNoiseRMS(100.0, 2e5, 1.0, 250.0), g["jy_scalar"], rtol=1e-14)
+    with pytest.raises(IndexError):
+        thermalNoiseRMS(1.0, 1e5, 1.0, NP.ones((2, 2, 2)), nbl=3, nchan=2, ntimes=2)
+    with pytest.raises(ValueError):
+        thermalNoiseRMS(1.0, 1e5, 1.0, -5.0)
+    with pytest.raises(ValueError):
+        thermalNoiseRMS(1.0, 1e5, 1.0, 5.0, flux_unit="mJy")
+    with pytest.raises(TypeError):
+        thermalNoiseRMS(1.0, [1e5], 1.0, 5.0)
+    with pytest.raises(TypeError):
+        thermalNoiseRMS(1.0, 1e5, 1.0, 5.0, nbl=2.0)
