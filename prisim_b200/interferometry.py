@@ -227,6 +227,42 @@ def baseline_groups(labels, baseline_locations):
     return labels[first[order]], ubl[order], {"groups": groups, "reversemap": reverse}
 
 
+def getBaselineGroupKeys(inp_labels, blgroups_reversemap):
+    """Same call as interferometry.py:2017-2095: for every label tuple the key of the redundant group it belongs to
+    (looked up as given, else reversed) and whether it had to be reversed; (None, None) when it is in neither form."""
+    if not isinstance(blgroups_reversemap, dict):
+        raise TypeError("Input blgroups_reversemap must be a dictionary")
+    if not isinstance(inp_labels, list):
+        inp_labels = [inp_labels]
+    keys, flipped = [], []
+    for lbl in inp_labels:
+        hit = None
+        for cand, flip in ((lbl, False), (lbl[::-1], True)):
+            if cand in blgroups_reversemap:
+                hit = (blgroups_reversemap[cand], flip)
+                break
+        if hit is None:
+            keys.append(None); flipped.append(None)
+            continue
+        val = hit[0]
+        if isinstance(val, NP.ndarray):
+            keys.append(tuple(val[0].tolist()) if val.dtype.names else tuple(val[0]))
+        elif isinstance(val, tuple):
+            keys.append(val)
+        else:
+            raise TypeError("Invalid type found in blgroups_reversemap")
+        flipped.append(hit[1])
+    return keys, flipped
+
+
+def getBaselinesInGroups(inp_labels, blgroups_reversemap, blgroups):
+    """Same call as interferometry.py:2100-2165: the label arrays of the redundant groups containing the given labels."""
+    if not isinstance(blgroups, dict):
+        raise TypeError("Input blgroups must be a dictionary")
+    keys, flipped = getBaselineGroupKeys(inp_labels, blgroups_reversemap)
+    return [None if k is None else blgroups[k] for k in keys], flipped
+
+
 ################################################################################
 
 def _validate_2d(name, val, nbl, nchan):

@@ -478,6 +478,22 @@ def main():
             sel, ind, cnt, occ = RI.uniq_baselines(blu, redundant=red)
             ub.update({"sel_" + key: sel, "ind_" + key: NP.asarray(ind), "cnt_" + key: NP.asarray(cnt),
                        "occ_len_" + key: NP.asarray([len(o) for o in occ]), "occ_flat_" + key: NP.concatenate([NP.asarray(o, dtype=int) for o in occ])})
+        # group lookups (interferometry.py:2017-2165) on groups built as getBaselineInfo builds them (:1999-2007)
+        dtl = [("A2", "U3"), ("A1", "U3")]
+        labs = NP.asarray([(str(j), str(i)) for i, j in zip(ii, jj)], dtype=dtl)
+        sel, ind, cnt, occ = RI.uniq_baselines(blu)
+        grp, rev = {}, {}
+        for gi, first in enumerate(ind):
+            grp[tuple(labs[first])] = labs[NP.asarray(occ[gi])]
+            for lbl in labs[NP.asarray(occ[gi])]:
+                rev[tuple(lbl)] = NP.asarray([labs[first]], dtype=labs.dtype)
+        query = [("1", "0"), ("0", "1"), ("20", "3"), ("7", "7"), ("5", "2"), ("2", "5"), ("19", "20")]
+        keys, flip = RI.getBaselineGroupKeys(query, rev)
+        members, flip2 = RI.getBaselinesInGroups(query, rev, grp)
+        ub.update(query=NP.asarray(query), keys=NP.asarray([["", ""] if k is None else list(k) for k in keys]),
+                  flipped=NP.asarray([-1 if f is None else int(f) for f in flip]),
+                  member_counts=NP.asarray([-1 if m is None else m.size for m in members]),
+                  member_first=NP.asarray([["", ""] if m is None else list(m[0].tolist()) for m in members]))
         NP.savez_compressed(os.path.join(OUT, "uniq_baselines.npz"), **ub)
 
     # ---------------- duplicate_measurements (interferometry.py:6823-6907): unique baselines -> redundant sets ----------------

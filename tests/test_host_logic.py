@@ -302,3 +302,26 @@ def test_thermal_noise_rms_matches_reference_golden():
         thermalNoiseRMS(1.0, [1e5], 1.0, 5.0)
     with pytest.raises(TypeError):
         thermalNoiseRMS(1.0, 1e5, 1.0, 5.0, nbl=2.0)
+
+
+def test_baseline_group_lookups_match_reference_golden():
+    """getBaselineGroupKeys / getBaselinesInGroups (interferometry.py:2017-2165) against the reference's own run."""
+    from prisim_b200.interferometry import getBaselineGroupKeys, getBaselinesInGroups, baseline_groups
+    g = NP.load(os.path.join(ROOT, "tests", "golden", "uniq_baselines.npz"))
+    n_ant = 21
+    ii, jj = NP.triu_indices(n_ant, k=1)
+    labs = NP.asarray([(str(j), str(i)) for i, j in zip(ii, jj)], dtype=[("A2", "U3"), ("A1", "U3")])
+    _, _, info = baseline_groups(labs, g["bl"])
+    query = [tuple(q) for q in g["query"].tolist()]
+    keys, flipped = getBaselineGroupKeys(query, info["reversemap"])
+    members, flipped2 = getBaselinesInGroups(query, info["reversemap"], info["groups"])
+    assert flipped == flipped2
+    for k, f, m, kr, fr, cr, mr in zip(keys, flipped, members, g["keys"].tolist(), g["flipped"].tolist(), g["member_counts"].tolist(), g["member_first"].tolist()):
+        if fr < 0:
+            assert k is None and f is None and m is None
+        else:
+            assert list(k) == kr and int(f) == fr and m.size == cr and list(m[0].tolist()) == mr
+    with pytest.raises(TypeError):
+        getBaselineGroupKeys(query, [("1", "0")])
+    with pytest.raises(TypeError):
+        getBaselinesInGroups(query, info["reversemap"], None)
