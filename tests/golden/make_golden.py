@@ -562,6 +562,36 @@ def main():
     roirec["centers"] = NP.concatenate([NP.asarray(c, dtype=float).reshape(1, 2) for c in roi.info["center"]], axis=0)
     if not ONLY or "roi_parameters" in ONLY:
         NP.savez_compressed(os.path.join(OUT, "roi_parameters.npz"), **roirec)
+    # ---------------- Tsys / bandpass bookkeeping forms of observe() (interferometry.py:5993-6086) ----------------
+    nbl, nchan, nsrc0 = 5, 16, 60
+    blk = rng.normal(0, 40.0, (nbl, 3)); blk[:, 2] *= 0.02
+    chans = 150e6 + (NP.arange(nchan) - nchan // 2) * 100e3
+    ia = RI.InterferometerArray([("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)], blk, chans, telescope=dict(hera), eff_Q=0.9,
+                                latitude=lat, skycoords="hadec", A_eff=NP.linspace(50.0, 90.0, nbl), pointing_coords="hadec",
+                                baseline_coords="localenu", freq_scale="Hz")
+    hadec_k = NP.stack((rng.uniform(0, 360, nsrc0), NP.degrees(NP.arcsin(rng.uniform(-1, 0.5, nsrc0)))), axis=1)
+    flux_k = 10 ** rng.uniform(-1, 1, nsrc0); sp_k = rng.normal(-0.8, 0.2, nsrc0)
+    sky_k = SkyModel(hadec_k, flux_k, sp_k, NP.full(nsrc0, 150e6))
+    bp1 = 1.0 + 0.2 * NP.sin(NP.arange(nchan) / 3.0)
+    bp2 = rng.uniform(0.5, 1.5, (nbl, nchan))
+    bp3 = rng.uniform(0.5, 1.5, (nbl, nchan, 1))
+    forms = [(bp1, {"Tnet": 150.0}, None),
+             (bp2, {"Tnet": NP.linspace(100.0, 200.0, nbl)}, None),
+             (bp3, {"Trx": 40.0, "Tant": {"T0": 180.0, "f0": 150e6, "spindex": -2.5}, "Tnet": None}, 1.0 + 0.05 * NP.arange(nchan)),
+             (bp1, {"Tnet": NP.linspace(90.0, 120.0, nchan)}, NP.linspace(0.8, 1.2, nbl)),
+             (bp1, {"Trx": 40.0, "Tant": {"T0": 180.0, "f0": 150e6, "spindex": -2.5}}, rng.uniform(0.9, 1.1, (nbl, nchan)))]
+    for j, (bpj, tsj, bcj) in enumerate(forms):
+        ia.observe(TimeObj(2451545.0 + j * 0.01, 5.0 * j), tsj, bpj, NP.asarray([0.0, lat]), sky_k, 10.0 + j, bpcorrect=bcj)
+    NP.random.seed(3)
+    ia.generate_noise()
+    ia.add_noise()
+    wk = nchan * windowing_bhw(nchan)
+    ia.delay_transform(pad=1.0, freq_wts=wk, verbose=False)
+    if not ONLY or "bookkeeping" in ONLY:
+        NP.savez_compressed(os.path.join(OUT, "bookkeeping.npz"), bl=blk, chans=chans, hadec=hadec_k, flux=flux_k, spindex=sp_k, latitude=lat,
+                            bp1=bp1, bp2=bp2, bp3=bp3, bc2=forms[2][2], bc3=forms[3][2], bc4=forms[4][2], A_eff=NP.linspace(50.0, 90.0, nbl),
+                            Tsys=ia.Tsys, bp=ia.bp, bp_wts=ia.bp_wts, vis_rms_freq=ia.vis_rms_freq, skyvis_freq=ia.skyvis_freq,
+                            skyvis_lag=ia.skyvis_lag, lag_kernel=ia.lag_kernel, t_acc=NP.asarray(ia.t_acc), window=wk)
     print("golden vectors written to", OUT)
 
 

@@ -133,6 +133,43 @@ def test_gradient_point_sources_vs_oracle_and_finite_difference():
     assert NP.abs(fd - dV).max() <= 1e-6 * NP.abs(dV).max()
 
 
+def test_tsys_bandpass_bookkeeping_forms_against_reference_golden():
+    """Every bandpass / Tsysinfo / bpcorrect form observe() accepts (interferometry.py:5993-6086), replaying the reference's run:
+    Tsys, bp, thermal rms, visibilities and the bandpass-weighted delay spectra."""
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    from prisim_b200.skymodel import SkyModel
+    g = NP.load(os.path.join(GOLD, "bookkeeping.npz"))
+    nbl, nchan, nsnap = g["Tsys"].shape
+    lat = float(g["latitude"])
+    ia = InterferometerArray([("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)], g["bl"], g["chans"], telescope=dict(OBSERVE_CASES["hera"]["telescope"]),
+                             eff_Q=0.9, latitude=lat, skycoords="hadec", A_eff=g["A_eff"], pointing_coords="hadec", freq_scale="Hz", device=0)
+    nsrc0 = g["flux"].size
+    sky = SkyModel(init_parms={"location": g["hadec"], "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+                               "spec_parms": {"name": NP.repeat("power-law", nsrc0), "power-law-index": g["spindex"], "freq-ref": NP.full(nsrc0, 150e6),
+                                              "flux-scale": g["flux"]}})
+    tant = {"Trx": 40.0, "Tant": {"T0": 180.0, "f0": 150e6, "spindex": -2.5}}
+    forms = [(g["bp1"], {"Tnet": 150.0}, None),
+             (g["bp2"], {"Tnet": NP.linspace(100.0, 200.0, nbl)}, None),
+             (g["bp3"], dict(tant, Tnet=None), g["bc2"]),
+             (g["bp1"], {"Tnet": NP.linspace(90.0, 120.0, nchan)}, g["bc3"]),
+             (g["bp1"], dict(tant), g["bc4"])]
+    for j, (bp, ts, bc) in enumerate(forms):
+        ia.observe(SimpleTime(2451545.0 + j * 0.01, 5.0 * j), ts, bp, NP.asarray([0.0, lat]), sky, float(g["t_acc"][j]), bpcorrect=bc)
+    assert NP.allclose(ia.Tsys, g["Tsys"], rtol=1e-13) and NP.allclose(ia.bp, g["bp"], rtol=0, atol=0)
+    assert NP.array_equal(ia.bp_wts, NP.ones((nbl, nchan, nsnap)))                 # unity until a delay transform sets them (:6024)
+    assert rel_err(ia.skyvis_freq, g["skyvis_freq"]) <= TOL
+    ia.generate_noise()
+    assert NP.allclose(ia.vis_rms_freq, g["vis_rms_freq"], rtol=1e-12)
+    ia.delay_transform(pad=1.0, freq_wts=g["window"], verbose=False)
+    assert ia.bp_wts.shape == g["bp_wts"].shape and NP.allclose(ia.bp_wts, g["bp_wts"], rtol=1e-15)     # the window, broadcast (:8096-8106)
+    assert rel_err(ia.skyvis_lag, g["skyvis_lag"]) <= TOL
+    assert NP.abs(ia.lag_kernel - g["lag_kernel"]).max() <= 1e-10 * NP.abs(g["lag_kernel"]).max()
+    with pytest.raises(ValueError):
+        ia.observe(SimpleTime(2451545.1, 30.0), {"Tnet": 100.0}, g["bp1"], NP.asarray([0.0, lat]), sky, 10.0, bpcorrect=NP.ones(nchan + 1))
+    with pytest.raises(KeyError):
+        ia.observe(SimpleTime(2451545.1, 30.0), {"Trx": 40.0}, g["bp1"], NP.asarray([0.0, lat]), sky, 10.0)
+
+
 def test_roi_about_the_pointing_centre_vs_oracle():
     """observe(roi_center='pointing_center', roi_radius=r) (interferometry.py:6212-6213): sources within r of an off-zenith
     pointing; the reference takes that branch through astropy coordinates, so the oracle gets the index list explicitly."""
