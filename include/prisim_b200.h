@@ -11,7 +11,12 @@
  *   - every function returns 0 on success or a negative PB200_E* code; pb200_last_error(ctx)
  *     gives the message.  Nothing throws or aborts.
  *   - work is enqueued on the CUDA stream passed as `stream` (a cudaStream_t cast to void*;
- *     NULL = legacy default stream); functions do not synchronise unless stated.
+ *     NULL = legacy default stream); functions do not synchronise unless stated.  Two one-off
+ *     exceptions: the first call that sees a new channel grid (h_freqs) uploads it and waits for
+ *     that copy (the ctx keeps the last four grids resident, later calls enqueue nothing for it),
+ *     and a call that needs more ctx scratch than any before it reallocates (cudaFree/cudaMalloc
+ *     synchronise the device).  Steady-state calls with the same shapes are fully asynchronous.
+ *   - every entry point runs on the ctx's device and restores the caller's current device.
  *   - one pb200_ctx per device per host thread; a ctx is not re-entrant.
  *   - visibilities are [nbl, nchan] row-major (channel fastest), complex128 = interleaved
  *     (re, im) doubles.
@@ -177,6 +182,9 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                  const double* d_src_fwhm_deg, void* d_vis, int method, void* stream);
+/* 1 when h_freqs is f0 + k df to within 1e-4 Hz -- the test pb200_skyvis applies before it takes a recurrence
+ * (or the fp64) kernel; the host shim uses the same test to decide whether precision control applies.        */
+int pb200_channels_uniform(const double* h_freqs, int nchan);
 
 /* ---------------------------------------------------------------------------------------------
  * Thermal noise + gains.  Replaces interferometry.py:6676-6693 (generate_noise) and :6707-6722
@@ -228,7 +236,7 @@ int pb200_healpix_beam(pb200_ctx* ctx, const void* d_map, int map_dtype, int nsi
  * InterferometerArray.phase_centering, interferometry.py:7869-7881 (called via rotate_visibilities,
  * scripts/run_prisim.py:2282):  V[b,f] *= exp(-2 pi i f b.(s_old - s_new)/c), in place.
  *   d_vis [nbl,nchan] complex128 (in/out), d_bl [nbl,3] metres in the frame of the direction
- *   cosines, h_dpos [3] = s_old - s_new (host), h_freqs [nchan] Hz (host).  Synchronises the stream.
+ *   cosines, h_dpos [3] = s_old - s_new (host), h_freqs [nchan] Hz (host).
  */
 int pb200_phase_rotate(pb200_ctx* ctx, void* d_vis, const double* d_bl, int nbl, const double* h_dpos,
                        const double* h_freqs, int nchan, void* stream);

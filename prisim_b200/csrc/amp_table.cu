@@ -215,7 +215,7 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
   if (amp_dtype != PB200_AMP_F32 && amp_dtype != PB200_AMP_F64)
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_scale: amp_dtype must be PB200_AMP_F32 or PB200_AMP_F64");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PbDeviceGuard guard(ctx->device);
   const int nslab = (nchan + PB200_SLAB - 1) / PB200_SLAB, nsrc_pad = pb200_nsrc_pad(nsrc);
   const int blocks = ctx->sm_count * 8;
   if (amp_dtype == PB200_AMP_F32)
@@ -257,21 +257,18 @@ int pb200_amp_table(pb200_ctx* ctx, const double* d_dircos, const int32_t* d_ind
   if (!spec->d_spectrum && (!spec->d_flux_scale || !spec->d_index || !spec->d_freq_ref))
     return pb_fail(ctx, PB200_EINVAL, "pb200_amp_table: power-law spectrum needs scale, index and freq_ref");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
-  void* dfreq;
-  int rc = pb_scratch(ctx, 1, sizeof(double) * (size_t)nchan, &dfreq);
+  PbDeviceGuard guard(ctx->device);
+  const double* dfreq;
+  int rc = pb_channels_device(ctx, h_freqs, nchan, nchan, stream, &dfreq);
   if (rc) return rc;
-  PB_CUDA(ctx, cudaMemcpyAsync(dfreq, h_freqs, sizeof(double) * nchan, cudaMemcpyHostToDevice, stream));
   AmpParams P;
   P.beam = *beam; P.spec = *spec;
-  P.dircos = d_dircos; P.index = d_index; P.pbeam = d_pbeam; P.freqs = (const double*)dfreq; P.amp = d_amp;
+  P.dircos = d_dircos; P.index = d_index; P.pbeam = d_pbeam; P.freqs = dfreq; P.amp = d_amp;
   P.nsrc = nsrc; P.nsrc_pad = pb200_nsrc_pad(nsrc > 0 ? nsrc : 1); P.nchan = nchan;
   P.nslab = (nchan + PB200_SLAB - 1) / PB200_SLAB;
   if (amp_dtype == PB200_AMP_F64) k_amp_table<double><<<P.nsrc_pad, AMP_THREADS, 0, stream>>>(P);
   else k_amp_table<float><<<P.nsrc_pad, AMP_THREADS, 0, stream>>>(P);
   PB_CHECK_LAUNCH(ctx, "k_amp_table");
-  // h_freqs was staged with an async copy from (possibly pageable) host memory
-  PB_CUDA(ctx, cudaStreamSynchronize(stream));
   return PB200_OK;
 }
 

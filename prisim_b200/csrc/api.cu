@@ -1,5 +1,6 @@
 // Context management for libprisim_b200.so.
 #include "common.cuh"
+#include <cstdlib>
 #include <new>
 
 extern "C" {
@@ -20,17 +21,22 @@ int pb200_ctx_create(pb200_ctx** out, int device) {
   memset(ctx, 0, sizeof(*ctx));
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PB200_ECUDA; }
+  const char* spc = getenv("PB200_SKYVIS_SPC");          // developer override of the phase-sum CTA shape (tools/variants.sh)
+  ctx->skyvis_spc_env = spc ? atoi(spc) : 0;
   *out = ctx;
   return PB200_OK;
 }
 
 void pb200_ctx_destroy(pb200_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  PbDeviceGuard guard(ctx->device);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->twiddle) cudaFree(ctx->twiddle);
+  for (int i = 0; i < PB_CHAN_CACHE; ++i) {
+    if (ctx->chan[i].dev) cudaFree(ctx->chan[i].dev);
+    if (ctx->chan[i].host) cudaFreeHost(ctx->chan[i].host);
+  }
   delete ctx;
 }
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../include/prisim_b200.h"
 
+#define PB_CHAN_CACHE 4
 struct pb200_ctx {
   int device;
   int sm_count;
@@ -17,6 +18,15 @@ struct pb200_ctx {
   // cached twiddle table for the delay transform
   void* twiddle;
   int twiddle_n;
+  // channel grids already resident on the device (pb_channels_device): host copy + device copy
+  struct {
+    double* host;
+    double* dev;
+    int nchan, npad;
+    unsigned long long stamp;
+  } chan[PB_CHAN_CACHE];
+  unsigned long long chan_clock;
+  int skyvis_spc_env;      // PB200_SKYVIS_SPC read once at ctx creation (developer override), 0 = unset
 };
 
 #define PB_SPEED_OF_LIGHT 299792458.0   // scipy.constants.c
@@ -53,6 +63,60 @@ inline int pb_scratch(pb200_ctx* ctx, int slot, size_t bytes, void** out) {
     ctx->scratch_bytes[slot] = want;
   }
   *out = ctx->scratch[slot];
+  return PB200_OK;
+}
+
+// Entry points run on ctx->device and put the caller's current device back on return (single-process
+// multi-GPU callers, e.g. torch with several devices, keep their own current device).
+struct PbDeviceGuard {
+  int prev;
+  bool changed;
+  explicit PbDeviceGuard(int device) : prev(-1), changed(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) changed = (cudaSetDevice(device) == cudaSuccess);
+  }
+  ~PbDeviceGuard() { if (changed) cudaSetDevice(prev); }
+  PbDeviceGuard(const PbDeviceGuard&) = delete;
+  PbDeviceGuard& operator=(const PbDeviceGuard&) = delete;
+};
+
+// Channel frequencies on the device.  The reference passes the same `channels` array to every call
+// (interferometry.py:5779-5786), so each ctx keeps the last PB_CHAN_CACHE grids resident: a call with a grid
+// seen before enqueues nothing and does not synchronise; a new grid is uploaded once (that call synchronises
+// the stream so the cached copy is complete before any other stream may use it).  `npad` >= nchan entries are
+// stored, padding repeats the last frequency.
+inline int pb_channels_device(pb200_ctx* ctx, const double* h_freqs, int nchan, int npad, cudaStream_t stream,
+                              const double** d_out) {
+  if (npad < nchan) npad = nchan;
+  int victim = 0;
+  for (int i = 0; i < PB_CHAN_CACHE; ++i) {
+    auto& e = ctx->chan[i];
+    if (e.dev && e.nchan == nchan && e.npad == npad && memcmp(e.host, h_freqs, sizeof(double) * nchan) == 0) {
+      e.stamp = ++ctx->chan_clock;
+      *d_out = e.dev;
+      return PB200_OK;
+    }
+    if (ctx->chan[i].stamp < ctx->chan[victim].stamp) victim = i;
+  }
+  auto& e = ctx->chan[victim];
+  if (e.dev) { cudaFree(e.dev); e.dev = nullptr; }
+  if (e.host) { cudaFreeHost(e.host); e.host = nullptr; }
+  cudaError_t err = cudaMallocHost((void**)&e.host, sizeof(double) * (size_t)npad);
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e.dev, sizeof(double) * (size_t)npad);
+  if (err != cudaSuccess) {
+    if (e.host) { cudaFreeHost(e.host); e.host = nullptr; }
+    e.dev = nullptr;
+    return pb_fail(ctx, PB200_ENOMEM, "channel grid allocation: %s", cudaGetErrorString(err));
+  }
+  for (int k = 0; k < npad; ++k) e.host[k] = h_freqs[k < nchan ? k : nchan - 1];
+  err = cudaMemcpyAsync(e.dev, e.host, sizeof(double) * (size_t)npad, cudaMemcpyHostToDevice, stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+  if (err != cudaSuccess) {
+    cudaFree(e.dev); cudaFreeHost(e.host);
+    e.dev = nullptr; e.host = nullptr;
+    return pb_fail(ctx, PB200_ECUDA, "channel grid upload: %s", cudaGetErrorString(err));
+  }
+  e.nchan = nchan; e.npad = npad; e.stamp = ++ctx->chan_clock;
+  *d_out = e.dev;
   return PB200_OK;
 }
 

@@ -364,7 +364,7 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
   if (nrows <= 0 || nchan <= 0 || !d_out || df <= 0.0) return pb_fail(ctx, PB200_EINVAL, "pb200_delay_transform: bad arguments");
   if (!d_x && !d_bp && !d_wts) return pb_fail(ctx, PB200_EINVAL, "pb200_delay_transform: nothing to transform");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PbDeviceGuard guard(ctx->device);
   Plan pl = make_plan(nchan, pad, downsample);
   if (ctx->twiddle_n != pl.nfft) {
     PB_CUDA(ctx, cudaStreamSynchronize(stream));

@@ -152,7 +152,7 @@ extern "C" int pb200_healpix_beam(pb200_ctx* ctx, const void* d_map, int map_dty
   if (map_dtype != PB200_AMP_F32 && map_dtype != PB200_AMP_F64)
     return pb_fail(ctx, PB200_EINVAL, "pb200_healpix_beam: map_dtype must be PB200_AMP_F32 or PB200_AMP_F64");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PbDeviceGuard guard(ctx->device);
   if (nsrc > 0) {
     if (!d_dircos) return pb_fail(ctx, PB200_EINVAL, "pb200_healpix_beam: null d_dircos");
     if (map_dtype == PB200_AMP_F64) k_healpix_gather<double><<<pb_div_up(nsrc, 8), 256, 0, stream>>>((const double*)d_map, nside, d_dircos, nsrc, nchan, d_logbeam);

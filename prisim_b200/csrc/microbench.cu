@@ -516,7 +516,7 @@ int main() {
 // Library entry: the three pipe rates bench.py quotes as roofline denominators.
 extern "C" int pb200_microbench(pb200_ctx* ctx, double* out, int n) {
   if (!ctx || !out || n < 5) return ctx ? pb_fail(ctx, PB200_EINVAL, "pb200_microbench: need out[5]") : PB200_EINVAL;
-  if (cudaSetDevice(ctx->device) != cudaSuccess) return pb_fail(ctx, PB200_ECUDA, "cudaSetDevice failed");
+  PbDeviceGuard guard(ctx->device);
   const int threads = 256, bps = 2;
   int blocks = ctx->sm_count * bps;
   float* o; long long* cyc;

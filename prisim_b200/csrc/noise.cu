@@ -125,7 +125,7 @@ extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d
   if (d_vis && !d_skyvis) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: d_vis requested without d_skyvis");
   if (nbl_total < bl_offset + nbl) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: shard exceeds nbl_total");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PbDeviceGuard guard(ctx->device);
   NoiseParams P;
   P.skyvis = (const double2*)d_skyvis; P.tsys = d_tsys; P.aeff = d_aeff; P.effq = d_effq;
   P.gains = (const double2*)d_gains; P.rms = d_rms; P.noise = (double2*)d_noise; P.vis = (double2*)d_vis;

@@ -10,15 +10,16 @@ namespace {
 __global__ void __launch_bounds__(256) k_phase_rotate(double2* __restrict__ vis, const double* __restrict__ bl,
                                                       const double* __restrict__ freqs, double dx, double dy, double dz,
                                                       int nbl, int nchan) {
-  const int b = blockIdx.y;
-  const double tau = (bl[3 * (size_t)b] * dx + bl[3 * (size_t)b + 1] * dy + bl[3 * (size_t)b + 2] * dz) / PB_SPEED_OF_LIGHT;
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nchan; f += gridDim.x * blockDim.x) {
-    double u = tau * freqs[f];
-    u -= rint(u);
-    double sn, cs;
-    sincospi(2.0 * u, &sn, &cs);
-    double2 v = vis[(size_t)b * nchan + f];
-    vis[(size_t)b * nchan + f] = make_double2(v.x * cs + v.y * sn, v.y * cs - v.x * sn);   // v * (cs - i sn)
+  for (int b = blockIdx.y; b < nbl; b += gridDim.y) {      // grid-stride: gridDim.y is capped at 65535
+    const double tau = (bl[3 * (size_t)b] * dx + bl[3 * (size_t)b + 1] * dy + bl[3 * (size_t)b + 2] * dz) / PB_SPEED_OF_LIGHT;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nchan; f += gridDim.x * blockDim.x) {
+      double u = tau * freqs[f];
+      u -= rint(u);
+      double sn, cs;
+      sincospi(2.0 * u, &sn, &cs);
+      double2 v = vis[(size_t)b * nchan + f];
+      vis[(size_t)b * nchan + f] = make_double2(v.x * cs + v.y * sn, v.y * cs - v.x * sn);   // v * (cs - i sn)
+    }
   }
 }
 
@@ -30,14 +31,12 @@ extern "C" int pb200_phase_rotate(pb200_ctx* ctx, void* d_vis, const double* d_b
   if (!d_vis || !d_bl || !h_dpos || !h_freqs || nbl <= 0 || nchan <= 0)
     return pb_fail(ctx, PB200_EINVAL, "pb200_phase_rotate: bad arguments");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
-  void* dfreq;
-  int rc = pb_scratch(ctx, 5, sizeof(double) * (size_t)nchan, &dfreq);
+  PbDeviceGuard guard(ctx->device);
+  const double* dfreq;
+  int rc = pb_channels_device(ctx, h_freqs, nchan, nchan, stream, &dfreq);
   if (rc) return rc;
-  PB_CUDA(ctx, cudaMemcpyAsync(dfreq, h_freqs, sizeof(double) * nchan, cudaMemcpyHostToDevice, stream));
-  dim3 grid(pb_div_up(nchan, 256), nbl);
-  k_phase_rotate<<<grid, 256, 0, stream>>>((double2*)d_vis, d_bl, (const double*)dfreq, h_dpos[0], h_dpos[1], h_dpos[2], nbl, nchan);
+  dim3 grid(pb_div_up(nchan, 256), nbl < 65535 ? nbl : 65535);
+  k_phase_rotate<<<grid, 256, 0, stream>>>((double2*)d_vis, d_bl, dfreq, h_dpos[0], h_dpos[1], h_dpos[2], nbl, nchan);
   PB_CHECK_LAUNCH(ctx, "k_phase_rotate");
-  PB_CUDA(ctx, cudaStreamSynchronize(stream));        // h_freqs staged from pageable host memory
   return PB200_OK;
 }

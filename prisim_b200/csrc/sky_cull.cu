@@ -130,7 +130,7 @@ extern "C" int pb200_sky_cull(pb200_ctx* ctx, const double* d_skypos, int nsrc0,
   if (nsrc0 == 0) return PB200_OK;
   if (!d_skypos || !d_dircos || !d_index) return pb_fail(ctx, PB200_EINVAL, "pb200_sky_cull: null device pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PbDeviceGuard guard(ctx->device);
   int nblocks = pb_div_up(nsrc0, CULL_THREADS);
   size_t b_dircos = sizeof(double) * 3 * (size_t)nsrc0;
   size_t b_flags = ((size_t)nsrc0 + 255) & ~(size_t)255;

@@ -69,17 +69,37 @@ template <int SPC> struct Shape {
 // return the fraction itself to fp32 rounding, with no coherent phase-scale bias.
 #define PB_INV_RCP2PI_F32 (1.0 / 0.15915493667125701904296875)
 
+// Work decomposition of one launch (persistent CTAs, one per SM).  An output tile = one CTA-sized block of
+// baselines x channels summed over all S source tiles.  The first `nwave * ncta` output tiles are done whole, one per
+// CTA and wave, all CTAs sweeping the source axis together (the amplitude table is then read from DRAM once per wave
+// and shared through L2).  The remaining `ntail` (< ncta) output tiles are split ALONG THE SOURCE AXIS over all CTAs
+// (stream-K): CTA c owns the contiguous unit range [c U / ncta, (c+1) U / ncta) of the ntail x S (tile, source tile)
+// units, so every SM finishes at the same time whatever nbl is -- without this a launch of 480 tiles on 148 SMs (one
+// eighth of HERA-350) runs 4 waves for 3.24 waves of work.  A CTA whose range starts inside an output tile writes that
+// partial sum to its own "head" slot; k_skyvis_finalize adds the head slots to the tile's own slot in CTA order, so the
+// result is deterministic (no atomics).
+struct Sched {
+  int gx;                  // output tiles along the channel axis (tile t -> x = t % gx, y = t / gx)
+  int ntile;               // output tiles
+  int S;                   // source tiles per output tile
+  int nwave;               // whole-tile waves
+  int ntail;               // output tiles of the stream-K tail
+  int ncta;                // persistent CTAs (gridDim.x)
+};
+
 struct SkyvisParams {
+  Sched sc;
   const void* amp;         // [nslab][nsrc_pad][SLAB] fp32 (fp64 for the fp64 kernel with an fp64 table)
   const double* geom;      // [nsrc_pad][4]: l, m, n, taper coefficient
   const double* bl;        // [nbl][3] metres
   const double* freqs;     // device [nchan_pad] Hz (padded channels repeat the last frequency)
   double* vis;             // [nbl][nchan] complex128
-  double2* accum;          // fp64 running sums, warp-tile layout [cta][warp][k][lane] (coalesced flushes)
+  double2* accum;          // fp64 running sums, warp-tile layout [slot][warp][k][lane] (coalesced flushes); slots
+                           // 0..ntile-1 = output tiles, ntile + c = head partial of CTA c
   double pc[3];            // phase-centre dircos
   double f0, df;           // uniform channels: f_k = f0 + k df
   int nsrc_pad, nbl, nchan, nslab;
-  int spc;                 // slabs per CTA of the launch that filled `accum` (finalize)
+  int kt, wc, wb;          // finalize: channels per thread, channel blocks and baseline groups per CTA of the launch that filled `accum`
   const unsigned* smax2_bits;   // device: float bits of max_s |s - s_pc|^2 (k_geom_stage)
 };
 
@@ -133,16 +153,51 @@ __device__ __forceinline__ Geometry load_baseline(const SkyvisParams& P, int b, 
   return G;
 }
 
-// add the fp32 partial sums of one thread into its fp64 running sums and clear them.  The running
-// sums live in a scratch buffer laid out [cta][warp][k][lane] so that every load/store of a warp is
-// one contiguous 512-byte run (the [nbl][nchan] output layout would put the 32 lanes 16 KB apart);
-// k_skyvis_finalize transposes the scratch into the output once at the end.
-__device__ __forceinline__ void flush_acc(const SkyvisParams& P, float2 (&acc_re)[KT / 2], float2 (&acc_im)[KT / 2]) {
-  const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-  double2* base = P.accum + ((cta * NWARPS + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
+// One piece of work of a persistent CTA: output tile `tile`, source tiles [s0, s1), partial sums into `slot`.
+struct Segment {
+  int tile, s0, s1;
+  size_t slot;
+};
+
+// Iterates the segments of CTA `cta` (see Sched): whole tiles first, then its share of the stream-K tail.
+struct SegmentIter {
+  const Sched sc;
+  const int cta;
+  int wave;
+  long long u, u1;
+  __device__ SegmentIter(const Sched& sc_, int cta_) : sc(sc_), cta(cta_), wave(0) {
+    const long long U = (long long)sc.ntail * sc.S;
+    u = U * cta / sc.ncta;
+    u1 = U * (cta + 1) / sc.ncta;
+  }
+  __device__ bool next(Segment& sg) {
+    if (wave < sc.nwave) {
+      sg.tile = wave * sc.ncta + cta; sg.s0 = 0; sg.s1 = sc.S; sg.slot = (size_t)sg.tile;
+      ++wave;
+      return true;
+    }
+    if (u >= u1) return false;
+    const int q = (int)(u / sc.S);
+    sg.s0 = (int)(u - (long long)q * sc.S);
+    sg.s1 = (int)min((long long)sc.S, sg.s0 + (u1 - u));
+    sg.tile = sc.nwave * sc.ncta + q;
+    sg.slot = sg.s0 == 0 ? (size_t)sg.tile : (size_t)sc.ntile + cta;
+    u += sg.s1 - sg.s0;
+    return true;
+  }
+};
+
+// Move the fp32 partial sums of one thread into its fp64 running sums and clear them.  The running sums live in a
+// scratch buffer laid out [slot][warp][k][lane] so that every load/store of a warp is one contiguous 512-byte run
+// (the [nbl][nchan] output layout would put the 32 lanes 16 KB apart); k_skyvis_finalize transposes the scratch into
+// the output once at the end.  `first`: the slot holds nothing yet -- store instead of read-modify-write (no memset
+// of the scratch, one read less).
+__device__ __forceinline__ void flush_acc(const SkyvisParams& P, size_t slot, bool first, float2 (&acc_re)[KT / 2],
+                                          float2 (&acc_im)[KT / 2]) {
+  double2* base = P.accum + ((slot * NWARPS + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
-    double2 v = base[k * 32];
+    double2 v = first ? make_double2(0.0, 0.0) : base[k * 32];
     v.x += (double)((k & 1) ? acc_re[k >> 1].y : acc_re[k >> 1].x);
     v.y += (double)((k & 1) ? acc_im[k >> 1].y : acc_im[k >> 1].x);
     base[k * 32] = v;
@@ -151,24 +206,50 @@ __device__ __forceinline__ void flush_acc(const SkyvisParams& P, float2 (&acc_re
   for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
 }
 
-// scratch [cta][warp][k][lane] -> vis[b][ch]: one CTA per warp tile, transposed through shared memory
-__global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P, int gridx) {
-  __shared__ double2 tile[KT][33];
-  const size_t t = blockIdx.x;                          // (cta * 16 + warp)
+// scratch [slot][warp][k][lane] -> vis[b][ch]: one CTA per warp tile, transposed through shared memory.  Adds the head
+// partials of the CTAs whose stream-K range starts inside this output tile, in CTA order.
+template <int KTV>
+__global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
+  __shared__ double2 tile[KTV][33];
+  const Sched sc = P.sc;
+  const size_t t = blockIdx.x;                          // (output tile * 16 + warp)
   const int warp = (int)(t % NWARPS);
-  const size_t cta = t / NWARPS;
-  const int gx = (int)(cta % gridx), gy = (int)(cta / gridx);
-  const int WC = P.spc * WCS, WB = NWARPS / WC;
-  const int wb = warp % WB, wc = warp / WB;
-  const double2* src = P.accum + t * KT * 32;
+  const int ot = (int)(t / NWARPS);
+  const int gx = ot % sc.gx, gy = ot / sc.gx;
+  const int wb = warp % P.wb, wc = warp / P.wb;
+  const size_t wtile = (size_t)KTV * 32;                // double2 per warp tile
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int k = ty; k < KT; k += 8) tile[k][tx] = src[k * 32 + tx];
+  // head partials: CTAs c with  q S < floor(c U / ncta) < (q+1) S,  q = index of this tile in the tail
+  int c_lo = 0, c_hi = 0;
+  const int q = ot - sc.nwave * sc.ncta;
+  const long long U = (long long)sc.ntail * sc.S;
+  if (q >= 0) {
+    const long long lo = (long long)q * sc.S, hi = lo + sc.S;
+    c_lo = (int)(lo * sc.ncta / U);
+    while (c_lo < sc.ncta && U * c_lo / sc.ncta <= lo) ++c_lo;
+    c_hi = c_lo;
+    while (c_hi < sc.ncta && U * c_hi / sc.ncta < hi) ++c_hi;
+  }
+  for (int k = ty; k < KTV; k += 8) {
+    double2 v = P.accum[t * wtile + k * 32 + tx];
+    for (int c = c_lo; c < c_hi; ++c) {
+      if (U * (c + 1) / sc.ncta == U * c / sc.ncta) continue;      // empty range: no head partial was written
+      const double2 h = P.accum[((size_t)(sc.ntile + c) * NWARPS + warp) * wtile + k * 32 + tx];
+      v.x += h.x; v.y += h.y;
+    }
+    tile[k][tx] = v;
+  }
   __syncthreads();
-  const int b0 = gy * 32 * WB + wb * 32, ch = (gx * P.spc + wc / WCS) * PB200_SLAB + (wc % WCS) * KT + tx;
+  const int b0 = gy * 32 * P.wb + wb * 32;
   double2* vis = reinterpret_cast<double2*>(P.vis);
   for (int r = ty; r < 32; r += 8) {
     const int b = b0 + r;
-    if (b < P.nbl && ch < P.nchan) vis[(size_t)b * P.nchan + ch] = tile[tx][r];
+#pragma unroll
+    for (int kk = 0; kk < KTV; kk += 32) {
+      const int k = kk + tx;
+      const int ch = (gx * P.wc + wc) * KTV + k;
+      if (k < KTV && b < P.nbl && ch < P.nchan) vis[(size_t)b * P.nchan + ch] = tile[k][r];
+    }
   }
 }
 
@@ -194,42 +275,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wb = warp % WB, wc = warp / WB;           // tid % BL == wb*32 + lane: producer and consumer baseline coincide
   const int sl = wc / WCS, wcs = wc % WCS;            // slab within the CTA, channel block within the slab
-  const int slab = blockIdx.x * SPC + sl;
   const int bcol = wb * 32 + lane;
-  const int b = blockIdx.y * S::BL + bcol;
-  const bool valid = b < P.nbl;
-  const int kbase = slab * PB200_SLAB + wcs * KT;     // first global channel of this thread
-  const int ntiles = P.nsrc_pad / T;
-  const Geometry G = load_baseline(P, b, valid);
-  const double fk0 = P.f0 + (double)kbase * P.df;
   const double df = P.df;
-
-  if (TAPER && tid < SPC * PB200_SLAB) {
-    const int ch = blockIdx.x * SPC * PB200_SLAB + tid;
-    const float fs = (float)(P.freqs[ch < P.nslab * PB200_SLAB ? ch : P.nslab * PB200_SLAB - 1] * 1e-8);
-    sfreq2[tid] = fs * fs;
-  }
-  // taper recurrence constants (uniform grid): F_k = F0 + k dF in units of 1e8 Hz
-  const float tF0 = (float)(fk0 * 1e-8), tdF = (float)(df * 1e-8);
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // slabs of this CTA that exist (the last CTA along x may be short when nslab % SPC != 0)
-  const int nsl = min(SPC, P.nslab - (int)blockIdx.x * SPC);
-  auto issue = [&](int tile, int stage) {
+  float2 acc_re[KT / 2], acc_im[KT / 2];
+#pragma unroll
+  for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
+
+  uint32_t fill = 0;                                  // source tiles this CTA has consumed so far: stage = fill & 1, mbarrier parity = (fill >> 1) & 1
+  SegmentIter seg_iter(P.sc, (int)blockIdx.x);
+  Segment sg;
+#pragma unroll 1
+  while (seg_iter.next(sg)) {
+  const int tile_x = sg.tile % P.sc.gx, tile_y = sg.tile / P.sc.gx;
+  const int slab = tile_x * SPC + sl;
+  const int b = tile_y * S::BL + bcol;
+  const bool valid = b < P.nbl;
+  const int kbase = slab * PB200_SLAB + wcs * KT;     // first global channel of this thread
+  const int ntiles = sg.s1 - sg.s0;
+  const Geometry G = load_baseline(P, b, valid);
+  const double fk0 = P.f0 + (double)kbase * P.df;
+
+  if (TAPER && tid < SPC * PB200_SLAB) {
+    const int ch = tile_x * SPC * PB200_SLAB + tid;
+    const float fs = (float)(P.freqs[ch < P.nslab * PB200_SLAB ? ch : P.nslab * PB200_SLAB - 1] * 1e-8);
+    sfreq2[tid] = fs * fs;
+  }
+  // taper recurrence constants (uniform grid): F_k = F0 + k dF in units of 1e8 Hz
+  const float tF0 = (float)(fk0 * 1e-8), tdF = (float)(df * 1e-8);
+
+  // slabs of this output tile that exist (the last tile along x may be short when nslab % SPC != 0)
+  const int nsl = min(SPC, P.nslab - tile_x * SPC);
+  auto issue = [&](int i, int stage) {                 // source tile sg.s0 + i of this segment
+    const size_t row0 = (size_t)(sg.s0 + i) * T;
     mbar_expect_tx(&full[stage], (uint32_t)(nsl * sizeof(float) * T * PB200_SLAB + sizeof(double) * T * 4));
-    for (int i = 0; i < nsl; ++i)
-      tma_bulk_g2s(&tin[stage].amp[i][0][0],
-                   (const float*)P.amp + ((size_t)(blockIdx.x * SPC + i) * P.nsrc_pad + (size_t)tile * T) * PB200_SLAB,
+    for (int j = 0; j < nsl; ++j)
+      tma_bulk_g2s(&tin[stage].amp[j][0][0],
+                   (const float*)P.amp + ((size_t)(tile_x * SPC + j) * P.nsrc_pad + row0) * PB200_SLAB,
                    sizeof(float) * T * PB200_SLAB, &full[stage]);
-    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
+    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T * 4, &full[stage]);
   };
   if (tid == 0) {
-    issue(0, 0);
-    if (ntiles > 1) issue(1, 1);
+    issue(0, fill & 1);
+    if (ntiles > 1) issue(1, (fill + 1) & 1);
   }
   const bool live = sl < nsl;                          // warps of a missing slab only help with the precompute
 
@@ -249,8 +342,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   // cooperative per-tile stage: tau and the channel rotation for S::PRE sources of this
   // thread's own baseline (sources s = wc, wc+WC, ...)
   auto precompute = [&](int tile) {
-    const int stage = tile & 1;
-    mbar_wait(&full[stage], (tile >> 1) & 1);
+    const int stage = (fill + tile) & 1;
+    mbar_wait(&full[stage], ((fill + tile) >> 1) & 1);
 #pragma unroll 2
     for (int j = 0; j < S::PRE; ++j) {
       const int s = wc + WC * j;
@@ -270,16 +363,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     }
   };
 
-  float2 acc_re[KT / 2], acc_im[KT / 2];
-#pragma unroll
-  for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
-
   precompute(0);
   __syncthreads();
 
   auto run_tile = [&](int tile, auto lift_c) {
     constexpr bool LIFT = decltype(lift_c)::value;
-    const int stage = tile & 1;
+    const int stage = (fill + tile) & 1;
     const TileIn<SPC>& ti = tin[stage];
     const TilePre<SPC>& tp = tpre[stage];
     // software pipeline over sources: the anchor(s) of source s+1 are evaluated while the channel loop of s runs
@@ -408,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     // PACKED: FFMA2/FMUL2 on (even, odd) channel pairs; otherwise the same arithmetic as scalar FFMA on the two halves
     auto fma2 = [](float2 a, float2 b, float2 c) { return PACKED ? __ffma2_rn(a, b, c) : make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); };
     auto mul2 = [](float2 a, float2 b) { return PACKED ? __fmul2_rn(a, b) : make_float2(a.x * b.x, a.y * b.y); };
-    const int stage = tile & 1;
+    const int stage = (fill + tile) & 1;
     const TileIn<SPC>& ti = tin[stage];
     const TilePre<SPC>& tp = tpre[stage];
     constexpr int H = KT / 2;                            // channels per half block
@@ -469,6 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     }
   };
 
+  bool fresh = true;                                   // nothing of this segment is in its slot yet
   for (int tile = 0; tile < ntiles; ++tile) {
     if (!live && tile + 1 < ntiles) precompute(tile + 1);
     if (live) {
@@ -477,12 +567,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       else run_tile(tile, std::false_type());
     }
     __syncthreads();                                   // tile consumed, next tile's tau/rot visible
-    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, tile & 1);
+    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, (fill + tile) & 1);
     // flushes are staggered over the warps of a scheduler like the precompute (accumulators are thread-private,
     // so a warp may flush at any tile boundary): one warp waits on its global read-modify-write, three keep going
-    if (live && ((tile + 1 + (warp >> 2) * (FLUSH_TILES / 4)) % FLUSH_TILES) == 0 && !(PB_ABLATE & 4)) flush_acc(P, acc_re, acc_im);
+    if (live && ((tile + 1 + (warp >> 2) * (FLUSH_TILES / 4)) % FLUSH_TILES) == 0 && !(PB_ABLATE & 4)) {
+      flush_acc(P, sg.slot, fresh, acc_re, acc_im);
+      fresh = false;
+    }
   }
-  if (live) flush_acc(P, acc_re, acc_im);
+  if (live) flush_acc(P, sg.slot, fresh, acc_re, acc_im);
+  fill += (uint32_t)ntiles;
+  }   // segments
 }
 
 // =================================================================================================
@@ -500,93 +595,115 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wb = warp % WB, wc = warp / WB;
-  const int slab = blockIdx.x;
-  const int b = blockIdx.y * S::BL + wb * 32 + lane;
-  const bool valid = b < P.nbl;
-  const int kbase = slab * PB200_SLAB + wc * KT;
-  const int ntiles = P.nsrc_pad / T;
-  const Geometry G = load_baseline(P, b, valid);
-
-  if (tid < PB200_SLAB) {
-    const double f = P.freqs[slab * PB200_SLAB + tid];
-    sfreq64[tid] = f;
-    const float fs = (float)(f * 1e-8);
-    sfreq2[tid] = fs * fs;
-  }
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  const float* amp_slab = (const float*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
-  auto issue = [&](int tile, int stage) {
-    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn<1>));
-    tma_bulk_g2s(&tin[stage].amp[0][0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
-    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
-  };
-  if (tid == 0) {
-    issue(0, 0);
-    if (ntiles > 1) issue(1, 1);
-  }
   float2 acc_re[KT / 2], acc_im[KT / 2];
 #pragma unroll
   for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int stage = tile & 1;
-    mbar_wait(&full[stage], (tile >> 1) & 1);
-    const TileIn<1>& ti = tin[stage];
+  uint32_t fill = 0;
+  SegmentIter seg_iter(P.sc, (int)blockIdx.x);
+  Segment sg;
 #pragma unroll 1
-    for (int s = 0; s < T; ++s) {
-      const double4 g = *reinterpret_cast<const double4*>(&ti.geom[s][0]);
-      const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;
-      const double tau = tau_g - G.tau_pc;
-      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[0][s][wc * KT]);
-      float kap = 0.f;
-      if (TAPER) kap = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
-#pragma unroll
-      for (int k4 = 0; k4 < KT / 4; ++k4) {
-        const float4 a4 = arow[k4];
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = 4 * k4 + j;
-          const float x = (float)(2.0 * frac_turns(tau * sfreq64[wc * KT + k]));   // interferometry.py:6332
-          float sn, cs;
-          sincospif(x, &sn, &cs);
-          float a = av[j];
-          if (TAPER) a *= exp2f(-kap * sfreq2[wc * KT + k]);
-          if (k & 1) { acc_re[k >> 1].y = fmaf(a, cs, acc_re[k >> 1].y); acc_im[k >> 1].y = fmaf(-a, sn, acc_im[k >> 1].y); }
-          else       { acc_re[k >> 1].x = fmaf(a, cs, acc_re[k >> 1].x); acc_im[k >> 1].x = fmaf(-a, sn, acc_im[k >> 1].x); }   // :6340
-        }
-      }
+  while (seg_iter.next(sg)) {
+    const int slab = sg.tile % P.sc.gx;
+    const int b = (sg.tile / P.sc.gx) * S::BL + wb * 32 + lane;
+    const bool valid = b < P.nbl;
+    const int ntiles = sg.s1 - sg.s0;
+    const Geometry G = load_baseline(P, b, valid);
+    __syncthreads();                                   // previous segment done with sfreq*, barriers initialised
+    if (tid < PB200_SLAB) {
+      const double f = P.freqs[slab * PB200_SLAB + tid];
+      sfreq64[tid] = f;
+      const float fs = (float)(f * 1e-8);
+      sfreq2[tid] = fs * fs;
     }
     __syncthreads();
-    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-    if (((tile + 1) % FLUSH_TILES) == 0) flush_acc(P, acc_re, acc_im);
+    const float* amp_slab = (const float*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
+    auto issue = [&](int i, int stage) {
+      const size_t row0 = (size_t)(sg.s0 + i) * T;
+      mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn<1>));
+      tma_bulk_g2s(&tin[stage].amp[0][0][0], amp_slab + row0 * PB200_SLAB, sizeof(float) * T * PB200_SLAB, &full[stage]);
+      tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T * 4, &full[stage]);
+    };
+    if (tid == 0) {
+      issue(0, fill & 1);
+      if (ntiles > 1) issue(1, (fill + 1) & 1);
+    }
+    bool fresh = true;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int stage = (fill + tile) & 1;
+      mbar_wait(&full[stage], ((fill + tile) >> 1) & 1);
+      const TileIn<1>& ti = tin[stage];
+#pragma unroll 1
+      for (int s = 0; s < T; ++s) {
+        const double4 g = *reinterpret_cast<const double4*>(&ti.geom[s][0]);
+        const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;
+        const double tau = tau_g - G.tau_pc;
+        const float4* arow = reinterpret_cast<const float4*>(&ti.amp[0][s][wc * KT]);
+        float kap = 0.f;
+        if (TAPER) kap = (float)(g.w * fmax(G.blen2 - tau_g * tau_g, 0.0));
+#pragma unroll
+        for (int k4 = 0; k4 < KT / 4; ++k4) {
+          const float4 a4 = arow[k4];
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            const float x = (float)(2.0 * frac_turns(tau * sfreq64[wc * KT + k]));   // interferometry.py:6332
+            float sn, cs;
+            sincospif(x, &sn, &cs);
+            float a = av[j];
+            if (TAPER) a *= exp2f(-kap * sfreq2[wc * KT + k]);
+            if (k & 1) { acc_re[k >> 1].y = fmaf(a, cs, acc_re[k >> 1].y); acc_im[k >> 1].y = fmaf(-a, sn, acc_im[k >> 1].y); }
+            else       { acc_re[k >> 1].x = fmaf(a, cs, acc_re[k >> 1].x); acc_im[k >> 1].x = fmaf(-a, sn, acc_im[k >> 1].x); }   // :6340
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
+      if (((tile + 1) % FLUSH_TILES) == 0) { flush_acc(P, sg.slot, fresh, acc_re, acc_im); fresh = false; }
+    }
+    flush_acc(P, sg.slot, fresh, acc_re, acc_im);
+    fill += (uint32_t)ntiles;
   }
-  flush_acc(P, acc_re, acc_im);
 }
 
 
 // =================================================================================================
-// fp64 kernel: same recurrence, every product and sum in double.  For skies whose visibilities are
-// the small residue of a strongly cancelling sum (smooth diffuse emission on resolved baselines:
+// fp64 kernel: same sum, every product and sum in double.  For skies whose visibilities are the small
+// residue of a strongly cancelling sum (smooth diffuse emission on resolved baselines:
 // |V_b| << sqrt(sum a^2)), where fp32 products cannot reach 1e-5 rms(V_b).  B200's FP64 pipe runs at
 // half the FP32 rate (measured 58.8 DFMA lanes/clk/SM), so this costs ~2-3x, not ~60x.
-// Thread = one baseline x 16 channels (32 fp64 accumulators); CTA = 8 channel blocks (one slab) x 2
-// baseline groups; tau and the rotation are computed once per (source, baseline) per tile with the
-// fp64 sincospi; each thread anchors its block with one fp64 sincospi.
+//   * thread = one baseline x 16 channels (32 fp64 accumulators); CTA = 8 channel blocks (one slab) x 2
+//     baseline groups; persistent CTAs over the same (whole tiles + stream-K tail) schedule as k_skyvis.
+//   * cooperative stage per sub-tile of TS sources, ONE thread per (source, baseline): delay tau, the slab
+//     anchor exp(-2 pi i tau f_slab0) and the channel rotation r = exp(-2 pi i tau df) with the fp64 sincospi,
+//     then the anchors of all 8 channel blocks by complex powering (r^16 by four squarings, seven complex
+//     multiplications) -- 3.5 DFMA per block anchor instead of one sincospi (~35 fp64 operations) per thread
+//     and source -- and, for extended sources, the taper weight and its per-channel ratio at every block
+//     start by a second-order chain from 6 transcendentals per (source, baseline) instead of 2 exp2 per thread
+//     and source.  Both are parked in shared memory (double-buffered; the stage of sub-tile i+1 overlaps the
+//     channel loops of sub-tile i).
+//   * channel loop: three-term recurrence z_{k+1} = 2 cos(phi) z_k - z_{k-1} for the unit phasor (2 DFMA per
+//     term; error growth steps^2/2 ulp = 1e-14 over 16 channels), accumulate 2 DFMA per term; with the taper
+//     w_{k+1} = w_k g_k, g_{k+1} = g_k + g_k (h - 1) and a w first: 7 DFMA per term (was 8 with the taper folded
+//     into a complex rotation).
 // =================================================================================================
 constexpr int KT64 = 16;
 constexpr int WC64 = PB200_SLAB / KT64;       // 8
 constexpr int WB64 = NWARPS / WC64;           // 2
 constexpr int BL64 = 32 * WB64;               // 64
-struct __align__(16) TilePre64 {
-  double tau[T][BL64];
-  double2 rot[T][BL64];
-  double kap[T][BL64];
-  float hm1[T][BL64];      // taper: h - 1 = expm1(-2 kap dF^2 ln2), the same for every channel block (fp32: it only scales R by 1 + hm1)
+template <bool TAPER> struct Sub64 { static constexpr int TS = TAPER ? 4 : 8; };   // sources per cooperative sub-tile
+template <int TS> struct __align__(16) Pre64 {
+  double2 anc[TS][WC64][BL64];                // exp(-2 pi i tau f) at the first channel of every 16-channel block
+  double2 rot[TS][BL64];                      // exp(-2 pi i tau df)
+};
+template <int TS> struct __align__(16) Pre64Taper {
+  double w[TS][WC64][BL64];                   // taper weight at the first channel of every block
+  double g[TS][WC64][BL64];                   // w_{k+1} / w_k there
+  double hm1[TS][BL64];                       // g_{k+1} / g_k - 1 (the same for every channel)
 };
 template <typename AMP> struct __align__(16) TileIn64 {
   AMP amp[T][PB200_SLAB];
@@ -595,130 +712,153 @@ template <typename AMP> struct __align__(16) TileIn64 {
 
 template <typename AMP, bool TAPER>
 __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams P) {
+  constexpr int TS = Sub64<TAPER>::TS;
+  constexpr int NSUB = T / TS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileIn64<AMP>* tin = reinterpret_cast<TileIn64<AMP>*>(smem_raw);
-  TilePre64* tpre = reinterpret_cast<TilePre64*>(smem_raw + NSTAGE * sizeof(TileIn64<AMP>));
-  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn64<AMP>) + sizeof(TilePre64));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
-  double* sfreq2 = reinterpret_cast<double*>(tail + 64);                   // [SLAB] (f/1e8)^2
+  Pre64<TS>* pre = reinterpret_cast<Pre64<TS>*>(smem_raw + NSTAGE * sizeof(TileIn64<AMP>));
+  Pre64Taper<TS>* pret = reinterpret_cast<Pre64Taper<TS>*>(smem_raw + NSTAGE * sizeof(TileIn64<AMP>) + 2 * sizeof(Pre64<TS>));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * sizeof(TileIn64<AMP>) + 2 * sizeof(Pre64<TS>) +
+                                               (TAPER ? 2 * sizeof(Pre64Taper<TS>) : 0));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wb = warp % WB64, wc = warp / WB64;
-  const int slab = blockIdx.x;
-  const int bcol = wb * 32 + lane;
-  const int b = blockIdx.y * BL64 + bcol;
-  const bool valid = b < P.nbl;
-  const int kbase = slab * PB200_SLAB + wc * KT64;
-  const int ntiles = P.nsrc_pad / T;
-  const Geometry G = load_baseline(P, b, valid);
-  const double fk0 = P.f0 + (double)kbase * P.df;
+  const int bcol = wb * 32 + lane;            // == tid % BL64: the stage thread of a pair owns the same baseline as in the channel loop
   const double df = P.df;
-  const double tF0 = fk0 * 1e-8, tdF = df * 1e-8;
-
-  if (tid < PB200_SLAB) {
-    const double fs = P.freqs[slab * PB200_SLAB + tid] * 1e-8;
-    sfreq2[tid] = fs * fs;
-  }
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const AMP* amp_slab = (const AMP*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
-  auto issue = [&](int tile, int stage) {
-    mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn64<AMP>));
-    tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + (size_t)tile * T * PB200_SLAB, sizeof(AMP) * T * PB200_SLAB, &full[stage]);
-    tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + (size_t)tile * T * 4, sizeof(double) * T * 4, &full[stage]);
-  };
-  if (tid == 0) {
-    issue(0, 0);
-    if (ntiles > 1) issue(1, 1);
-  }
-  auto precompute = [&](int tile) {
-    const int stage = tile & 1;
-    mbar_wait(&full[stage], (tile >> 1) & 1);
-    for (int j = 0; j < T / WC64; ++j) {
-      const int s = wc + WC64 * j;
-      const double4 g = *reinterpret_cast<const double4*>(&tin[stage].geom[s][0]);
-      const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;
-      const double tau = tau_g - G.tau_pc;
+
+  uint32_t fill = 0;
+  SegmentIter seg_iter(P.sc, (int)blockIdx.x);
+  Segment sg;
+#pragma unroll 1
+  while (seg_iter.next(sg)) {
+    const int slab = sg.tile % P.sc.gx;
+    const int b = (sg.tile / P.sc.gx) * BL64 + bcol;
+    const bool valid = b < P.nbl;
+    const int kbase = slab * PB200_SLAB + wc * KT64;
+    const int ntiles = sg.s1 - sg.s0;
+    const Geometry G = load_baseline(P, b, valid);
+    const double fs0 = P.f0 + (double)(slab * PB200_SLAB) * P.df;        // first channel of the slab
+    const double tF0 = fs0 * 1e-8, tdF = df * 1e-8;
+    const AMP* amp_slab = (const AMP*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
+    auto issue = [&](int i, int stage) {
+      const size_t row0 = (size_t)(sg.s0 + i) * T;
+      mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn64<AMP>));
+      tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + row0 * PB200_SLAB, sizeof(AMP) * T * PB200_SLAB, &full[stage]);
+      tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T * 4, &full[stage]);
+    };
+    if (tid == 0) {
+      issue(0, fill & 1);
+      if (ntiles > 1) issue(1, (fill + 1) & 1);
+    }
+    // cooperative stage of sub-tile `sub` (sources sub*TS .. sub*TS+TS-1) of source tile `tile`: thread (wc, bcol) does source wc
+    auto stage_sub = [&](int tile, int sub) {
+      const int st = (fill + tile) & 1;
+      if (sub == 0) mbar_wait(&full[st], ((fill + tile) >> 1) & 1);
+      if (wc >= TS) return;
+      const int buf = (tile * NSUB + sub) & 1;
+      const double4 g = *reinterpret_cast<const double4*>(&tin[st].geom[sub * TS + wc][0]);
+      const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
+      const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
       double sn, cs;
       sincospi(2.0 * frac_turns(tau * df), &sn, &cs);
-      tpre[stage].tau[s][bcol] = tau;
-      tpre[stage].rot[s][bcol] = make_double2(cs, -sn);
+      const double2 r = make_double2(cs, -sn);
+      pre[buf].rot[wc][bcol] = r;
+      sincospi(2.0 * frac_turns(tau * fs0), &sn, &cs);
+      double2 a = make_double2(cs, -sn);
+      double2 r16 = r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r16 = make_double2(fma(r16.x, r16.x, -r16.y * r16.y), 2.0 * r16.x * r16.y);
+      pre[buf].anc[wc][0][bcol] = a;
+#pragma unroll
+      for (int j = 1; j < WC64; ++j) {
+        a = make_double2(fma(-a.y, r16.y, a.x * r16.x), fma(a.y, r16.x, a.x * r16.y));
+        pre[buf].anc[wc][j][bcol] = a;
+      }
       if (TAPER) {
+        // w_k = exp2(-kap F_k^2), F_k = F0 + k dF in units of 1e8 Hz (interferometry.py:6262-6283; g.w folds ln2 d^2 1e16 log2 e,
+        // sqrt argument clamped at 0).  Block starts k = 16 j by the chain  w <- w X, X <- X Y;  g <- g Z.
         const double kap = g.w * fmax(G.blen2 - tau_g * tau_g, 0.0);
-        tpre[stage].kap[s][bcol] = kap;
-        tpre[stage].hm1[s][bcol] = (float)expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
-      }
-    }
-  };
-  double acc_re[KT64], acc_im[KT64];
+        double w = exp2(-kap * tF0 * tF0);
+        double X = exp2(-kap * 16.0 * tdF * (2.0 * tF0 + 16.0 * tdF));
+        const double Y = exp2(-512.0 * kap * tdF * tdF);
+        double gk = exp2(-kap * tdF * (2.0 * tF0 + tdF));
+        const double Z = exp2(-32.0 * kap * tdF * tdF);
+        pret[buf].hm1[wc][bcol] = expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
 #pragma unroll
-  for (int k = 0; k < KT64; ++k) { acc_re[k] = 0.0; acc_im[k] = 0.0; }
-  precompute(0);
-  __syncthreads();
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int stage = tile & 1;
-    if (tile + 1 < ntiles) precompute(tile + 1);
-    const TileIn64<AMP>& ti = tin[stage];
-    const TilePre64& tp = tpre[stage];
-#pragma unroll 1
-    for (int s = 0; s < T; ++s) {
-      double sn, cs;
-      sincospi(2.0 * frac_turns(tp.tau[s][bcol] * fk0), &sn, &cs);
-      double pr = cs, pi = -sn;
-      const double2 r = tp.rot[s][bcol];
-      double rr = r.x, ri = r.y, hm1 = 0.0;
-      if (TAPER) {
-        // w_k = exp2(-kap F_k^2), F_k = F0 + k dF (units of 1e8 Hz), by recurrence: w_{k+1} = w_k g_k,
-        // g_k = exp2(-kap (2 F_k dF + dF^2)), g_{k+1} = g_k h, h = exp2(-2 kap dF^2); folded into the
-        // phasor (q = p w) and the rotation (R_k = r g_k, R_{k+1} = R_k + R_k (h - 1))
-        const double kap = tp.kap[s][bcol];
-        const double w0 = exp2(-kap * tF0 * tF0), g0 = exp2(-kap * tdF * (2.0 * tF0 + tdF));
-        hm1 = (double)tp.hm1[s][bcol];
-        pr *= w0; pi *= w0; rr *= g0; ri *= g0;
-      }
-      const AMP* arow = &ti.amp[s][wc * KT64];
-      if (TAPER) {
-#pragma unroll
-        for (int k = 0; k < KT64; ++k) {
-          const double a = (double)arow[k];
-          acc_re[k] = fma(a, pr, acc_re[k]);
-          acc_im[k] = fma(a, pi, acc_im[k]);
-          const double nr = fma(-pi, ri, pr * rr);
-          const double ni = fma(pi, rr, pr * ri);
-          pr = nr; pi = ni;
-          rr = fma(rr, hm1, rr); ri = fma(ri, hm1, ri);
-        }
-      } else {
-        // unit phasors: three-term recurrence z_{k+1} = 2 cos(phi) z_k - z_{k-1} (one DFMA per component instead of a
-        // complex multiplication; over 16 channels in fp64 the error growth, steps^2/2 ulp, is 1e-14)
-        double qr = fma(-pi, ri, pr * rr), qi = fma(pi, rr, pr * ri);          // z_1 = z_0 r
-        const double C = 2.0 * rr;
-        {
-          const double a0 = (double)arow[0], a1 = (double)arow[1];
-          acc_re[0] = fma(a0, pr, acc_re[0]); acc_im[0] = fma(a0, pi, acc_im[0]);
-          acc_re[1] = fma(a1, qr, acc_re[1]); acc_im[1] = fma(a1, qi, acc_im[1]);
-        }
-#pragma unroll
-        for (int k = 2; k < KT64; k += 2) {
-          pr = fma(C, qr, -pr); pi = fma(C, qi, -pi);                           // z_k     (overwrites z_{k-2})
-          qr = fma(C, pr, -qr); qi = fma(C, pi, -qi);                           // z_{k+1} (overwrites z_{k-1})
-          const double a0 = (double)arow[k], a1 = (double)arow[k + 1];
-          acc_re[k] = fma(a0, pr, acc_re[k]); acc_im[k] = fma(a0, pi, acc_im[k]);
-          acc_re[k + 1] = fma(a1, qr, acc_re[k + 1]); acc_im[k + 1] = fma(a1, qi, acc_im[k + 1]);
+        for (int j = 0; j < WC64; ++j) {
+          pret[buf].w[wc][j][bcol] = w;
+          pret[buf].g[wc][j][bcol] = gk;
+          w *= X; X *= Y; gk *= Z;
         }
       }
-    }
+    };
+    double acc_re[KT64], acc_im[KT64];
+#pragma unroll
+    for (int k = 0; k < KT64; ++k) { acc_re[k] = 0.0; acc_im[k] = 0.0; }
+    stage_sub(0, 0);
     __syncthreads();
-    if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-  }
-  if (valid) {
-    double2* row = reinterpret_cast<double2*>(P.vis) + (size_t)b * P.nchan;
+#pragma unroll 1
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int st = (fill + tile) & 1;
+      const TileIn64<AMP>& ti = tin[st];
+#pragma unroll 1
+      for (int sub = 0; sub < NSUB; ++sub) {
+        if (sub + 1 < NSUB) stage_sub(tile, sub + 1);
+        else if (tile + 1 < ntiles) stage_sub(tile + 1, 0);
+        const int buf = (tile * NSUB + sub) & 1;
+#pragma unroll 1
+        for (int ss = 0; ss < TS; ++ss) {
+          const double2 z0 = pre[buf].anc[ss][wc][bcol];
+          const double2 r = pre[buf].rot[ss][bcol];
+          const AMP* arow = &ti.amp[sub * TS + ss][wc * KT64];
+          // unit phasors: three-term recurrence z_{k+1} = 2 cos(phi) z_k - z_{k-1}
+          double pr = z0.x, pi = z0.y;
+          double qr = fma(-pi, r.y, pr * r.x), qi = fma(pi, r.x, pr * r.y);      // z_1 = z_0 r
+          const double C = 2.0 * r.x;
+          if (TAPER) {
+            double w = pret[buf].w[ss][wc][bcol], gk = pret[buf].g[ss][wc][bcol];
+            const double hm1 = pret[buf].hm1[ss][bcol];
 #pragma unroll
-    for (int k = 0; k < KT64; ++k)
-      if (kbase + k < P.nchan) row[kbase + k] = make_double2(acc_re[k], acc_im[k]);
+            for (int k = 0; k < KT64; k += 2) {
+              if (k > 0) {
+                pr = fma(C, qr, -pr); pi = fma(C, qi, -pi);
+                qr = fma(C, pr, -qr); qi = fma(C, pi, -qi);
+              }
+              const double a0 = (double)arow[k] * w;
+              w *= gk; gk = fma(gk, hm1, gk);
+              const double a1 = (double)arow[k + 1] * w;
+              w *= gk; gk = fma(gk, hm1, gk);
+              acc_re[k] = fma(a0, pr, acc_re[k]); acc_im[k] = fma(a0, pi, acc_im[k]);
+              acc_re[k + 1] = fma(a1, qr, acc_re[k + 1]); acc_im[k + 1] = fma(a1, qi, acc_im[k + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < KT64; k += 2) {
+              if (k > 0) {
+                pr = fma(C, qr, -pr); pi = fma(C, qi, -pi);                       // z_k     (overwrites z_{k-2})
+                qr = fma(C, pr, -qr); qi = fma(C, pi, -qi);                       // z_{k+1} (overwrites z_{k-1})
+              }
+              const double a0 = (double)arow[k], a1 = (double)arow[k + 1];
+              acc_re[k] = fma(a0, pr, acc_re[k]); acc_im[k] = fma(a0, pi, acc_im[k]);
+              acc_re[k + 1] = fma(a1, qr, acc_re[k + 1]); acc_im[k + 1] = fma(a1, qi, acc_im[k + 1]);
+            }
+          }
+        }
+        __syncthreads();                               // sub-tile consumed, the next one's anchors visible
+      }
+      if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, st);
+    }
+    // partial sums of this segment -> scratch slot (k_skyvis_finalize adds head partials and transposes)
+    double2* base = P.accum + ((sg.slot * NWARPS + warp) * KT64) * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < KT64; ++k) base[k * 32] = make_double2(acc_re[k], acc_im[k]);
+    fill += (uint32_t)ntiles;
+    (void)kbase;
   }
 }
 
@@ -758,7 +898,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_3TERM_SCALAR)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PB_CUDA(ctx, cudaSetDevice(ctx->device));
+  PbDeviceGuard guard(ctx->device);
   if (nsrc == 0) {                                     // empty ROI: zeros (interferometry.py:6378-6382)
     PB_CUDA(ctx, cudaMemsetAsync(d_vis, 0, sizeof(double) * 2 * (size_t)nbl * nchan, stream));
     return PB200_OK;
@@ -766,9 +906,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
 
   // uniform channel grid?  (reference channels are f0 + k*df, run_prisim.py:900)
   const double df = nchan > 1 ? (h_freqs[nchan - 1] - h_freqs[0]) / (double)(nchan - 1) : 0.0;
-  bool uniform = true;
-  for (int k = 0; k < nchan; ++k)
-    if (fabs(h_freqs[k] - (h_freqs[0] + k * df)) > 1e-4) { uniform = false; break; }   // 1e-4 Hz * 1e-5 s = 1e-9 turn
+  const bool uniform = pb200_channels_uniform(h_freqs, nchan) != 0;
   const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64 ||
                          method == PB200_SKYVIS_RECURRENCE_LIFT || method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR);
   const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
@@ -778,68 +916,72 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   const int nslab = (nchan + PB200_SLAB - 1) / PB200_SLAB;
   const int nchan_pad = nslab * PB200_SLAB;
   const int nsrc_pad = pb200_nsrc_pad(nsrc);
-  void *geom, *dfreq;
+  void* geom;
   int rc = pb_scratch(ctx, 2, sizeof(double) * 4 * (size_t)nsrc_pad + 16, &geom);
   if (rc) return rc;
   unsigned* smax2_bits = reinterpret_cast<unsigned*>((double*)geom + 4 * (size_t)nsrc_pad);
   PB_CUDA(ctx, cudaMemsetAsync(smax2_bits, 0, 16, stream));
-  rc = pb_scratch(ctx, 3, sizeof(double) * (size_t)nchan_pad, &dfreq);
+  const double* dfreq;                                 // padded channel frequencies, resident per ctx (no copy, no sync after the first call)
+  rc = pb_channels_device(ctx, h_freqs, nchan, nchan_pad, stream, &dfreq);
   if (rc) return rc;
-  {
-    // padded channel frequencies (pinned staging is unnecessary: nchan doubles)
-    double* tmp = new double[nchan_pad];
-    for (int k = 0; k < nchan_pad; ++k) tmp[k] = h_freqs[k < nchan ? k : nchan - 1];
-    cudaError_t e = cudaMemcpyAsync(dfreq, tmp, sizeof(double) * nchan_pad, cudaMemcpyHostToDevice, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    delete[] tmp;
-    if (e != cudaSuccess) return pb_fail(ctx, PB200_ECUDA, "freq upload: %s", cudaGetErrorString(e));
-  }
   k_geom_stage<<<pb_div_up(nsrc_pad, 256), 256, 0, stream>>>(d_dircos, d_src_fwhm_deg, nsrc, nsrc_pad, (double*)geom,
                                                              h_pc[0], h_pc[1], h_pc[2], smax2_bits);
   PB_CHECK_LAUNCH(ctx, "k_geom_stage");
 
   SkyvisParams P;
-  P.amp = d_amp; P.geom = (const double*)geom; P.bl = d_bl; P.freqs = (const double*)dfreq; P.vis = (double*)d_vis;
+  P.amp = d_amp; P.geom = (const double*)geom; P.bl = d_bl; P.freqs = dfreq; P.vis = (double*)d_vis;
   P.pc[0] = h_pc[0]; P.pc[1] = h_pc[1]; P.pc[2] = h_pc[2];
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
   P.smax2_bits = smax2_bits;
   const int mode = method == PB200_SKYVIS_RECURRENCE_LIFT ? 1 : (method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ? 2 : 0);
-  if (method == PB200_SKYVIS_FP64) {
-    dim3 grid64(nslab, pb_div_up(nbl, BL64));
-#define LAUNCH64(AMP, TP)                                                                                     \
-  do {                                                                                                        \
-    const size_t smem = NSTAGE * (sizeof(TileIn64<AMP>) + sizeof(TilePre64)) + 64 + PB200_SLAB * sizeof(double); \
-    PB_CUDA(ctx, cudaFuncSetAttribute(k_skyvis_fp64<AMP, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_skyvis_fp64<AMP, TP><<<grid64, NTHREADS, smem, stream>>>(P);                                            \
-  } while (0)
-    const bool tp64 = d_src_fwhm_deg != nullptr;
-    if (amp_dtype == PB200_AMP_F64) { if (tp64) LAUNCH64(double, true); else LAUNCH64(double, false); }
-    else { if (tp64) LAUNCH64(float, true); else LAUNCH64(float, false); }
-#undef LAUNCH64
-    PB_CHECK_LAUNCH(ctx, "k_skyvis_fp64");
-    return PB200_OK;
-  }
-  // CTA shape: wide-channel CTAs when the slab count allows it, 1 slab otherwise
-  const char* spc_env = getenv("PB200_SKYVIS_SPC");
-  int spc = direct ? 1 : (nslab % 2 == 0 ? 2 : 1);   // measured on B200: 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4
-  if (!direct && spc_env) { int v = atoi(spc_env); if ((v == 1 || v == 2 || v == 4)) spc = v; }
-  P.spc = spc;
-  const int bl_per_cta = 32 * (NWARPS / (spc * WCS));
-  dim3 grid(pb_div_up(nslab, spc), pb_div_up(nbl, bl_per_cta));
-  const size_t ntile_out = (size_t)grid.x * grid.y * NWARPS;
-  void* accum;
-  rc = pb_scratch(ctx, 4, ntile_out * KT * 32 * sizeof(double2), &accum);
-  if (rc) return rc;
-  PB_CUDA(ctx, cudaMemsetAsync(accum, 0, ntile_out * KT * 32 * sizeof(double2), stream));
-  P.accum = (double2*)accum;
   const bool taper = d_src_fwhm_deg != nullptr;
-  const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR && method != PB200_SKYVIS_RECURRENCE_3TERM_SCALAR;
+
+  // CTA shape: fp64 kernel 1 slab x 64 baselines; direct kernel 1 slab x 128 baselines; recurrence kernel wide-channel
+  // CTAs when the slab count allows it (measured on B200: 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4 slabs)
+  const bool fp64 = method == PB200_SKYVIS_FP64;
+  int spc = (direct || fp64) ? 1 : (nslab % 2 == 0 ? 2 : 1);
+  if (!direct && !fp64 && (ctx->skyvis_spc_env == 1 || ctx->skyvis_spc_env == 2 || ctx->skyvis_spc_env == 4)) spc = ctx->skyvis_spc_env;
+  P.kt = fp64 ? KT64 : KT;
+  P.wc = fp64 ? WC64 : spc * WCS;
+  P.wb = NWARPS / P.wc;
+  const int bl_per_cta = 32 * P.wb;
+  // persistent schedule (struct Sched): one CTA per SM (every variant needs > half of an SM's shared memory or registers)
+  Sched& sc = P.sc;
+  sc.gx = pb_div_up(nslab, spc);
+  sc.ntile = sc.gx * pb_div_up(nbl, bl_per_cta);
+  sc.S = nsrc_pad / T;
+  const long long units = (long long)sc.ntile * sc.S;
+  sc.ncta = (int)(units < ctx->sm_count ? units : ctx->sm_count);
+  sc.nwave = sc.ntile / sc.ncta;
+  sc.ntail = sc.ntile % sc.ncta;
+  const size_t slot_bytes = (size_t)NWARPS * P.kt * 32 * sizeof(double2);
+  void* accum;
+  rc = pb_scratch(ctx, 4, ((size_t)sc.ntile + sc.ncta) * slot_bytes, &accum);
+  if (rc) return rc;
+  P.accum = (double2*)accum;
+  const dim3 grid(sc.ncta);
 #define LAUNCH(KERNEL, SMEM)                                                                              \
   do {                                                                                                    \
     PB_CUDA(ctx, cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
     KERNEL<<<grid, NTHREADS, (SMEM), stream>>>(P);                                                        \
   } while (0)
+  if (fp64) {
+#define SMEM64(AMP, TP) (NSTAGE * sizeof(TileIn64<AMP>) + 2 * sizeof(Pre64<Sub64<TP>::TS>) + (TP ? 2 * sizeof(Pre64Taper<Sub64<TP>::TS>) : 0) + 64)
+    if (amp_dtype == PB200_AMP_F64) {
+      if (taper) LAUNCH((k_skyvis_fp64<double, true>), SMEM64(double, true));
+      else LAUNCH((k_skyvis_fp64<double, false>), SMEM64(double, false));
+    } else {
+      if (taper) LAUNCH((k_skyvis_fp64<float, true>), SMEM64(float, true));
+      else LAUNCH((k_skyvis_fp64<float, false>), SMEM64(float, false));
+    }
+#undef SMEM64
+    PB_CHECK_LAUNCH(ctx, "k_skyvis_fp64");
+    k_skyvis_finalize<KT64><<<(unsigned)sc.ntile * NWARPS, 256, 0, stream>>>(P);
+    PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
+    return PB200_OK;
+  }
+  const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR && method != PB200_SKYVIS_RECURRENCE_3TERM_SCALAR;
 #define SMEM_REC(SPC) (NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) + \
                        (taper ? NSTAGE * sizeof(TileKap<SPC>) : 0))
 #define LAUNCH_REC(SPC)                                                                   \
@@ -872,7 +1014,16 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
 #undef SMEM_REC
 #undef LAUNCH
   PB_CHECK_LAUNCH(ctx, "k_skyvis");
-  k_skyvis_finalize<<<(unsigned)ntile_out, 256, 0, stream>>>(P, (int)grid.x);
+  k_skyvis_finalize<KT><<<(unsigned)sc.ntile * NWARPS, 256, 0, stream>>>(P);
   PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
   return PB200_OK;
+}
+
+// 1 when the channels are f0 + k df to within 1e-4 Hz (1e-4 Hz x 1e-5 s = 1e-9 turn): the recurrence kernels apply
+extern "C" int pb200_channels_uniform(const double* h_freqs, int nchan) {
+  if (!h_freqs || nchan <= 0) return 0;
+  const double df = nchan > 1 ? (h_freqs[nchan - 1] - h_freqs[0]) / (double)(nchan - 1) : 0.0;
+  for (int k = 0; k < nchan; ++k)
+    if (fabs(h_freqs[k] - (h_freqs[0] + k * df)) > 1e-4) return 0;
+  return 1;
 }

@@ -259,9 +259,17 @@ def phase_rotate(vis, baselines_dev, dpos_dircos, freqs_hz):
     device = vis.device.index
     ctx = get_context(device)
     nbl, nchan = vis.shape
-    ctx.check(ctx.lib.pb200_phase_rotate(ctx.handle, _ptr(vis), _ptr(baselines_dev), int(nbl), _ptr(_h64(dpos_dircos)),
-                                         _ptr(_h64(freqs_hz)), int(nchan), ctx.stream()))
+    dpos, freqs = _h64(dpos_dircos), _h64(freqs_hz)      # keep the converted host arrays alive across the call
+    ctx.check(ctx.lib.pb200_phase_rotate(ctx.handle, _ptr(vis), _ptr(baselines_dev), int(nbl), _ptr(dpos),
+                                         _ptr(freqs), int(nchan), ctx.stream()))
     return vis
+
+
+def channels_uniform(freqs_hz):
+    """``pb200_channels_uniform``: the library's own test for a uniformly spaced channel grid (the recurrence and
+    fp64 kernels need one)."""
+    freqs = _h64(freqs_hz)
+    return bool(_lib.load().pb200_channels_uniform(_ptr(freqs), int(freqs.size)))
 
 
 def microbench(device=None):

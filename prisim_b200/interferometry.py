@@ -18,6 +18,7 @@ Deliberate deviations from the reference (documented in DESIGN.md):
 """
 from __future__ import annotations
 
+import os
 import warnings
 
 import numpy as NP
@@ -63,6 +64,25 @@ def _noise_input(name, val, nbl, nchan, ntimes):
     return arr
 
 
+def fresh_noise_seed():
+    """A 63-bit seed from the operating system: the default of ``InterferometerArray(noise_seed=None)`` and
+    ``generateNoise(seed=None)``, so that separate objects / calls draw independent noise as the reference's
+    ``NP.random.randn`` does (interferometry.py:6693, :329).  Pass an explicit seed for reproducible or sharded runs."""
+    return int.from_bytes(os.urandom(8), "little") >> 1
+
+
+def _realisation_seed(seed, realisation):
+    """Philox key of the `realisation`-th noise draw of one object: the seed itself for the first draw, a splitmix64
+    hash of (seed, realisation) afterwards -- repeated ``generate_noise()`` calls give fresh, reproducible noise."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    if realisation == 0:
+        return seed
+    z = (seed + 0x9E3779B97F4A7C15 * int(realisation)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
 def thermalNoiseRMS(A_eff, df, dt, Tsys, nbl=1, nchan=1, ntimes=1, flux_unit="Jy", eff_Q=1.0):
     """Thermal-noise rms of a complex visibility, same call as interferometry.py:89-230: 2 k Tsys / (A_eff eff_Q sqrt(df dt))
     in Jy, or Tsys / (eff_Q sqrt(df dt)) in K; inputs are scalars or arrays broadcastable to (nbl, nchan, ntimes)."""
@@ -88,9 +108,12 @@ def thermalNoiseRMS(A_eff, df, dt, Tsys, nbl=1, nchan=1, ntimes=1, flux_unit="Jy
 
 
 def generateNoise(noiseRMS=None, A_eff=None, df=None, dt=None, Tsys=None, nbl=1, nchan=1, ntimes=1, flux_unit="Jy", eff_Q=1.0,
-                  seed=0, device=None):
+                  seed=None, device=None):
     """Complex thermal noise rms/sqrt(2) (N + iN) of shape (nbl, nchan, ntimes), same call as interferometry.py:236-329
-    plus `seed` / `device`: the deviates come from the device Philox generator (``pb200_noise``), one launch per time."""
+    plus `seed` / `device`: the deviates come from the device Philox generator (``pb200_noise``), one launch per time.
+    seed=None draws a fresh seed per call (independent realisations, like the reference's NP.random.randn)."""
+    if seed is None:
+        seed = fresh_noise_seed()
     if noiseRMS is None:
         noiseRMS = thermalNoiseRMS(A_eff, df, dt, Tsys, nbl=nbl, nchan=nchan, ntimes=ntimes, flux_unit=flux_unit, eff_Q=eff_Q)
     else:
@@ -436,7 +459,7 @@ class InterferometerArray(object):
     def __init__(self, labels, baselines, channels, telescope=None, eff_Q=0.89, latitude=34.0790, longitude=0.0,
                  altitude=0.0, skycoords="radec", A_eff=NP.pi * (25.0 / 2) ** 2, pointing_coords="hadec", layout=None,
                  blgroupinfo=None, baseline_coords="localenu", freq_scale=None, gaininfo=None, init_file=None,
-                 simparms_file=None, device=None, bl_offset=0, nbl_total=None, noise_seed=0):
+                 simparms_file=None, device=None, bl_offset=0, nbl_total=None, noise_seed=None):
         if init_file is not None:
             raise NotImplementedError("loading saved simulations is outside the hot-path scope (SURVEY.md section 8f)")
         if gaininfo is not None:
@@ -536,7 +559,12 @@ class InterferometerArray(object):
         self.device = engine._dev(device)
         self.bl_offset = int(bl_offset)                  # position of this shard in the full baseline list
         self.nbl_total = nbl if nbl_total is None else int(nbl_total)
-        self.noise_seed = int(noise_seed)
+        # None: a fresh seed per object (recorded here), so that separate arrays (sub-bands, polarisations, Monte-Carlo
+        # repeats) draw independent noise like the reference's global numpy generator; pass a seed for reproducible or
+        # baseline-sharded runs (sharding.make_sharded_array shares rank 0's).  Every generate_noise() call advances
+        # a realisation counter folded into the Philox key.
+        self.noise_seed = fresh_noise_seed() if noise_seed is None else int(noise_seed)
+        self._noise_realisation = 0
         # 'fp32': fp32 phasors/amplitudes everywhere (fastest); 'fp64': fp64 kernel + fp64 amplitude table;
         # 'auto': fp32 first; every baseline whose visibilities are a strongly cancelling sum
         # (rms_b < cancel_ratio * incoherent norm) is recomputed by the fp64 kernel, and a sample of the
@@ -562,6 +590,9 @@ class InterferometerArray(object):
         self._lag = {}                                   # product name -> list of [nbl,nout] tensors
         self._d_aeff = None
         self._d_effq = None
+        # [nbl, nchan] complex128 CUDA tensor the NEXT observe() writes its visibilities into (consumed by that call).
+        # sharding.ShardedObserver points it at this rank's rows of the writing rank's buffer (NVLink peer memory).
+        self.next_skyvis_out = None
 
     # ------------------------------------------------------------------ helpers
     def _dev_str(self):
@@ -615,7 +646,8 @@ class InterferometerArray(object):
             return NP.ones((self.baselines.shape[0], self.channels.size))
         if self._bp_wts is None:
             return NP.ones((self.baselines.shape[0], self.channels.size, len(self._bp)))
-        return self._stack([self._bp_wts(t) for t in range(len(self._bp))], expand=True)
+        base = getattr(self, "_drained", 0)
+        return self._stack([self._bp_wts(base + t) for t in range(len(self._bp))], expand=True)
 
     @property
     def Tsys(self):
@@ -780,10 +812,10 @@ class InterferometerArray(object):
             Tsys = NP.asarray(Tsys, dtype=NP.float64)
             if NP.any(Tsys < 0.0):
                 raise ValueError("Tsys should be non-negative.")
-            if Tsys.size == nchan:
-                Tsys_t = engine._f64(Tsys.ravel(), self.device)
-            elif Tsys.size == nbl:
+            if Tsys.size == nbl:                                                       # the reference tests nbl first (:6068)
                 Tsys_t = self._compact(NP.repeat(Tsys.reshape(-1, 1), nchan, axis=1))
+            elif Tsys.size == nchan:
+                Tsys_t = engine._f64(Tsys.ravel(), self.device)
             elif Tsys.size == nbl * nchan:
                 Tsys_t = self._compact(Tsys.reshape(-1, nchan))
             else:
@@ -882,7 +914,8 @@ class InterferometerArray(object):
             self.obs_catalog_indices = self.obs_catalog_indices + [index.cpu().numpy().astype(NP.int64)]   # :6377
         else:                                                                          # :6378-6382
             warnings.warn("No sources found in the catalog within matching radius. Simply populating the observed visibilities and/or gradients with noise.")
-            skyvis = torch.zeros((nbl, nchan), dtype=torch.complex128, device=self._dev_str())
+            out, self.next_skyvis_out = self.next_skyvis_out, None
+            skyvis = out.zero_() if out is not None else torch.zeros((nbl, nchan), dtype=torch.complex128, device=self._dev_str())
             grad = torch.zeros((3, nbl, nchan), dtype=torch.complex128, device=self._dev_str()) if gradient_mode is not None else None
 
         # bookkeeping (:6103-6108, :6384-6399)
@@ -912,22 +945,28 @@ class InterferometerArray(object):
         for point-source skies.  Each gradient component goes through the same precision control as V."""
         nbl, nchan = self.baselines.shape[0], self.channels.size
         kw = dict(pbeam=pbeam, device=self.device)
-        uniform = nchan < 3 or NP.allclose(NP.diff(self.channels), self.freq_resolution, rtol=0, atol=1e-4)
+        uniform = engine.channels_uniform(self.channels)      # the library's own criterion (pb200_channels_uniform)
+        if self.precision == "fp64" and not uniform:
+            raise ValueError("precision='fp64' needs uniformly spaced channels (the fp64 kernel is a channel recurrence); "
+                             "this channel grid takes the direct fp32 kernel -- use precision='fp32' or 'auto'")
 
-        def run64(bl, amp64=None):
+        def run64(bl, amp64=None, out=None):
             if amp64 is None:
                 amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
             return engine.skyvis(dircos, amp64, nsrc, bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, method="fp64",
-                                 device=self.device)
+                                 device=self.device, out=out)
 
         def scaled(amp_any, i):
             return engine.amp_scale(amp_any, nsrc, nchan, dircos, i, device=self.device)
 
+        out, self.next_skyvis_out = self.next_skyvis_out, None
+        if out is not None and (tuple(out.shape) != (nbl, nchan) or out.dtype != torch.complex128 or not out.is_contiguous()):
+            raise ValueError("next_skyvis_out must be a contiguous [nbl, nchan] complex128 CUDA tensor")
         if uniform and (self.precision == "fp64" or (self.precision == "auto" and self._fp64_sticky)):
             self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl, "audited": 0, "audit_max_err": 0.0})
             amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
             grad = torch.stack([run64(self._d_bl, scaled(amp64, i)) for i in range(3)]) if gradient else None
-            return run64(self._d_bl, amp64), grad
+            return run64(self._d_bl, amp64, out=out), grad
         amp = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, **kw)
         amp64_cache = {}
 
@@ -936,10 +975,10 @@ class InterferometerArray(object):
                 amp64_cache["t"] = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
             return amp64_cache["t"]
 
-        def certified(amp32, amp64_fn, report):
+        def certified(amp32, amp64_fn, report, out=None):
             """fp32 phase sum of one amplitude table + the 'auto' cancellation test and fp64 audit."""
             skyvis = engine.skyvis(dircos, amp32, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device,
-                                   method=self.skyvis_method)
+                                   method=self.skyvis_method, out=out)
             if not (self.precision == "auto" and uniform):
                 return skyvis
             # (1) cancellation test.  The fp32 kernel's absolute error on incoherent (point-source) skies is
@@ -978,7 +1017,7 @@ class InterferometerArray(object):
                 self._fp64_sticky = nflag > 0.5 * nbl
             return skyvis
 
-        skyvis = certified(amp, amp64_table, True)
+        skyvis = certified(amp, amp64_table, True, out=out)
         grad = None
         if gradient:      # every component is certified like V itself (the l and m weights change sign over the sky: they cancel more)
             grad = torch.stack([certified(scaled(amp, i), lambda i=i: scaled(amp64_table(), i), False) for i in range(3)])
@@ -1084,9 +1123,11 @@ class InterferometerArray(object):
         nbl, nchan = self.baselines.shape[0], self.channels.size
         self._rms, self._noise = [], []
         base = getattr(self, "_drained", 0)
+        seed = _realisation_seed(self.noise_seed, self._noise_realisation)        # a new realisation on every call (:6693)
+        self._noise_realisation += 1
         for t in range(len(self._skyvis)):
             rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
-                                      self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
+                                      seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
                                       nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
                                       want=("rms", "noise"), device=self.device)
             self._rms.append(rms)
@@ -1135,9 +1176,10 @@ class InterferometerArray(object):
         self.lags = NP.fft.fftshift(NP.fft.fftfreq(nchan, d=self.freq_resolution))    # :8114
         products = {"skyvis": self._skyvis, "vis": self._vis, "noise": self._noise}
         self._lag = {"skyvis": [], "vis": [], "noise": [], "kernel": []}
+        base = getattr(self, "_drained", 0)
         for t in range(len(self._skyvis)):
             bp = self._bp[t]
-            wts = None if self._bp_wts is None else self._bp_wts(t)
+            wts = None if self._bp_wts is None else self._bp_wts(base + t)
             for name, lst in products.items():
                 if lst:
                     self._lag[name].append(engine.delay_transform(lst[t], bp, wts, self.freq_resolution, pad=pad,
@@ -1326,7 +1368,7 @@ class InterferometerArray(object):
                 prod.update(vis_rms_freq=rms, vis_noise_freq=nz, vis_freq=engine.add_noise(self._skyvis[t], nz))
             if delay_transform is not None:
                 pad = delay_transform.get("pad", 1.0)
-                wts = None if getter is None else getter(t)
+                wts = None if getter is None else getter(base + t)          # per-snapshot weights are indexed by the global snapshot
                 for key in [k for k in ("skyvis_freq", "vis_freq", "vis_noise_freq") if k in prod]:
                     prod[key.replace("_freq", "_lag")] = engine.delay_transform(prod[key], self._bp[t], wts, self.freq_resolution,
                                                                                pad=pad, downsample=True)
@@ -1393,10 +1435,11 @@ class InterferometerArray(object):
                 hadec = phase_center.copy() if coords_new == "hadec" else NP.stack((lst - phase_center[:, 0], phase_center[:, 1]), axis=1)
             stored = hadec if cur == "hadec" else NP.stack((lst - hadec[:, 0], hadec[:, 1]), axis=1)
         pos_diff = cur_dircos - new_dircos                                                  # :7866
-        for t in range(nsnap):
+        base = getattr(self, "_drained", 0)                 # snapshots already streamed out by drain() are not resident
+        for t in range(len(self._skyvis)):
             for lst_t in (self._skyvis, self._vis, self._noise):                            # :7871-7881
                 if lst_t:
-                    engine.phase_rotate(lst_t[t], self._d_bl, pos_diff[t], self.channels)
+                    engine.phase_rotate(lst_t[t], self._d_bl, pos_diff[base + t], self.channels)
         self.phase_center = stored
         if do_delay_transform:
             self.delay_transform(verbose=verbose)

@@ -70,6 +70,12 @@ def make_sharded_array(cls, labels, baselines, channels, rank=None, world_size=N
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_initialized() else 1
     baselines = NP.asarray(baselines)
+    if kwargs.get("noise_seed", None) is None and dist.is_initialized() and world_size > 1:
+        # one noise seed for the whole run: rank 0 draws it, every shard uses it with its global baseline offset
+        from .interferometry import fresh_noise_seed
+        box = [fresh_noise_seed() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        kwargs["noise_seed"] = box[0]
     sl = shard_slice(baselines.shape[0], world_size, rank)
     labels = NP.asarray(labels)[sl] if not isinstance(labels, list) else labels[sl]
     return cls(labels, baselines[sl], channels, bl_offset=sl.start, nbl_total=baselines.shape[0], **kwargs)
@@ -83,25 +89,39 @@ class _RawCudaBuffer(object):
 
 
 class PeerGatherBuffer(object):
-    """Gather through peer memory: rank `dst` owns a [world, *shape] complex128 buffer; every other rank maps it over
-    NVLink (CUDA IPC) and lets its kernels write the result slice directly (pass ``local`` as ``out=`` to
-    ``engine.skyvis``).  ``wait()`` = stream sync + barrier; afterwards ``full`` on `dst` holds all slices.
-    Falls back to an NCCL point-to-point gather when peer mapping is unavailable (``mode == 'nccl'``)."""
+    """Gather through peer memory: rank `dst` owns the output buffer; every other rank maps it over NVLink (CUDA IPC)
+    and lets its kernels write the result slice directly (pass ``local`` as ``out=`` to ``engine.skyvis``).
+    ``wait()`` = stream sync + barrier; afterwards ``full`` on `dst` holds all slices.
 
-    def __init__(self, shape, device, dst=0, group=None):
+      * ``row_bounds=None`` (snapshot sharding): the buffer is [world, *shape], rank r owns ``full[r]``;
+      * ``row_bounds=shard_bounds(nbl, world)`` (baseline sharding, the reference's pp.key='bl' mode): the buffer
+        is ``shape`` = [nbl, ...] itself and rank r owns rows row_bounds[r]:row_bounds[r+1] -- rank `dst` ends up
+        with exactly the array an unsharded run would have produced, with no concatenation step
+        (scripts/run_prisim.py:2233-2242).
+
+    Falls back to an NCCL point-to-point gather when peer mapping is unavailable (``mode == 'nccl'``;
+    ``force_nccl=True`` selects it for A/B tests)."""
+
+    def __init__(self, shape, device, dst=0, group=None, row_bounds=None, force_nccl=False):
         import ctypes as C
         from . import _lib
         self.group, self.dst, self.shape = group, dst, tuple(shape)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.device = int(device)
         self.ctx = _lib.get_context(self.device)
+        self.bounds = None if row_bounds is None else [int(b) for b in row_bounds]
         dev = "cuda:{0}".format(self.device)
         nel = int(NP.prod(self.shape))
+        row_el = nel // self.shape[0] if self.shape[0] else 0
+        full_shape = (self.world,) + self.shape if self.bounds is None else self.shape
+        full_el = int(NP.prod(full_shape))
         self._base = C.c_void_p()
         self._mapped = False
+        self._owned = False
         handle = torch.zeros(65, dtype=torch.uint8, device=dev)               # 64-byte handle + ok flag
-        if self.rank == dst:
-            ok = self.ctx.lib.pb200_device_alloc(self.ctx.handle, nel * 16 * self.world, C.byref(self._base)) == 0
+        if self.rank == dst and not force_nccl:
+            ok = self.ctx.lib.pb200_device_alloc(self.ctx.handle, max(full_el, 1) * 16, C.byref(self._base)) == 0
+            self._owned = ok
             hb = (C.c_ubyte * 64)()
             ok = ok and self.ctx.lib.pb200_peer_export(self.ctx.handle, self._base, hb) == 0
             handle[:64] = torch.tensor(list(hb), dtype=torch.uint8)
@@ -115,23 +135,45 @@ class PeerGatherBuffer(object):
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         self.mode = "peer" if bool(flag.item()) else "nccl"
+        if self.bounds is None:
+            lo, n_local = self.rank * nel, nel
+            local_shape = self.shape
+        else:
+            lo, n_local = self.bounds[self.rank] * row_el, (self.bounds[self.rank + 1] - self.bounds[self.rank]) * row_el
+            local_shape = (self.bounds[self.rank + 1] - self.bounds[self.rank],) + self.shape[1:]
         if self.mode == "peer":
             base = self._base.value
-            self.local = torch.as_tensor(_RawCudaBuffer(base + self.rank * nel * 16, self.shape, "<c16"), device=dev)
-            self.full = (torch.as_tensor(_RawCudaBuffer(base, (self.world,) + self.shape, "<c16"), device=dev)
-                         if self.rank == dst else None)
+            if n_local > 0:
+                self.local = torch.as_tensor(_RawCudaBuffer(base + lo * 16, local_shape, "<c16"), device=dev)
+            else:
+                self.local = torch.empty(local_shape, dtype=torch.complex128, device=dev)
+            self.full = torch.as_tensor(_RawCudaBuffer(base, full_shape, "<c16"), device=dev) if self.rank == dst else None
         else:
-            self.full = torch.empty((self.world,) + self.shape, dtype=torch.complex128, device=dev) if self.rank == dst else None
-            self.local = self.full[dst] if self.rank == dst else torch.empty(self.shape, dtype=torch.complex128, device=dev)
+            if self._owned:                                  # exported but somebody could not map it
+                self.ctx.lib.pb200_device_free(self.ctx.handle, self._base)
+                self._owned = False
+            elif self._mapped:
+                self.ctx.lib.pb200_peer_close(self.ctx.handle, self._base)
+                self._mapped = False
+            self._base.value = None
+            self.full = torch.empty(full_shape, dtype=torch.complex128, device=dev) if self.rank == dst else None
+            if self.rank == dst:
+                self.local = self.full[dst] if self.bounds is None else self.full[self.bounds[dst]:self.bounds[dst + 1]]
+            else:
+                self.local = torch.empty(local_shape, dtype=torch.complex128, device=dev)
+
+    def _slice_of(self, r):
+        return self.full[r] if self.bounds is None else self.full[self.bounds[r]:self.bounds[r + 1]]
 
     def wait(self):
         """Make every rank's slice visible on `dst` (peer mode: stores are complete when the writers' streams are;
         nccl mode: one batched point-to-point gather)."""
         if self.mode == "nccl":
             if self.rank == self.dst:
-                ops = [dist.P2POp(dist.irecv, self.full[r], r, group=self.group) for r in range(self.world) if r != self.dst]
+                ops = [dist.P2POp(dist.irecv, self._slice_of(r), r, group=self.group) for r in range(self.world)
+                       if r != self.dst and self._slice_of(r).numel() > 0]
             else:
-                ops = [dist.P2POp(dist.isend, self.local, self.dst, group=self.group)]
+                ops = [dist.P2POp(dist.isend, self.local, self.dst, group=self.group)] if self.local.numel() > 0 else []
             for req in (dist.batch_isend_irecv(ops) if ops else []):
                 req.wait()
         torch.cuda.synchronize(self.device)
@@ -147,3 +189,43 @@ class PeerGatherBuffer(object):
             elif self._mapped:
                 self.ctx.lib.pb200_peer_close(self.ctx.handle, self._base)
             self._base.value = None
+
+
+class ShardedObserver(object):
+    """One snapshot at a time over all ranks, sharded over baselines (the reference's ``pp.key='bl'`` equal-volume
+    mode, scripts/run_prisim.py:1775-1791 / :2165-2209) with the concatenation on the writing rank
+    (:2233-2242) fused into the kernel epilogue: every rank owns an ``InterferometerArray`` over its contiguous
+    baseline block whose phase-sum kernel stores straight into rank `dst`'s [nbl_total, nchan] buffer.
+
+        so = ShardedObserver(InterferometerArray, labels, baselines, channels, device=local_rank, ...)
+        full = so.observe(timeobj, Tsysinfo, bandpass, pointing, skymodel, t_acc)    # rank dst: [nbl_total, nchan] CUDA tensor
+
+    ``observe`` returns the gathered snapshot on `dst` (a view of the gather buffer, valid until the next call) and
+    None elsewhere; ``so.ia`` is the rank-local array (noise / delay transforms stay local: channels are unsplit)."""
+
+    def __init__(self, cls, labels, baselines, channels, dst=0, group=None, force_nccl=False, **kwargs):
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dst = dst
+        baselines = NP.asarray(baselines)
+        self.nbl_total = baselines.shape[0]
+        self.bounds = shard_bounds(self.nbl_total, self.world)
+        self.ia = make_sharded_array(cls, labels, baselines, channels, rank=self.rank, world_size=self.world, **kwargs)
+        self.gbuf = None
+        if self.world > 1:
+            self.gbuf = PeerGatherBuffer((self.nbl_total, self.ia.channels.size), self.ia.device, dst=dst, group=group,
+                                         row_bounds=self.bounds, force_nccl=force_nccl)
+
+    def observe(self, *args, **kwargs):
+        if self.gbuf is None:
+            self.ia.observe(*args, **kwargs)
+            return self.ia.skyvis_freq_device(-1)
+        self.ia.next_skyvis_out = self.gbuf.local            # the kernel epilogue writes into the writing rank's buffer
+        self.ia.observe(*args, **kwargs)
+        self.gbuf.wait()
+        return self.gbuf.full if self.rank == self.dst else None
+
+    def close(self):
+        if self.gbuf is not None:
+            self.gbuf.close()
+            self.gbuf = None

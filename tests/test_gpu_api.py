@@ -626,6 +626,19 @@ def test_config4_full_size_mwa_tile_subset_parity():
     Vg = V[torch.as_tensor(bsel).cuda()][:, torch.as_tensor(csel).cuda()].cpu().numpy()
     rms_b = V[torch.as_tensor(bsel).cuda()].abs().pow(2).mean(dim=1, keepdim=True).sqrt().cpu().numpy()
     assert float((NP.abs(Vg - Vo) / rms_b).max()) <= TOL
+    # every one of the 8,128 x 768 cells: the raw fp32 kernel against the fp64 kernel
+    out = {}
+    for prec in ("fp32", "fp64"):
+        ib = InterferometerArray(cfg["labels"], cfg["baselines"], cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
+                                 skycoords="radec", pointing_coords="altaz", device=0)
+        ib.precision = prec
+        ib.observe(SimpleTime(2451545.0, 50.0), {"Tnet": 200.0}, NP.ones(768), cfg["pointing_altaz"], cfg["skymodel"], cfg["t_acc"], pb_info=cfg["pb_info"])
+        out[prec] = ib.skyvis_freq_device(0)
+    rms_all = out["fp64"].abs().pow(2).mean(dim=1, keepdim=True).sqrt()
+    worst = float(((out["fp32"] - out["fp64"]).abs() / rms_all).max().item())
+    print("config 4, all 8128 x 768 cells: max |dV|/rms_b = {0:.3e}".format(worst))
+    assert worst <= TOL
+    assert float(((V - out["fp64"]).abs() / rms_all).max().item()) <= TOL       # and what precision='auto' returned
 
 
 def test_config5_pipeline_three_snapshots():
