@@ -349,13 +349,20 @@ def run_config2(env, pipeline=False):
         df = float(cfg["channels"][1] - cfg["channels"][0])
         tail_events = []
 
-    def step(timed):
+    def tables():
+        """cull + brightest-first order + amplitude table, as InterferometerArray.observe does them"""
         dircos, index = engine.sky_cull(d_hadec, "hadec", latitude_deg=cfg["latitude"], device=lr)
         nsrc = int(index.shape[0])
+        perm, nbright = engine.brightness_order(dircos, index, nsrc, spec, beam, cfg["channels"], device=lr)
+        dircos, index = dircos.index_select(0, perm).contiguous(), index.index_select(0, perm).contiguous()
+        return dircos, index, nsrc, nbright
+
+    def step(timed):
+        dircos, index, nsrc, nbright = tables()
         amp = engine.amp_table(dircos, index, nsrc, spec, beam, cfg["channels"], device=lr)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], out=vis, device=lr)
+        engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], out=vis, device=lr, nsrc_bright=nbright)
         e1.record()
         if timed:
             k1_events.append((e0, e1))
@@ -385,10 +392,10 @@ def run_config2(env, pipeline=False):
 
     # ---- correctness of what rank 0 holds (after the timed loop, same inputs) ----
     check = {"ranks": world}
-    dircos, index = engine.sky_cull(d_hadec, "hadec", latitude_deg=cfg["latitude"], device=lr)
+    dircos, index, nsrc, nbright = tables()
     amp = engine.amp_table(dircos, index, nsrc, spec, beam, cfg["channels"], device=lr)
-    private = engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], device=lr)
-    engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], out=vis, device=lr)
+    private = engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], device=lr, nsrc_bright=nbright)
+    engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], out=vis, device=lr, nsrc_bright=nbright)
     if gbuf is not None:
         gbuf.wait()
     mine = torch.tensor([bit_checksum(private)], dtype=torch.int64, device=dev)
@@ -497,7 +504,8 @@ def run_config2(env, pipeline=False):
                            "schedule": "persistent CTAs (1 per SM): whole output tiles in lock-step waves + stream-K split of the tail tiles along the source axis",
                            "l2": "inputs larger than L2: amplitude table {0:.2f} GB + {1:.2f} GB output per step and GPU".format(
                                nsrc * nchan * 4 / 1e9, nbl_local * nchan * 16 / 1e9),
-                           "phase_arith": "fp64 anchors, fp32 rotation recurrence, fp32 accumulate flushed to fp64"},
+                           "phase_arith": "fp64-reduced MUFU anchors for both channels of a pair, fp32 rotation recurrence by r^2, fp32 accumulate flushed to fp64 "
+                                          "every 256 sources (every 32 for the brightest, which are summed first)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "gather_check": check}
         env.emit(line)

@@ -166,6 +166,11 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
  *   h_freqs    [nchan] Hz (host).  Uniformly spaced channels take the recurrence kernel;
  *              anything else takes the direct (sincospi per term) kernel.
  *   d_src_fwhm_deg  NULL, or [nsrc] sqrt(major*minor) FWHM in degrees (:6267) -> taper on
+ *   nsrc_bright  0, or: the caller has ordered the sources (d_dircos, amplitude-table rows, d_src_fwhm_deg) so
+ *              that the first nsrc_bright are the brightest; their fp32 partial sums are then moved to the fp64
+ *              running sums after every 32-source tile instead of every 512 sources, so that the handful of
+ *              sources that carry most of sum a^2 do not set the rounding unit of everybody else's additions.
+ *              The sum itself does not depend on the order.
  *   d_vis      [nbl,nchan] complex128, overwritten
  *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM
  */
@@ -181,7 +186,7 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
 #define PB200_SKYVIS_RECURRENCE_3TERM_SCALAR 7   /* the same with scalar FFMA (A/B) */
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
-                 const double* d_src_fwhm_deg, void* d_vis, int method, void* stream);
+                 const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, int method, void* stream);
 /* 1 when h_freqs is f0 + k df to within 1e-4 Hz -- the test pb200_skyvis applies before it takes a recurrence
  * (or the fp64) kernel; the host shim uses the same test to decide whether precision control applies.        */
 int pb200_channels_uniform(const double* h_freqs, int nchan);

