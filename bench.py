@@ -312,7 +312,7 @@ def run_config2(env, pipeline=False):
     from prisim_b200 import primary_beams as PB
     from prisim_b200 import synthetic as S
     from prisim_b200.interferometry import InterferometerArray, SimpleTime
-    from prisim_b200.sharding import PeerGatherBuffer, ShardedObserver, shard_bounds
+    from prisim_b200.sharding import PeerGatherBuffer, ShardedObserver, shard_rows
     world, rank, lr, dev = env.world, env.rank, env.local_rank, env.dev
     strong = args.scaling in ("auto", "strong")
 
@@ -321,9 +321,10 @@ def run_config2(env, pipeline=False):
     sp = sky.spec_parms
     nbl, nchan = cfg["baselines"].shape[0], cfg["channels"].size
     lst_deg = 0.0 if strong else 0.0 + 15.0 * rank / 8.0       # weak: every rank observes its own snapshot
-    bounds = shard_bounds(nbl, world) if strong else None
-    sl = slice(int(bounds[rank]), int(bounds[rank + 1])) if strong else slice(0, nbl)
-    nbl_local = sl.stop - sl.start
+    # strong scaling: rank r owns baselines r, r + world, ... (interleaved: the short, strongly cancelling baselines that the
+    # precision control recomputes in fp64 sit at the front of PRISim's length-sorted list and would all land on rank 0)
+    sl = shard_rows(nbl, world, rank, interleave=True) if strong else slice(0, nbl)
+    nbl_local = len(range(*sl.indices(nbl)))
 
     # ---- resident inputs ----
     d_hadec = engine._f64(NP.stack((lst_deg - sky.location[:, 0], sky.location[:, 1]), axis=1), lr)
@@ -336,7 +337,7 @@ def run_config2(env, pipeline=False):
     # peer memory (sharding.PeerGatherBuffer); NCCL point-to-point is the fallback if mapping fails
     gbuf = None
     if world > 1:
-        gbuf = PeerGatherBuffer((nbl, nchan), lr, dst=0, row_bounds=bounds) if strong else PeerGatherBuffer((nbl, nchan), lr, dst=0)
+        gbuf = PeerGatherBuffer((nbl, nchan), lr, dst=0, interleave=True) if strong else PeerGatherBuffer((nbl, nchan), lr, dst=0)
     vis = gbuf.local if gbuf is not None else torch.empty((nbl, nchan), dtype=torch.complex128, device=dev)
     k1_events = []
     window = None
@@ -369,9 +370,10 @@ def run_config2(env, pipeline=False):
         if pipeline:       # the rank-0 tail of run_prisim.py:2278-2284 on this rank's rows: noise, add, three delay transforms
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record()
-            _, nz, v = engine.noise(vis, tsys, aeff, effq, df, cfg["t_acc"], 5, nbl_local, nchan, snapshot=0, bl_offset=sl.start,
-                                    nbl_total=nbl, want=("noise", "vis"), device=lr)
-            for x in (vis, v, nz):
+            sky_local = vis if vis.is_contiguous() else vis.contiguous()
+            _, nz, v = engine.noise(sky_local, tsys, aeff, effq, df, cfg["t_acc"], 5, nbl_local, nchan, snapshot=0, bl_offset=sl.start or 0,
+                                    bl_step=sl.step or 1, nbl_total=nbl, want=("noise", "vis"), device=lr)
+            for x in (sky_local, v, nz):
                 engine.delay_transform(x, bp, window, df, pad=1.0, downsample=True)
             e3.record()
             if timed:
@@ -407,7 +409,7 @@ def run_config2(env, pipeline=False):
     if rank == 0:
         full = gbuf.full if gbuf is not None else vis
         if strong:
-            got = [bit_checksum(full[int(bounds[r]):int(bounds[r + 1])]) for r in range(world)]
+            got = [bit_checksum(full[r::world]) for r in range(world)]
         else:
             got = [bit_checksum(full[r]) for r in range(world)] if world > 1 else [bit_checksum(full)]
         check["checksums_equal"] = [int(s.item()) == g for s, g in zip(sums, got)]
@@ -473,7 +475,7 @@ def run_config2(env, pipeline=False):
         d2h_all, = env.reduce([float(d2h)], "SUM")
         e2e = {"value": terms_step / (e2e_ms * 1e-3) / 1e9, "unit": "Gterms/s", "h2d_bytes_per_step": int(h2d) * (world if strong else 1),
                "d2h_bytes_per_step": int(d2h_all if strong else d2h), "ms_per_step": e2e_ms,
-               "api": ("sharding.ShardedObserver.observe (baseline blocks, kernel epilogue stores into rank 0's buffer) + ONE device->host copy of "
+               "api": ("sharding.ShardedObserver.observe (interleaved baseline shards, kernel epilogue stores into rank 0's buffer) + ONE device->host copy of "
                        "the gathered skyvis_freq from rank 0 (pinned)" if strong and world > 1 else
                        "InterferometerArray.observe + device->host copy of skyvis_freq (pinned)") +
                       "; precision='auto': fp32 kernel + fp64 recompute of cancelling baselines + sampled fp64 audit" +
@@ -494,7 +496,7 @@ def run_config2(env, pipeline=False):
                                 "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / roofline["hbm_gbs_measured"] if roofline["hbm_gbs_measured"] else None}
         cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, terms_step)
         mode = ("single GPU" if world == 1 else
-                ("baseline blocks of ONE snapshot, " if strong else "one snapshot per GPU, ") +
+                ("interleaved baseline shards of ONE snapshot, " if strong else "one snapshot per GPU, ") +
                 ("kernel epilogue stores over NVLink peer memory into rank 0's buffer" if gbuf.mode == "peer" else "NCCL point-to-point gather to rank 0"))
         line = {"metric": METRIC, "value": value, "unit": "Gterms/s", "n_gpus": world, "steps": args.steps, "warmup": env.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -523,7 +525,7 @@ def run_config3(env):
     from prisim_b200 import synthetic as S
     from prisim_b200.interferometry import InterferometerArray, SimpleTime
     world, rank, lr, dev = env.world, env.rank, env.local_rank, env.dev
-    cfg = S.config3(nsnap=1)
+    cfg = S.config3(nside=args.nside, nsnap=1)
     sky = cfg["skymodel"]
     sp = sky.spec_parms
     nbl, nchan = cfg["baselines"].shape[0], cfg["channels"].size
@@ -623,6 +625,7 @@ def main():
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
                     help="configs 2/5 at N>1: strong (default) = baseline blocks of one snapshot; weak = one snapshot per rank")
     ap.add_argument("--nsrc", type=int, default=300000, help="catalogue size (default = the headline 300k)")
+    ap.add_argument("--nside", type=int, default=256, help="config 3: HEALPix nside of the diffuse sky (default = the configuration's 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

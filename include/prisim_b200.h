@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PB200_VERSION 100
+#define PB200_VERSION 200
 
 #define PB200_OK            0
 #define PB200_EINVAL       -1   /* bad argument */
@@ -171,7 +171,9 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
  *              running sums after every 32-source tile instead of every 512 sources, so that the handful of
  *              sources that carry most of sum a^2 do not set the rounding unit of everybody else's additions.
  *              The sum itself does not depend on the order.
- *   d_vis      [nbl,nchan] complex128, overwritten
+ *   d_vis      [nbl,nchan] complex128, overwritten; consecutive baseline rows are vis_row_stride complex elements
+ *              apart (0 = nchan, i.e. dense).  A multiple of nchan addresses every n-th row of a larger array: the
+ *              interleaved baseline shard of one rank inside the writing rank's buffer (sharding.py).
  *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM
  */
 #define PB200_SKYVIS_AUTO       0
@@ -186,7 +188,8 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
 #define PB200_SKYVIS_RECURRENCE_3TERM_SCALAR 7   /* the same with scalar FFMA (A/B) */
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
-                 const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, int method, void* stream);
+                 const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, long long vis_row_stride, int method,
+                 void* stream);
 /* 1 when h_freqs is f0 + k df to within 1e-4 Hz -- the test pb200_skyvis applies before it takes a recurrence
  * (or the fp64) kernel; the host shim uses the same test to decide whether precision control applies.        */
 int pb200_channels_uniform(const double* h_freqs, int nchan);
@@ -198,16 +201,17 @@ int pb200_channels_uniform(const double* h_freqs, int nchan);
  * One snapshot, logical shape [nbl,nchan].  d_tsys / d_aeff / d_effq are fp64 with element
  * strides (row, col) given in `strides[6]` = {tsys_row, tsys_col, aeff_row, aeff_col, effq_row,
  * effq_col}; a zero stride broadcasts (a [nchan] Tsys is {0,1}, a scalar is {0,0}).
- * Normal deviates come from Philox4x32-10 keyed by seed with counter (snapshot*nbl_total + bl_offset + b) *
+ * Normal deviates come from Philox4x32-10 keyed by seed with counter (snapshot*nbl_total + bl_offset + b*bl_step) *
  * ceil(nchan/2) + (f mod ceil(nchan/2)) -- words 0-1 serve channel f < ceil(nchan/2), words 2-3 channel f +
- * ceil(nchan/2) -- so a result does not depend on how baselines are sharded across GPUs.  Box-Muller in fp32 (24-bit
+ * ceil(nchan/2) -- so a result does not depend on how baselines are sharded across GPUs (bl_step = 1: contiguous
+ * block starting at bl_offset; bl_step = world size: interleaved shard, local row b is global baseline bl_offset + b*bl_step).  Box-Muller in fp32 (24-bit
  * deviates), rms and scaling in fp64.  d_gains (complex128 [nbl,nchan]) may be NULL (unity).  Any of d_rms /
  * d_noise / d_vis may be NULL to skip that output.
  * add_only != 0: d_noise is an INPUT and only d_vis = gains*skyvis + noise is written (:6722).
  */
 int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d_tsys, const double* d_aeff,
                 const double* d_effq, const long long* strides, const void* d_gains, int nbl, int nchan,
-                double df, double t_acc, int flux_unit_k, uint64_t seed, int snapshot, int bl_offset,
+                double df, double t_acc, int flux_unit_k, uint64_t seed, int snapshot, int bl_offset, int bl_step,
                 int nbl_total, int add_only, double* d_rms, void* d_noise, void* d_vis, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -926,6 +926,52 @@ def multi_window_delay_transform(vis_freq, bp, freq_wts, freq_resolution, pad=1.
     return NP.stack(out, axis=1), vis_freq.shape[1] / NP.sum(freq_wts, axis=1)
 
 
+def subband_weights(channels, bw_eff, freq_center, shape="rect"):
+    """Frequency weights of DelaySpectrum.subband_delay_transform, delay_spectrum.py:2153-2176 (fftpow = 1): [nwin, nchan].
+    frac_width = DSP.window_N2width(shape, area_normalize=False, power_normalize=True) [AU-memory: sum((w/max w)^2)/N];
+    n_window = round(bw_eff / frac_width / df) (:2156-2157); window = sqrt(frac_width n) * power-normalised window (:2166)
+    centred on the channel nearest the centre frequency (LKP.find_1NN within df/2), sorted by channel, clipped to the band."""
+    channels = NP.asarray(channels, dtype=NP.float64)
+    df = channels[1] - channels[0]
+    bw_eff = NP.asarray(bw_eff, dtype=NP.float64).reshape(-1)
+    freq_center = NP.asarray(freq_center, dtype=NP.float64).reshape(-1)
+    w = windowing(1000000, shape=shape.lower())
+    frac_width = NP.sum((w / w.max()) ** 2) / w.size
+    n_window = NP.round(bw_eff / frac_width / df).astype(int)
+    ind = NP.rint((freq_center - channels[0]) / df).astype(int)
+    order = NP.argsort(ind, kind="stable")
+    ind, n_window = ind[order], n_window[order]
+    freq_wts = NP.zeros((ind.size, channels.size))
+    for i, ic in enumerate(ind):
+        window = NP.sqrt(frac_width * n_window[i]) * windowing(int(n_window[i]), shape=shape.lower(), power_normalize=True)
+        k = ic + NP.arange(int(n_window[i])) - int(n_window[i] / 2)
+        ok = (k >= 0) & (k < channels.size)
+        freq_wts[i, k[ok]] = window[ok]
+    return freq_wts
+
+
+def subband_delay_transform(vis_freq, bp, freq_wts, freq_resolution, pad=1.0):
+    """delay_spectrum.py:2178-2201 for one product: [nbl, nchan, nsnap] -> full-resolution [nbl, nwin, nchan + npad, nsnap]
+    (no decimation), the lags, and the correlation length nchan / sum(window) (:2201)."""
+    nchan = vis_freq.shape[1]
+    npad = int(nchan * pad)
+    x = vis_freq[:, NP.newaxis, :, :] * bp[:, NP.newaxis, :, :] * freq_wts[NP.newaxis, :, :, NP.newaxis]
+    out = FT1D(NP.pad(x, ((0, 0), (0, 0), (0, npad), (0, 0)), mode="constant"), ax=2, inverse=True, shift=True) * (npad + nchan) * freq_resolution
+    return out, spectral_axis(nchan + npad, delx=freq_resolution, shift=True), nchan / NP.sum(freq_wts, axis=1)
+
+
+def subband_resample(lags, lag_kernel, spectra, bw_eff, total_bw):
+    """delay_spectrum.py:2220-2240: decimation by min(total_bw / bw_eff); lags and kernel by linear interpolation at
+    arange(0, n, factor), spectra by Fourier resampling to round(n / factor) samples (DSP.downsampler(method='FFT') [AU-memory])."""
+    from scipy import signal
+    factor = NP.min(total_bw / NP.asarray(bw_eff))
+    n = lags.size
+    pos = NP.arange(0, n, factor)
+    f = interpolate.interp1d(NP.arange(n), lag_kernel, kind="linear", axis=2, bounds_error=False, fill_value=NP.nan)
+    rlags = NP.interp(pos, NP.arange(n), lags)
+    return rlags, f(pos), [signal.resample(x, int(NP.round(n / factor)), axis=2) for x in spectra], (1.0 / NP.asarray(bw_eff)) / (rlags[1] - rlags[0])
+
+
 # --------------------------------------------------------------------------------------------
 # phase centring / projected baselines (interferometry.py:7712-7995)
 # --------------------------------------------------------------------------------------------

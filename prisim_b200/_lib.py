@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libprisim_b200.so")   # PB200_LIB: developer override (tools/variants.sh)
 
 PB200_OK = 0
+ABI_VERSION = 200                     # PB200_VERSION of include/prisim_b200.h
 SKY_ALTAZ, SKY_HADEC, SKY_DIRCOS = 0, 1, 2
 BEAM_DELTA, BEAM_AIRY, BEAM_GAUSSIAN, BEAM_DIPOLE, BEAM_TABLE, BEAM_LOGTABLE = 0, 1, 2, 3, 4, 5
 ARRAY_NONE, ARRAY_ANALYTIC, ARRAY_ELEMENTS = 0, 1, 2
@@ -56,9 +57,9 @@ SYMBOLS = {
     "pb200_nsrc_pad": (_i, [_i]),
     "pb200_amp_table": (_i, [_vp, _vp, _vp, _i, C.POINTER(SpectrumDesc), C.POINTER(BeamDesc), _vp, _vp, _i, _i, _vp, _vp]),
     "pb200_amp_scale": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
-    "pb200_skyvis": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "pb200_skyvis": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _ll, _i, _vp]),
     "pb200_channels_uniform": (_i, [_vp, _i]),
-    "pb200_noise": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_ll), _vp, _i, _i, _d, _d, _i, _u64, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pb200_noise": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_ll), _vp, _i, _i, _d, _d, _i, _u64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pb200_delay_nout": (_i, [_i, _d, _i]),
     "pb200_delay_transform": (_i, [_vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _d, _d, _i, _vp, _vp]),
     "pb200_phase_rotate": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
@@ -92,6 +93,9 @@ def load():
         fn = getattr(lib, name)         # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.pb200_version() != ABI_VERSION:
+        raise PB200Error("libprisim_b200.so has ABI version {0}, this package needs {1}: rebuild it (make -C prisim_b200/csrc)".format(
+            lib.pb200_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -23,6 +23,8 @@ int pb200_ctx_create(pb200_ctx** out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   const char* spc = getenv("PB200_SKYVIS_SPC");          // developer override of the phase-sum CTA shape (tools/variants.sh)
   ctx->skyvis_spc_env = spc ? atoi(spc) : 0;
+  const char* r8 = getenv("PB200_DT_R8");
+  ctx->dt_force_r8 = r8 ? atoi(r8) : 0;
   *out = ctx;
   return PB200_OK;
 }

@@ -27,6 +27,7 @@ struct pb200_ctx {
   } chan[PB_CHAN_CACHE];
   unsigned long long chan_clock;
   int skyvis_spc_env;      // PB200_SKYVIS_SPC read once at ctx creation (developer override), 0 = unset
+  int dt_force_r8;         // PB200_DT_R8=1: 1024-point delay transforms through k_delay_fft_r8 instead of k_delay_fft_w32 (A/B)
 };
 
 #define PB_SPEED_OF_LIGHT 299792458.0   // scipy.constants.c

@@ -261,6 +261,87 @@ __global__ void __launch_bounds__(256, PB_DT_MINBLOCKS) k_delay_fft_r8(const Del
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_delay_fft_w32: one WARP per 1024-point row, two passes of radix 32 (1024 = 32 x 32).
+// k_delay_fft_r8 is bound by L1/TEX requests (profiles/delay_fft_r8_r01_ncu.txt: 72 % of peak, HBM at 46 %): with 8
+// points per thread and the 8.8.8.2 factorisation every point crosses the L1/TEX pipe 8 times (global load, three
+// shared-memory round trips, global store) plus the weight and twiddle loads.  Here a lane holds 32 points:
+//   pass 1  lane a loads x[a + 32 b] * w (b = 0..31; every b is one coalesced 512-byte run), does the 32-point
+//           inverse FFT over b in registers, multiplies by W^(a c) (powers of ONE table entry, four interleaved
+//           chains) and writes row a of a 32 x 33 shared-memory tile;
+//   pass 2  lane c reads column c (conflict-free: 16-byte elements, row stride 33), does the 32-point inverse FFT
+//           over a in registers and stores X[c + 32 d] (scale and fftshift fused; every d is a coalesced run).
+// 4 L1/TEX crossings per point instead of 8, one __syncwarp instead of 5 CTA barriers, no idle lanes in a radix-2
+// tail.  ~190 registers per thread: 8 warps per SM, each with 32 x 16 B loads in flight per lane (128 KB per SM).
+// The 32-point transform is 4 x 8: four-point transforms over q of v[p + 8 q], twiddles W32^(p c4), eight-point
+// transforms over p; output index c4 + 4 c8.
+// ---------------------------------------------------------------------------------------------
+__constant__ double W32C[22] = {1.00000000000000000000e+00, 9.80785280403230430579e-01, 9.23879532511286738483e-01, 8.31469612302545235671e-01, 7.07106781186547572737e-01, 5.55570233019602288671e-01, 3.82683432365089837290e-01, 1.95090322016128331351e-01, 6.12323399573676603587e-17, -1.95090322016128192573e-01, -3.82683432365089726268e-01, -5.55570233019601955604e-01, -7.07106781186547461715e-01, -8.31469612302545346694e-01, -9.23879532511286738483e-01, -9.80785280403230430579e-01, -1.00000000000000000000e+00, -9.80785280403230430579e-01, -9.23879532511286849505e-01, -8.31469612302545457716e-01, -7.07106781186547683760e-01, -5.55570233019602177649e-01};
+__constant__ double W32S[22] = {0.00000000000000000000e+00, 1.95090322016128248084e-01, 3.82683432365089781779e-01, 5.55570233019602177649e-01, 7.07106781186547461715e-01, 8.31469612302545235671e-01, 9.23879532511286738483e-01, 9.80785280403230430579e-01, 1.00000000000000000000e+00, 9.80785280403230430579e-01, 9.23879532511286738483e-01, 8.31469612302545457716e-01, 7.07106781186547572737e-01, 5.55570233019602177649e-01, 3.82683432365089892802e-01, 1.95090322016128608906e-01, 1.22464679914735320717e-16, -1.95090322016128359106e-01, -3.82683432365089670757e-01, -5.55570233019601955604e-01, -7.07106781186547461715e-01, -8.31469612302545235671e-01};
+
+__device__ __forceinline__ void ifft32(double2 (&v)[32]) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    double2 t[4] = {v[p], v[p + 8], v[p + 16], v[p + 24]};
+    ifft_small<4>(t);
+    v[p] = t[0];
+#pragma unroll
+    for (int c4 = 1; c4 < 4; ++c4)
+      v[p + 8 * c4] = p == 0 ? t[c4] : cmul(t[c4], make_double2(W32C[p * c4], W32S[p * c4]));
+  }
+  double2 o[32];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    double2 t[8];
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) t[pp] = v[pp + 8 * c4];
+    ifft_small<8>(t);
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) o[c4 + 4 * c8] = t[c8];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = o[i];
+}
+
+constexpr int W32_WARPS = 4;                  // rows per CTA
+constexpr int W32_STRIDE = 33;                // double2 elements per shared-memory tile row
+
+template <bool HAS_X>
+__global__ void __launch_bounds__(32 * W32_WARPS, 2) k_delay_fft_w32(const DelayParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2* tile = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * 32 * W32_STRIDE;
+  const int row = blockIdx.x * W32_WARPS + warp;
+  if (row >= P.nrows) return;                  // warp-uniform; no CTA barrier below
+  double2 v[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) v[b] = load_in_nb<HAS_X>(P, row, lane + 32 * b);
+  ifft32(v);                                   // v[c] = sum_b x[a + 32 b] W32^(b c)
+  {
+    // twiddles W^(a c), W = exp(2 pi i / 1024): four chains c = c0, c0 + 4, ... stepped by W^(4 a)
+    const double2 w1 = __ldg(&P.twiddle[lane]);
+    const double2 w2 = cmul(w1, w1);
+    const double2 w4 = cmul(w2, w2);
+    double2 ch[4] = {make_double2(1.0, 0.0), w1, w2, cmul(w2, w1)};
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c >= 4) ch[c & 3] = cmul(ch[c & 3], w4);
+      tile[lane * W32_STRIDE + c] = c == 0 ? v[0] : cmul(v[c], ch[c & 3]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int a = 0; a < 32; ++a) v[a] = tile[a * W32_STRIDE + lane];
+  ifft32(v);                                   // v[d] = X[c + 32 d], c = lane
+  double2* out = P.out + (size_t)row * P.nout;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    const int i = (lane + 32 * d - P.shift) & 1023;              // fftshift: out[i] = X[(i + shift) mod N]
+    out[i] = make_double2(v[d].x * P.scale, v[d].y * P.scale);
+  }
+}
+
 // direct evaluation of the needed bins; blockDim.x threads share one row staged in smem
 __global__ void __launch_bounds__(FFT_THREADS) k_delay_dft(const DelayParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -403,6 +484,18 @@ int pb200_delay_transform(pb200_ctx* ctx, const void* d_x, const double* d_bp, l
         PB_CHECK_LAUNCH(ctx, "k_mul_rows");
         P.bp = (const double*)tmp; P.wts = nullptr;
       }
+    }
+    if (pl.nfft == 1024 && !ctx->dt_force_r8) {       // one warp per row, 32 x 32 (see k_delay_fft_w32)
+      const size_t smem32 = sizeof(double2) * 32 * W32_STRIDE * W32_WARPS;
+      if (P.x) {
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_w32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+        k_delay_fft_w32<true><<<pb_div_up(nrows, W32_WARPS), 32 * W32_WARPS, smem32, stream>>>(P);
+      } else {
+        PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_w32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+        k_delay_fft_w32<false><<<pb_div_up(nrows, W32_WARPS), 32 * W32_WARPS, smem32, stream>>>(P);
+      }
+      PB_CHECK_LAUNCH(ctx, "k_delay_fft_w32");
+      return PB200_OK;
     }
     if (P.x) {
       PB_CUDA(ctx, cudaFuncSetAttribute(k_delay_fft_r8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -38,6 +38,7 @@ struct NoiseParams {
   int flux_unit_k;
   unsigned long long seed;
   long long row_offset;    // snapshot*nbl_total + bl_offset: global row of this shard's first baseline
+  long long row_step;      // global rows between consecutive local rows (1 = contiguous block, world size = interleaved shard)
   long long nrows;
   long long st[6];         // element strides (row, col) of tsys, aeff, effq
   int nchan;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) k_noise(const NoiseParams P) {
     return;
   }
   uint32_t r[4];
-  const unsigned long long ctr = (unsigned long long)(P.row_offset + row) * (unsigned long long)H + (unsigned long long)c;
+  const unsigned long long ctr = (unsigned long long)(P.row_offset + row * P.row_step) * (unsigned long long)H + (unsigned long long)c;
   philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), r);
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) k_noise(const NoiseParams P) {
 extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d_tsys, const double* d_aeff,
                            const double* d_effq, const long long* strides, const void* d_gains, int nbl, int nchan,
                            double df, double t_acc, int flux_unit_k, uint64_t seed, int snapshot, int bl_offset,
-                           int nbl_total, int add_only, double* d_rms, void* d_noise, void* d_vis, void* stream_) {
+                           int bl_step, int nbl_total, int add_only, double* d_rms, void* d_noise, void* d_vis, void* stream_) {
   if (!ctx) return PB200_EINVAL;
   if (nbl <= 0 || nchan <= 0) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: bad shape");
   if (add_only) {
@@ -123,7 +124,8 @@ extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d
     return pb_fail(ctx, PB200_EINVAL, "pb200_noise: bad arguments");
   }
   if (d_vis && !d_skyvis) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: d_vis requested without d_skyvis");
-  if (nbl_total < bl_offset + nbl) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: shard exceeds nbl_total");
+  if (bl_step < 1) bl_step = 1;
+  if (nbl_total < bl_offset + (nbl - 1) * bl_step + 1) return pb_fail(ctx, PB200_EINVAL, "pb200_noise: shard exceeds nbl_total");
   cudaStream_t stream = (cudaStream_t)stream_;
   PbDeviceGuard guard(ctx->device);
   NoiseParams P;
@@ -135,6 +137,7 @@ extern "C" int pb200_noise(pb200_ctx* ctx, const void* d_skyvis, const double* d
   P.flux_unit_k = flux_unit_k;
   P.seed = seed;
   P.row_offset = (long long)snapshot * nbl_total + bl_offset;
+  P.row_step = bl_step;
   P.nrows = nbl;
   k_noise<<<pb_div_up((long long)nbl * ((nchan + 1) / 2), 256), 256, 0, stream>>>(P);
   PB_CHECK_LAUNCH(ctx, "k_noise");

@@ -99,7 +99,8 @@ struct SkyvisParams {
   const double* geom;      // [nsrc_pad][4]: l, m, n, taper coefficient
   const double* bl;        // [nbl][3] metres
   const double* freqs;     // device [nchan_pad] Hz (padded channels repeat the last frequency)
-  double* vis;             // [nbl][nchan] complex128
+  double* vis;             // [nbl][nchan] complex128, rows vis_stride complex elements apart
+  long long vis_stride;
   double2* accum;          // fp64 running sums, warp-tile layout [slot][warp][k][lane] (coalesced flushes); slots
                            // 0..ntile-1 = output tiles, ntile + c = head partial of CTA c
   double pc[3];            // phase-centre dircos
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
     for (int kk = 0; kk < KTV; kk += 32) {
       const int k = kk + tx;
       const int ch = (gx * P.wc + wc) * KTV + k;
-      if (k < KTV && b < P.nbl && ch < P.nchan) vis[(size_t)b * P.nchan + ch] = tile[k][r];
+      if (k < KTV && b < P.nbl && ch < P.nchan) vis[(size_t)b * P.vis_stride + ch] = tile[k][r];
     }
   }
 }
@@ -909,7 +910,8 @@ __global__ void k_geom_stage(const double* __restrict__ dircos, const double* __
 
 extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                             const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
-                            const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, int method, void* stream_) {
+                            const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, long long vis_row_stride, int method,
+                            void* stream_) {
   if (!ctx) return PB200_EINVAL;
   if (nsrc < 0 || nbl <= 0 || nchan <= 0 || !d_bl || !h_pc || !h_freqs || !d_vis)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: bad arguments");
@@ -920,8 +922,10 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PbDeviceGuard guard(ctx->device);
+  if (vis_row_stride == 0) vis_row_stride = nchan;
+  if (vis_row_stride < nchan) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: vis_row_stride smaller than nchan");
   if (nsrc == 0) {                                     // empty ROI: zeros (interferometry.py:6378-6382)
-    PB_CUDA(ctx, cudaMemsetAsync(d_vis, 0, sizeof(double) * 2 * (size_t)nbl * nchan, stream));
+    PB_CUDA(ctx, cudaMemset2DAsync(d_vis, sizeof(double) * 2 * (size_t)vis_row_stride, 0, sizeof(double) * 2 * (size_t)nchan, nbl, stream));
     return PB200_OK;
   }
 
@@ -950,7 +954,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   PB_CHECK_LAUNCH(ctx, "k_geom_stage");
 
   SkyvisParams P;
-  P.amp = d_amp; P.geom = (const double*)geom; P.bl = d_bl; P.freqs = dfreq; P.vis = (double*)d_vis;
+  P.amp = d_amp; P.geom = (const double*)geom; P.bl = d_bl; P.freqs = dfreq; P.vis = (double*)d_vis; P.vis_stride = vis_row_stride;
   P.pc[0] = h_pc[0]; P.pc[1] = h_pc[1]; P.pc[2] = h_pc[2];
   P.f0 = h_freqs[0]; P.df = df;
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;

@@ -38,13 +38,50 @@ def windowing(N, shape="rect", pad_width=0, centering=True, area_normalize=False
     return win
 
 
-def window_N2width(n_window=None, shape="rect", fftpow=1.0):
+def window_N2width(n_window=None, shape="rect", fftpow=1.0, area_normalize=True, power_normalize=False):
     """Width of the equivalent rectangular window as a fraction of the window length (``DSP.window_N2width`` of the
-    un-vendored astroutils, used at interferometry.py:8236): sum(w / max w) / N, evaluated on a long window when
-    n_window is None (rect 1.0, bhw 0.35875, bnw 0.3635819)."""
+    un-vendored astroutils [AU-memory], used at interferometry.py:8236 and delay_spectrum.py:2155): sum(w / max w) / N
+    (rect 1.0, bhw 0.35875, bnw 0.3635819), or with power_normalize sum((w / max w)^2) / N (bhw 0.2580); evaluated on
+    a long window when n_window is None."""
     n = 1000000 if n_window is None else int(n_window)
     w = windowing(n, shape=shape.lower()) ** fftpow
-    return float(NP.sum(w / w.max()) / n)
+    w = w / w.max()
+    return float(NP.sum(w ** 2) / n) if (power_normalize and not area_normalize) else float(NP.sum(w) / n)
+
+
+def window_fftpow(N_window, shape="rect", fftpow=1.0, centering=True, peak=None, area_normalize=False, power_normalize=False):
+    """``DSP.window_fftpow`` of astroutils for fftpow = 1 (the default of every PRISim call site): the plain window.
+    The construction for fftpow != 1 (window whose Fourier transform is raised to a power) lives in the un-vendored
+    astroutils and could not be pinned here, so it is refused rather than guessed."""
+    if float(fftpow) != 1.0:
+        raise NotImplementedError("window_fftpow with fftpow != 1 is defined in the un-vendored astroutils package and is not restated here")
+    return windowing(int(N_window), shape=shape.lower(), centering=centering, area_normalize=area_normalize, power_normalize=power_normalize,
+                     peak=1.0 if peak is None else peak)
+
+
+def subband_weights(f, df, bw_eff, freq_center, shape="rect", fftpow=1.0):
+    """The [n_win, nchan] frequency weights of ``DelaySpectrum.subband_delay_transform`` (delay_spectrum.py:2153-2176):
+    for every (effective bandwidth, centre frequency) a power-normalised window of n = round(bw_eff / (frac_width df))
+    samples scaled by sqrt(frac_width n), centred on the channel nearest to the centre frequency (within df/2; others are
+    dropped), clipped to the band; windows ordered by centre channel.  Returns (weights, kept centre-channel indices)."""
+    f = NP.asarray(f, dtype=NP.float64)
+    bw_eff = NP.asarray(bw_eff, dtype=NP.float64).reshape(-1)
+    freq_center = NP.asarray(freq_center, dtype=NP.float64).reshape(-1)
+    frac_width = window_N2width(n_window=None, shape=shape, fftpow=fftpow, area_normalize=False, power_normalize=True)
+    n_window = NP.round(bw_eff / frac_width / df).astype(int)                           # :2156-2157
+    nearest = NP.rint((freq_center - f[0]) / df).astype(int)                             # LKP.find_1NN within df/2, out-of-band removed
+    ok = (nearest >= 0) & (nearest < f.size)
+    ok &= NP.abs(f[NP.clip(nearest, 0, f.size - 1)] - freq_center) <= 0.5 * df
+    nearest, n_window = nearest[ok], n_window[ok]
+    order = NP.argsort(nearest, kind="stable")                                            # :2159-2163
+    nearest, n_window = nearest[order], n_window[order]
+    wts = NP.zeros((nearest.size, f.size))
+    for i, (c, n) in enumerate(zip(nearest, n_window)):
+        win = NP.sqrt(frac_width * n) * window_fftpow(n, shape=shape, fftpow=fftpow, centering=True, power_normalize=True)   # :2166
+        k = c + NP.arange(n) - int(n / 2)                                                 # :2168
+        inside = (k >= 0) & (k < f.size)
+        wts[i, k[inside]] = win[inside]
+    return wts, nearest
 
 
 class DelaySpectrum(object):
@@ -62,6 +99,9 @@ class DelaySpectrum(object):
         self.lags = None
         self.bp_wts = None
         self.vis_lag = self.skyvis_lag = self.vis_noise_lag = self.lag_kernel = None
+        self.cc_lags = None                                              # no delay CLEAN here: the 'cc' branch of the sub-band transform is skipped (:2151)
+        self.subband_delay_spectra = {}
+        self.subband_delay_spectra_resampled = {}
 
     @property
     def bp(self):
@@ -183,3 +223,133 @@ class DelaySpectrum(object):
             self.vis_lag, self.skyvis_lag = result["vis_lag"], result["skyvis_lag"]
             self.vis_noise_lag, self.lag_kernel = result["vis_noise_lag"], result["lag_kernel"]
         return result
+
+    def subband_delay_transform(self, bw_eff, freq_center=None, shape=None, fftpow=None, pad=None, bpcorrect=False, action=None,
+                                verbose=True):
+        """Delay transforms on frequency sub-bands, same call as delay_spectrum.py:1842-2248.  Arguments are dictionaries
+        with the keys 'cc' and 'sim' like the reference's; only the 'sim' branch is computed (the 'cc' branch needs delay
+        CLEAN products, which are outside the hot-path scope -- the reference skips it too while ``cc_lags`` is None,
+        :2151).  Stores ``subband_delay_spectra`` (full resolution: 'skyvis_lag', 'vis_lag', 'vis_noise_lag', 'lag_kernel' of
+        shape [nbl, n_win, nchan + npad, n_t], 'freq_wts', 'lags', 'lag_corr_length', ...) and
+        ``subband_delay_spectra_resampled`` (:2220-2240: decimated by min((nchan + npad) df / bw_eff); kernel and lags by
+        linear interpolation, spectra by Fourier resampling) and returns one of them for action = 'return_oversampled' /
+        'return_resampled'.  Every (window, snapshot) is one launch of the delay-transform kernel with the window as its
+        weights; the resampling of the returned numpy arrays is host post-processing (scipy.signal.resample)."""
+        if not isinstance(bw_eff, dict):
+            raise TypeError("Effective bandwidth must be specified as a dictionary")
+        bw = {}
+        for key in ("cc", "sim"):
+            if key in bw_eff:
+                if not isinstance(bw_eff[key], (int, float, list, NP.ndarray)):
+                    raise TypeError("Value of effective bandwidth must be a scalar, list or numpy array")
+                bw[key] = NP.asarray(bw_eff[key], dtype=NP.float64).reshape(-1)
+                if NP.any(bw[key] <= 0.0):
+                    raise ValueError("All values in effective bandwidth must be strictly positive")
+        if "sim" not in bw:
+            raise KeyError("Effective bandwidth for key 'sim' must be specified")
+        if freq_center is None:
+            fc = {key: NP.asarray(self.f[self.f.size // 2]).reshape(-1) for key in bw}
+        elif isinstance(freq_center, dict):
+            fc = {}
+            for key in bw:
+                if not isinstance(freq_center.get(key, None), (int, float, list, NP.ndarray)):
+                    raise TypeError("Values(s) of frequency center must be scalar, list or numpy array")
+                fc[key] = NP.asarray(freq_center[key], dtype=NP.float64).reshape(-1)
+                if NP.any((fc[key] <= self.f.min()) | (fc[key] >= self.f.max())):
+                    raise ValueError("Value(s) of frequency center(s) must lie strictly inside the observing band")
+        else:
+            raise TypeError("Input frequency center must be specified as a dictionary")
+        for key in bw:
+            if bw[key].size == 1 and fc[key].size > 1:
+                bw[key] = NP.repeat(bw[key], fc[key].size)
+            elif bw[key].size > 1 and fc[key].size == 1:
+                fc[key] = NP.repeat(fc[key], bw[key].size)
+            elif bw[key].size != fc[key].size:
+                raise ValueError("Effective bandwidth(s) and frequency center(s) must have same number of elements")
+        if shape is not None:
+            if not isinstance(shape, dict):
+                raise TypeError("Window shape must be specified as a dictionary")
+            for key in bw:
+                if not isinstance(shape[key], str):
+                    raise TypeError("Window shape must be a string")
+                if shape[key] not in ["rect", "bhw", "bnw", "RECT", "BHW", "BNW"]:
+                    raise ValueError("Invalid value for window shape specified.")
+        else:
+            shape = {key: "rect" for key in bw}
+        if fftpow is None:
+            fftpow = {key: 1.0 for key in bw}
+        else:
+            if not isinstance(fftpow, dict):
+                raise TypeError("Power to raise FFT of window by must be specified as a dictionary")
+            for key in bw:
+                if not isinstance(fftpow[key], (int, float)):
+                    raise TypeError("Power to raise window FFT by must be a scalar value.")
+                if fftpow[key] < 0.0:
+                    raise ValueError("Power for raising FFT of window by must be positive.")
+        if pad is None:
+            pad = {key: 1.0 for key in bw}
+        else:
+            if not isinstance(pad, dict):
+                raise TypeError("Padding for delay transform must be specified as a dictionary")
+            pad = dict(pad)
+            for key in bw:
+                if not isinstance(pad[key], (int, float)):
+                    raise TypeError("pad fraction must be a scalar value.")
+                if pad[key] < 0.0:
+                    pad[key] = 0.0
+        if not isinstance(bpcorrect, bool):
+            raise TypeError("Input keyword bpcorrect must be of boolean type")
+
+        import torch
+        ia = self.ia
+        key = "sim"
+        nbl, nchan, nsnap = ia.baselines.shape[0], self.f.size, len(ia._skyvis)
+        freq_wts, _ = subband_weights(self.f, self.df, bw[key], fc[key], shape=shape[key], fftpow=fftpow[key])
+        nwin = freq_wts.shape[0]
+        npad = int(nchan * pad[key])                                                          # :2178
+        lags = NP.fft.fftshift(NP.fft.fftfreq(nchan + npad, d=self.df))                        # :2179
+        wts_dev = engine._f64(freq_wts, ia.device)
+        res = {"freq_center": fc[key], "shape": shape[key], "freq_wts": freq_wts, "bw_eff": bw[key], "npad": npad, "lags": lags,
+               "lag_corr_length": nchan / NP.sum(freq_wts, axis=1)}
+        for name, lst in (("skyvis_lag", ia._skyvis), ("vis_lag", ia._vis), ("vis_noise_lag", ia._noise), ("lag_kernel", None)):
+            if lst is not None and not lst:
+                continue                                                                      # product not generated (the reference needs all three)
+            out = torch.empty((nbl, nwin, nchan + npad, nsnap), dtype=torch.complex128, device=ia._dev_str())
+            for t in range(nsnap):
+                for i in range(nwin):
+                    if lst is None:
+                        k = engine.delay_transform(None, ia._bp[t], wts_dev[i], self.df, pad=pad[key], downsample=False,
+                                                   nrows=nbl if ia._bp[t].ndim == 2 else 1, nchan=nchan, device=ia.device)
+                    else:
+                        k = engine.delay_transform(lst[t], ia._bp[t], wts_dev[i], self.df, pad=pad[key], downsample=False)
+                    out[:, i, :, t] = k
+            res[name] = out.cpu().numpy()
+        result = {key: res}
+        self.subband_delay_spectra = result
+        # resampled products (:2220-2240)
+        from scipy import signal
+        rs = {"freq_center": res["freq_center"], "bw_eff": res["bw_eff"]}
+        factor = float(NP.min((nchan + npad) * self.df / rs["bw_eff"]))
+        pos = NP.arange(0, lags.size, factor)
+        rs["lags"] = NP.interp(pos, NP.arange(lags.size), lags)
+
+        def interp_axis2(a):                    # DSP.downsampler(method='interp', kind='linear') along axis 2
+            j0 = NP.floor(pos).astype(int)
+            fr = (pos - j0).reshape(1, 1, -1, 1)
+            j1 = NP.minimum(j0 + 1, a.shape[2] - 1)
+            out = a[:, :, j0, :] * (1.0 - fr) + a[:, :, j1, :] * fr
+            out[:, :, pos > a.shape[2] - 1, :] = NP.nan          # beyond the last sample: interp1d(bounds_error=False) fills NaN
+            return out
+
+        rs["lag_kernel"] = interp_axis2(res["lag_kernel"])
+        nout = int(NP.round(lags.size / factor))
+        for name in ("skyvis_lag", "vis_lag", "vis_noise_lag"):
+            if name in res:
+                rs[name] = signal.resample(res[name], nout, axis=2)                           # DSP.downsampler(method='FFT') [AU-memory]
+        dlag = rs["lags"][1] - rs["lags"][0]
+        rs["lag_corr_length"] = (1.0 / res["bw_eff"]) / dlag
+        self.subband_delay_spectra_resampled = {key: rs}
+        if action == "return_oversampled":
+            return result
+        if action == "return_resampled":
+            return self.subband_delay_spectra_resampled

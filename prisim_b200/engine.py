@@ -151,12 +151,16 @@ def skyvis(dircos, amp, nsrc, baselines_enu, pc_dircos, freqs_hz, src_fwhm_deg=N
     nbl, nchan = bl.shape[0], freqs.size
     if out is None:
         out = torch.empty((nbl, nchan), dtype=torch.complex128, device=bl.device)
+    if tuple(out.shape) != (nbl, nchan) or out.dtype != torch.complex128 or (nchan > 1 and out.stride(1) != 1) or \
+            (nbl > 1 and out.stride(0) < nchan):
+        raise ValueError("out must be a [nbl, nchan] complex128 CUDA tensor with unit channel stride (rows may be strided)")
+    row_stride = out.stride(0) if nbl > 1 else nchan
     code = {"auto": _lib.SKYVIS_AUTO, "recurrence": _lib.SKYVIS_RECURRENCE, "direct": _lib.SKYVIS_DIRECT,
             "recurrence_scalar": _lib.SKYVIS_RECURRENCE_SCALAR, "fp64": _lib.SKYVIS_FP64,
             "recurrence_lift": _lib.SKYVIS_RECURRENCE_LIFT, "recurrence_3term": _lib.SKYVIS_RECURRENCE_3TERM, "recurrence_3term_scalar": _lib.SKYVIS_RECURRENCE_3TERM_SCALAR}[method]
     amp_dtype = _lib.AMP_F64 if (amp is not None and amp.dtype == torch.float64) else _lib.AMP_F32
     ctx.check(ctx.lib.pb200_skyvis(ctx.handle, _ptr(dircos), _ptr(amp), amp_dtype, int(nsrc), _ptr(bl), int(nbl), _ptr(pc),
-                                   _ptr(freqs), int(nchan), _ptr(src_fwhm_deg), int(nsrc_bright), _ptr(out), code, ctx.stream()))
+                                   _ptr(freqs), int(nchan), _ptr(src_fwhm_deg), int(nsrc_bright), _ptr(out), int(row_stride), code, ctx.stream()))
     return out
 
 
@@ -199,7 +203,7 @@ def _bcast_strides(t, nbl, nchan):
 
 
 def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, bl_offset=0, nbl_total=None, gains=None,
-          flux_unit_k=False, want=("rms", "noise", "vis"), device=None):
+          flux_unit_k=False, want=("rms", "noise", "vis"), device=None, bl_step=1):
     """``pb200_noise`` for one snapshot.  tsys / aeff / effq are contiguous fp64 CUDA tensors of
     shape [nbl,nchan], [nchan], [nbl] or scalar (broadcast through strides).
     Replaces interferometry.py:6676-6693 and :6707-6722."""
@@ -216,7 +220,7 @@ def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, b
     strides = (C.c_longlong * 6)(*st)
     ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), _ptr(tsys), _ptr(aeff), _ptr(effq), strides, _ptr(gains),
                                   int(nbl), int(nchan), float(df), float(t_acc), int(bool(flux_unit_k)),
-                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(snapshot), int(bl_offset), nbl_total, 0,
+                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(snapshot), int(bl_offset), int(bl_step), nbl_total, 0,
                                   _ptr(rms), _ptr(nz), _ptr(vis), ctx.stream()))
     return rms, nz, vis
 
@@ -228,7 +232,7 @@ def add_noise(skyvis_t, noise_t, gains=None):
     nbl, nchan = skyvis_t.shape
     vis = torch.empty_like(skyvis_t)
     ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), None, None, None, None, _ptr(gains), int(nbl), int(nchan),
-                                  1.0, 1.0, 0, 0, 0, 0, nbl, 1, None, _ptr(noise_t), _ptr(vis), ctx.stream()))
+                                  1.0, 1.0, 0, 0, 0, 0, 1, nbl, 1, None, _ptr(noise_t), _ptr(vis), ctx.stream()))
     return vis
 
 

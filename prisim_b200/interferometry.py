@@ -459,7 +459,7 @@ class InterferometerArray(object):
     def __init__(self, labels, baselines, channels, telescope=None, eff_Q=0.89, latitude=34.0790, longitude=0.0,
                  altitude=0.0, skycoords="radec", A_eff=NP.pi * (25.0 / 2) ** 2, pointing_coords="hadec", layout=None,
                  blgroupinfo=None, baseline_coords="localenu", freq_scale=None, gaininfo=None, init_file=None,
-                 simparms_file=None, device=None, bl_offset=0, nbl_total=None, noise_seed=None):
+                 simparms_file=None, device=None, bl_offset=0, nbl_total=None, noise_seed=None, bl_step=1):
         if init_file is not None:
             raise NotImplementedError("loading saved simulations is outside the hot-path scope (SURVEY.md section 8f)")
         if gaininfo is not None:
@@ -557,7 +557,8 @@ class InterferometerArray(object):
 
         # ---- device state ----
         self.device = engine._dev(device)
-        self.bl_offset = int(bl_offset)                  # position of this shard in the full baseline list
+        self.bl_offset = int(bl_offset)                  # position of this shard in the full baseline list: local row b is global
+        self.bl_step = int(bl_step)                      # baseline bl_offset + b * bl_step (noise is keyed by the global index)
         self.nbl_total = nbl if nbl_total is None else int(nbl_total)
         # None: a fresh seed per object (recorded here), so that separate arrays (sub-bands, polarisations, Monte-Carlo
         # repeats) draw independent noise like the reference's global numpy generator; pass a seed for reproducible or
@@ -926,6 +927,8 @@ class InterferometerArray(object):
         else:
             self.pointing_center = NP.vstack((self.pointing_center, pointing_center))
             self.phase_center = NP.vstack((self.phase_center, pointing_center))
+        if not skyvis.is_contiguous():                   # strided rows of another rank's buffer (interleaved shard): keep a dense local copy
+            skyvis = skyvis.contiguous()
         self._skyvis.append(skyvis)
         if gradient_mode is not None:                                                  # :6386-6394
             self._gradient.append(grad)
@@ -970,8 +973,8 @@ class InterferometerArray(object):
             return engine.amp_scale(amp_any, nsrc, nchan, dircos, i, device=self.device)
 
         out, self.next_skyvis_out = self.next_skyvis_out, None
-        if out is not None and (tuple(out.shape) != (nbl, nchan) or out.dtype != torch.complex128 or not out.is_contiguous()):
-            raise ValueError("next_skyvis_out must be a contiguous [nbl, nchan] complex128 CUDA tensor")
+        if out is not None and (tuple(out.shape) != (nbl, nchan) or out.dtype != torch.complex128 or (nchan > 1 and out.stride(1) != 1)):
+            raise ValueError("next_skyvis_out must be a [nbl, nchan] complex128 CUDA tensor with unit channel stride")
         if uniform and (self.precision == "fp64" or (self.precision == "auto" and self._fp64_sticky)):
             self.precision_report.append({"fp64_baselines": nbl, "nbl": nbl, "audited": 0, "audit_max_err": 0.0})
             amp64 = engine.amp_table(dircos, index, nsrc, spec, beam, self.channels, dtype=torch.float64, **kw)
@@ -1137,7 +1140,7 @@ class InterferometerArray(object):
         self._noise_realisation += 1
         for t in range(len(self._skyvis)):
             rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
-                                      seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
+                                      seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset, bl_step=self.bl_step,
                                       nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
                                       want=("rms", "noise"), device=self.device)
             self._rms.append(rms)
@@ -1372,7 +1375,7 @@ class InterferometerArray(object):
                 prod["gradient_" + self.gradient_mode] = self._gradient[t]
             if noise:
                 rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
-                                          self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset,
+                                          self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset, bl_step=self.bl_step,
                                           nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
                                           want=("rms", "noise"), device=self.device)
                 prod.update(vis_rms_freq=rms, vis_noise_freq=nz, vis_freq=engine.add_noise(self._skyvis[t], nz))

@@ -29,24 +29,35 @@ def shard_slice(nbl, world_size, rank):
     return slice(int(b[rank]), int(b[rank + 1]))
 
 
-def gather_baseline_shards(local, nbl_total, dst=0, group=None):
+def shard_rows(nbl, world_size, rank, interleave=False):
+    """Rows of the full baseline list owned by `rank`: a contiguous block (the reference's pp.key='bl' chunks,
+    scripts/run_prisim.py:1775-1791) or, interleaved, every world_size-th baseline starting at `rank`.  Interleaving
+    deals every kind of baseline (PRISim sorts them by length; the short, strongly cancelling ones that the precision
+    control recomputes in fp64 all sit at the front) evenly to the ranks."""
+    if interleave:
+        return slice(int(rank), int(nbl), int(world_size))
+    return shard_slice(nbl, world_size, rank)
+
+
+def gather_baseline_shards(local, nbl_total, dst=0, group=None, interleave=False):
     """Gather [nbl_local, ...] shards (baseline axis first) into [nbl_total, ...] on rank `dst`.
     One batched point-to-point exchange; other ranks return None."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    bounds = shard_bounds(nbl_total, world)
+    rows = [shard_rows(nbl_total, world, r, interleave) for r in range(world)]
+    nrows = [len(range(*sl.indices(nbl_total))) for sl in rows]
     local = local.contiguous()
     if rank == dst:
         full = torch.empty((nbl_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        full[bounds[dst]:bounds[dst + 1]] = local
+        full[rows[dst]] = local
         ops = []
         views = []
         for r in range(world):
-            if r == dst or bounds[r + 1] == bounds[r]:
+            if r == dst or nrows[r] == 0:
                 continue
-            v = full[bounds[r]:bounds[r + 1]]
-            buf = v if v.is_contiguous() else torch.empty_like(v)
+            v = full[rows[r]]
+            buf = v if v.is_contiguous() else torch.empty_like(v, memory_format=torch.contiguous_format)
             views.append((v, buf))
             ops.append(dist.P2POp(dist.irecv, buf, r, group=group))
         if ops:
@@ -62,9 +73,9 @@ def gather_baseline_shards(local, nbl_total, dst=0, group=None):
     return None
 
 
-def make_sharded_array(cls, labels, baselines, channels, rank=None, world_size=None, **kwargs):
-    """Construct the rank-local ``InterferometerArray`` over this rank's baseline block; noise is
-    keyed by the global baseline index (bl_offset/nbl_total) so any world size gives the same run."""
+def make_sharded_array(cls, labels, baselines, channels, rank=None, world_size=None, interleave=False, **kwargs):
+    """Construct the rank-local ``InterferometerArray`` over this rank's baselines (``shard_rows``); noise is
+    keyed by the global baseline index (bl_offset / bl_step / nbl_total) so any world size gives the same run."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
     if world_size is None:
@@ -76,9 +87,9 @@ def make_sharded_array(cls, labels, baselines, channels, rank=None, world_size=N
         box = [fresh_noise_seed() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         kwargs["noise_seed"] = box[0]
-    sl = shard_slice(baselines.shape[0], world_size, rank)
+    sl = shard_rows(baselines.shape[0], world_size, rank, interleave)
     labels = NP.asarray(labels)[sl] if not isinstance(labels, list) else labels[sl]
-    return cls(labels, baselines[sl], channels, bl_offset=sl.start, nbl_total=baselines.shape[0], **kwargs)
+    return cls(labels, baselines[sl], channels, bl_offset=sl.start, bl_step=sl.step or 1, nbl_total=baselines.shape[0], **kwargs)
 
 
 class _RawCudaBuffer(object):
@@ -97,12 +108,14 @@ class PeerGatherBuffer(object):
       * ``row_bounds=shard_bounds(nbl, world)`` (baseline sharding, the reference's pp.key='bl' mode): the buffer
         is ``shape`` = [nbl, ...] itself and rank r owns rows row_bounds[r]:row_bounds[r+1] -- rank `dst` ends up
         with exactly the array an unsharded run would have produced, with no concatenation step
-        (scripts/run_prisim.py:2233-2242).
+        (scripts/run_prisim.py:2233-2242);
+      * ``interleave=True``: the same [nbl, ...] buffer, rank r owns rows r, r + world, ... (``local`` is a strided
+        view; ``pb200_skyvis`` takes the row stride).
 
     Falls back to an NCCL point-to-point gather when peer mapping is unavailable (``mode == 'nccl'``;
     ``force_nccl=True`` selects it for A/B tests)."""
 
-    def __init__(self, shape, device, dst=0, group=None, row_bounds=None, force_nccl=False):
+    def __init__(self, shape, device, dst=0, group=None, row_bounds=None, force_nccl=False, interleave=False):
         import ctypes as C
         from . import _lib
         self.group, self.dst, self.shape = group, dst, tuple(shape)
@@ -110,10 +123,12 @@ class PeerGatherBuffer(object):
         self.device = int(device)
         self.ctx = _lib.get_context(self.device)
         self.bounds = None if row_bounds is None else [int(b) for b in row_bounds]
+        self.interleave = bool(interleave)
         dev = "cuda:{0}".format(self.device)
         nel = int(NP.prod(self.shape))
         row_el = nel // self.shape[0] if self.shape[0] else 0
-        full_shape = (self.world,) + self.shape if self.bounds is None else self.shape
+        whole = self.bounds is not None or self.interleave          # the buffer is the [nbl, ...] array itself
+        full_shape = self.shape if whole else (self.world,) + self.shape
         full_el = int(NP.prod(full_shape))
         self._base = C.c_void_p()
         self._mapped = False
@@ -135,7 +150,10 @@ class PeerGatherBuffer(object):
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         self.mode = "peer" if bool(flag.item()) else "nccl"
-        if self.bounds is None:
+        if self.interleave:
+            nloc = len(range(self.rank, self.shape[0], self.world))
+            lo, n_local, local_shape = 0, nloc * row_el, (nloc,) + self.shape[1:]
+        elif self.bounds is None:
             lo, n_local = self.rank * nel, nel
             local_shape = self.shape
         else:
@@ -143,7 +161,9 @@ class PeerGatherBuffer(object):
             local_shape = (self.bounds[self.rank + 1] - self.bounds[self.rank],) + self.shape[1:]
         if self.mode == "peer":
             base = self._base.value
-            if n_local > 0:
+            if self.interleave and n_local > 0:
+                self.local = torch.as_tensor(_RawCudaBuffer(base, full_shape, "<c16"), device=dev)[self.rank::self.world]
+            elif n_local > 0:
                 self.local = torch.as_tensor(_RawCudaBuffer(base + lo * 16, local_shape, "<c16"), device=dev)
             else:
                 self.local = torch.empty(local_shape, dtype=torch.complex128, device=dev)
@@ -158,24 +178,36 @@ class PeerGatherBuffer(object):
             self._base.value = None
             self.full = torch.empty(full_shape, dtype=torch.complex128, device=dev) if self.rank == dst else None
             if self.rank == dst:
-                self.local = self.full[dst] if self.bounds is None else self.full[self.bounds[dst]:self.bounds[dst + 1]]
+                self.local = self._slice_of(dst)
             else:
                 self.local = torch.empty(local_shape, dtype=torch.complex128, device=dev)
 
     def _slice_of(self, r):
+        if self.interleave:
+            return self.full[r::self.world]
         return self.full[r] if self.bounds is None else self.full[self.bounds[r]:self.bounds[r + 1]]
 
     def wait(self):
         """Make every rank's slice visible on `dst` (peer mode: stores are complete when the writers' streams are;
         nccl mode: one batched point-to-point gather)."""
         if self.mode == "nccl":
+            staged = []
             if self.rank == self.dst:
-                ops = [dist.P2POp(dist.irecv, self._slice_of(r), r, group=self.group) for r in range(self.world)
-                       if r != self.dst and self._slice_of(r).numel() > 0]
+                ops = []
+                for r in range(self.world):
+                    v = self._slice_of(r)
+                    if r == self.dst or v.numel() == 0:
+                        continue
+                    buf = v if v.is_contiguous() else torch.empty(v.shape, dtype=v.dtype, device=v.device)
+                    staged.append((v, buf))
+                    ops.append(dist.P2POp(dist.irecv, buf, r, group=self.group))
             else:
                 ops = [dist.P2POp(dist.isend, self.local, self.dst, group=self.group)] if self.local.numel() > 0 else []
             for req in (dist.batch_isend_irecv(ops) if ops else []):
                 req.wait()
+            for v, buf in staged:
+                if buf.data_ptr() != v.data_ptr():
+                    v.copy_(buf)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
 
@@ -194,8 +226,9 @@ class PeerGatherBuffer(object):
 class ShardedObserver(object):
     """One snapshot at a time over all ranks, sharded over baselines (the reference's ``pp.key='bl'`` equal-volume
     mode, scripts/run_prisim.py:1775-1791 / :2165-2209) with the concatenation on the writing rank
-    (:2233-2242) fused into the kernel epilogue: every rank owns an ``InterferometerArray`` over its contiguous
-    baseline block whose phase-sum kernel stores straight into rank `dst`'s [nbl_total, nchan] buffer.
+    (:2233-2242) fused into the kernel epilogue: every rank owns an ``InterferometerArray`` over its share of the
+    baselines (interleaved by default, ``shard_rows``; ``interleave=False`` gives the reference's contiguous chunks)
+    whose phase-sum kernel stores straight into its rows of rank `dst`'s [nbl_total, nchan] buffer.
 
         so = ShardedObserver(InterferometerArray, labels, baselines, channels, device=local_rank, ...)
         full = so.observe(timeobj, Tsysinfo, bandpass, pointing, skymodel, t_acc)    # rank dst: [nbl_total, nchan] CUDA tensor
@@ -203,18 +236,22 @@ class ShardedObserver(object):
     ``observe`` returns the gathered snapshot on `dst` (a view of the gather buffer, valid until the next call) and
     None elsewhere; ``so.ia`` is the rank-local array (noise / delay transforms stay local: channels are unsplit)."""
 
-    def __init__(self, cls, labels, baselines, channels, dst=0, group=None, force_nccl=False, **kwargs):
+    def __init__(self, cls, labels, baselines, channels, dst=0, group=None, force_nccl=False, interleave=True, **kwargs):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dst = dst
         baselines = NP.asarray(baselines)
         self.nbl_total = baselines.shape[0]
+        self.interleave = bool(interleave)
         self.bounds = shard_bounds(self.nbl_total, self.world)
-        self.ia = make_sharded_array(cls, labels, baselines, channels, rank=self.rank, world_size=self.world, **kwargs)
+        self.rows = shard_rows(self.nbl_total, self.world, self.rank, self.interleave)
+        self.ia = make_sharded_array(cls, labels, baselines, channels, rank=self.rank, world_size=self.world, interleave=self.interleave,
+                                     **kwargs)
         self.gbuf = None
         if self.world > 1:
             self.gbuf = PeerGatherBuffer((self.nbl_total, self.ia.channels.size), self.ia.device, dst=dst, group=group,
-                                         row_bounds=self.bounds, force_nccl=force_nccl)
+                                         row_bounds=None if self.interleave else self.bounds, interleave=self.interleave,
+                                         force_nccl=force_nccl)
 
     def observe(self, *args, **kwargs):
         if self.gbuf is None:

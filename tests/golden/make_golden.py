@@ -124,6 +124,9 @@ def spectral_axis(length, delx=1.0, shift=False, use_real=False):
 def downsampler(inp, factor, axis=-1, verbose=True, method="interp", kind="linear", fill_value=NP.nan):
     inp = NP.asarray(inp)
     n = inp.shape[axis]
+    if method in ("FFT", "fft"):        # [AU-memory]: Fourier resampling to round(n / factor) samples
+        from scipy import signal
+        return signal.resample(inp, int(NP.round(n / factor)), axis=axis)
     f = interpolate.interp1d(NP.arange(n), inp, kind=kind, axis=axis, bounds_error=False, fill_value=fill_value)
     return f(NP.arange(0, n, factor))
 
@@ -149,7 +152,19 @@ def window_N2width(n_window=None, shape="rect", area_normalize=True, power_norma
     sum(w / max w) / N on a long window (rect 1.0, bhw 0.35875, bnw 0.3635819)."""
     n = 1000000 if n_window is None else int(n_window)
     w = windowing(n, shape=shape) ** fftpow
-    return NP.sum(w / w.max()) / n
+    w = w / w.max()
+    if power_normalize and not area_normalize:          # [AU-memory]: equivalent width of the POWER window
+        return NP.sum(w ** 2) / n
+    return NP.sum(w) / n
+
+
+def window_fftpow(N_window, shape="rect", pad_width=0, pad_value=0.0, fftpow=1.0, centering=True, peak=None, area_normalize=False,
+                  power_normalize=False, verbose=True):
+    """DSP.window_fftpow [AU-memory] for fftpow = 1 only (the PRISim default): the plain window."""
+    if fftpow != 1.0:
+        raise NotImplementedError("window_fftpow stub: fftpow != 1 is not restated")
+    return windowing(N_window, shape=shape, centering=centering, area_normalize=area_normalize, power_normalize=power_normalize,
+                     peak=1.0 if peak is None else peak)
 
 
 def find_1NN(ref, inp, distance_ULIM=NP.inf, remove_oob=True):
@@ -184,7 +199,7 @@ def install_stubs():
     au.geometry = _mod("astroutils.geometry", altaz2dircos=altaz2dircos, dircos2altaz=dircos2altaz, hadec2altaz=hadec2altaz,
                        altaz2hadec=altaz2hadec, sphdist=sphdist, xyz2enu=xyz2enu, enu2xyz=enu2xyz, spherematch=spherematch)
     au.DSP_modules = _mod("astroutils.DSP_modules", FT1D=FT1D, spectral_axis=spectral_axis, downsampler=downsampler,
-                          windowing=windowing, window_N2width=window_N2width)
+                          windowing=windowing, window_N2width=window_N2width, window_fftpow=window_fftpow)
     au.catalog = _mod("astroutils.catalog", SkyModel=SkyModel)
     au.constants = _mod("astroutils.constants", Jy=1.0e-26, sday=0.99726958, rest_freq_HI=1420405751.77)
     for name in ("gridding_modules", "lookup_operations", "nonmathops", "mathops", "ephemeris_timing", "mpi_modules"):
@@ -243,7 +258,7 @@ class TimeObj(object):
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference not present; golden vectors can only be regenerated in the build container")
-    for alias, typ in (("int", int), ("float", float), ("bool", bool), ("complex", complex)):
+    for alias, typ in (("int", int), ("float", float), ("bool", bool), ("complex", complex), ("float_", NP.float64)):
         if alias not in NP.__dict__:
             setattr(NP, alias, typ)             # NP.int / NP.float were removed from numpy
     install_stubs()
@@ -412,6 +427,29 @@ def main():
             mw.update(skyvis_lag_rect=res["skyvis_lag"], lag_corr_length_rect=res["lag_corr_length"], bw_eff=bw_eff, freq_center=fc,
                       vis_noise_freq=ia.vis_noise_freq)
             NP.savez_compressed(os.path.join(OUT, "multiwin_hera.npz"), **mw)
+        if tag == "hera" and (not ONLY or "subband_hera" in ONLY):
+            # DelaySpectrum.subband_delay_transform (delay_spectrum.py:1842-2248), 'sim' branch: three Blackman-Harris sub-bands
+            # (one given out of order, one clipped by the band edge), pad 1.0; then one rectangular sub-band without padding
+            ds2 = DSM.DelaySpectrum(interferometer_array=ia)
+            sb = {}
+            bw_sb = NP.asarray([0.9e6, 0.7e6, 1.1e6]); fc_sb = NP.asarray([chans[20] + 1.0e4, chans[9], chans[29] - 2.0e4])
+            args = dict(freq_center={"cc": fc_sb.copy(), "sim": fc_sb.copy()}, shape={"cc": "bhw", "sim": "bhw"},
+                        pad={"cc": 1.0, "sim": 1.0}, verbose=False)
+            r = ds2.subband_delay_transform({"cc": bw_sb.copy(), "sim": bw_sb.copy()}, action="return_oversampled", **args)["sim"]
+            for k in ("freq_wts", "lags", "skyvis_lag", "vis_lag", "vis_noise_lag", "lag_kernel", "lag_corr_length"):
+                sb["bhw_" + k] = r[k]
+            r = ds2.subband_delay_spectra_resampled["sim"]
+            for k in ("lags", "skyvis_lag", "vis_lag", "vis_noise_lag", "lag_kernel", "lag_corr_length"):
+                sb["bhw_rs_" + k] = r[k]
+            r = ds2.subband_delay_transform({"cc": NP.asarray([1.3e6]), "sim": NP.asarray([1.3e6])},
+                                            freq_center={"cc": NP.asarray([chans[15]]), "sim": NP.asarray([chans[15]])},
+                                            pad={"cc": 0.0, "sim": 0.0}, action="return_resampled", verbose=False)["sim"]
+            for k in ("lags", "skyvis_lag", "lag_kernel", "lag_corr_length"):
+                sb["rect_rs_" + k] = r[k]
+            sb.update(bw_eff=bw_sb, freq_center=fc_sb, rect_freq_wts=ds2.subband_delay_spectra["sim"]["freq_wts"],
+                      rect_skyvis_lag=ds2.subband_delay_spectra["sim"]["skyvis_lag"],
+                      skyvis_freq=ia.skyvis_freq, vis_freq=ia.vis_freq, vis_noise_freq=ia.vis_noise_freq, bp=ia.bp, chans=chans)
+            NP.savez_compressed(os.path.join(OUT, "subband_hera.npz"), **sb)
         if tag == "hera" and (not ONLY or "rotate_hera" in ONLY):
             # rotate_visibilities = phase_centering + project_baselines (interferometry.py:7655-7995), twice:
             # to a fixed HA/Dec, then to an RA/Dec that differs per snapshot

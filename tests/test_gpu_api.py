@@ -331,6 +331,52 @@ def test_multi_window_delay_transform_against_reference_golden():
         ia.multi_window_delay_transform("wide")
 
 
+def test_subband_delay_transform_against_reference_golden():
+    """DelaySpectrum.subband_delay_transform (delay_spectrum.py:1842-2248) against the reference's own run: full-resolution and
+    resampled products, window bookkeeping, argument checks."""
+    from prisim_b200.delay_spectrum import DelaySpectrum
+    from prisim_b200.interferometry import InterferometerArray
+    g = NP.load(os.path.join(GOLD, "observe_hera.npz"))
+    m = NP.load(os.path.join(GOLD, "subband_hera.npz"))
+    chans = m["chans"]
+    nbl, nchan, nsnap = m["skyvis_freq"].shape
+    from prisim_b200 import engine
+    ia = InterferometerArray([("B{0}".format(i), "A{0}".format(i)) for i in range(nbl)], g["bl"], chans, telescope=dict(OBSERVE_CASES["hera"]["telescope"]),
+                             latitude=float(g["latitude"]), skycoords="hadec", pointing_coords="hadec", freq_scale="Hz", device=0, noise_seed=5)
+    # the reference's own frequency-domain products, so that the comparison isolates the sub-band transform
+    for t in range(nsnap):
+        ia._skyvis.append(engine._c128(NP.ascontiguousarray(m["skyvis_freq"][:, :, t]), 0)); ia._vis.append(engine._c128(NP.ascontiguousarray(m["vis_freq"][:, :, t]), 0))
+        ia._noise.append(engine._c128(NP.ascontiguousarray(m["vis_noise_freq"][:, :, t]), 0)); ia._bp.append(engine._f64(NP.ascontiguousarray(m["bp"][:, :, t]), 0))
+    ds = DelaySpectrum(interferometer_array=ia)
+    args = dict(freq_center={"sim": m["freq_center"]}, shape={"sim": "bhw"}, pad={"sim": 1.0}, verbose=False)
+    r = ds.subband_delay_transform({"sim": m["bw_eff"]}, action="return_oversampled", **args)["sim"]
+    assert NP.abs(r["freq_wts"] - m["bhw_freq_wts"]).max() <= 1e-13 and NP.allclose(r["lags"], m["bhw_lags"], rtol=0, atol=1e-18)
+    assert NP.allclose(r["lag_corr_length"], m["bhw_lag_corr_length"], rtol=1e-12) and r["npad"] == nchan
+    for name in ("skyvis_lag", "vis_lag", "vis_noise_lag", "lag_kernel"):
+        ref = m["bhw_" + name]
+        assert r[name].shape == ref.shape and NP.abs(r[name] - ref).max() <= 1e-11 * NP.abs(ref).max(), name
+    rs = ds.subband_delay_spectra_resampled["sim"]
+    assert NP.allclose(rs["lags"], m["bhw_rs_lags"], rtol=0, atol=1e-18) and NP.allclose(rs["lag_corr_length"], m["bhw_rs_lag_corr_length"], rtol=1e-12)
+    assert NP.allclose(rs["lag_kernel"], m["bhw_rs_lag_kernel"], rtol=1e-10, atol=1e-11 * NP.nanmax(NP.abs(m["bhw_rs_lag_kernel"])), equal_nan=True)
+    for name in ("skyvis_lag", "vis_lag", "vis_noise_lag"):
+        ref = m["bhw_rs_" + name]
+        assert rs[name].shape == ref.shape and NP.abs(rs[name] - ref).max() <= 1e-10 * NP.abs(ref).max(), name
+    r2 = ds.subband_delay_transform({"sim": NP.asarray([1.3e6])}, freq_center={"sim": NP.asarray([chans[15]])}, pad={"sim": 0.0},
+                                    action="return_resampled", verbose=False)["sim"]
+    assert NP.abs(ds.subband_delay_spectra["sim"]["freq_wts"] - m["rect_freq_wts"]).max() <= 1e-13
+    assert NP.abs(ds.subband_delay_spectra["sim"]["skyvis_lag"] - m["rect_skyvis_lag"]).max() <= 1e-11 * NP.abs(m["rect_skyvis_lag"]).max()
+    assert NP.abs(r2["skyvis_lag"] - m["rect_rs_skyvis_lag"]).max() <= 1e-10 * NP.abs(m["rect_rs_skyvis_lag"]).max()
+    assert NP.allclose(r2["lags"], m["rect_rs_lags"], rtol=0, atol=1e-18)
+    with pytest.raises(TypeError):
+        ds.subband_delay_transform(1e6)
+    with pytest.raises(ValueError):
+        ds.subband_delay_transform({"sim": [1e6, 2e6]}, freq_center={"sim": [chans[5], chans[6], chans[7]]})
+    with pytest.raises(ValueError):
+        ds.subband_delay_transform({"sim": 1e6}, freq_center={"sim": chans[0]})
+    with pytest.raises(NotImplementedError):
+        ds.subband_delay_transform({"sim": 1e6}, fftpow={"sim": 2.0})
+
+
 def test_duplicate_measurements_against_reference_golden():
     """Unique baselines -> redundant sets (interferometry.py:6823-6907), replaying the reference's own run."""
     from prisim_b200.interferometry import InterferometerArray, SimpleTime

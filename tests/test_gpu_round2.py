@@ -183,19 +183,23 @@ def _two_gpu_worker(rank, port, q):
         full = so.observe(*args)
         res["mode"] = so.gbuf.mode
         # (2) every rank's block computed into private memory, gathered over NCCL: must be the same bits
-        ia = make_sharded_array(InterferometerArray, labels, bl, chans, **kw)
+        ia = make_sharded_array(InterferometerArray, labels, bl, chans, interleave=True, **kw)
         ia.observe(*args)
-        priv = gather_baseline_shards(ia.skyvis_freq_device(0), bl.shape[0], dst=0)
+        priv = gather_baseline_shards(ia.skyvis_freq_device(0), bl.shape[0], dst=0, interleave=True)
         # (3) the NCCL fallback of the gather buffer
         so2 = ShardedObserver(InterferometerArray, labels, bl, chans, force_nccl=True, **kw)
         full2 = so2.observe(*args)
         res["mode2"] = so2.gbuf.mode
         # noise is keyed by the global baseline index: sharded == unsharded, bit for bit
         so.ia.generate_noise()
-        nz = gather_baseline_shards(so.ia._noise[0], bl.shape[0], dst=0)
+        nz = gather_baseline_shards(so.ia._noise[0], bl.shape[0], dst=0, interleave=True)
+        # the reference's contiguous chunks (interleave=False) give the same gathered array
+        so3 = ShardedObserver(InterferometerArray, labels, bl, chans, interleave=False, **kw)
+        full3 = so3.observe(*args)
         if rank == 0:
             res["peer_equals_private"] = bool(torch.equal(full, priv))
             res["nccl_equals_peer"] = bool(torch.equal(full2, full))
+            res["blocks_vs_interleaved"] = float(((full3 - full).abs() / full.abs().pow(2).mean(dim=1, keepdim=True).sqrt()).max().item())
             one = InterferometerArray(labels, bl, chans, **kw)
             one.observe(*args)
             V1 = one.skyvis_freq_device(0)
@@ -210,7 +214,7 @@ def _two_gpu_worker(rank, port, q):
                                        dict(S.HERA_TELESCOPE), sp["flux-scale"], sp["power-law-index"], sp["freq-ref"])
             got = full[torch.as_tensor(rows).cuda()].cpu().numpy()
             res["oracle_err"] = float((NP.abs(got - Vo) / NP.sqrt(NP.mean(NP.abs(Vo) ** 2, axis=1, keepdims=True))).max())
-        so.close(); so2.close()
+        so.close(); so2.close(); so3.close()
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, res))
@@ -240,4 +244,5 @@ def test_sharded_observer_two_gpus_peer_gather_and_nccl_fallback():
     print("two-GPU gather:", r0)
     assert r0["mode"] == "peer" and r0["mode2"] == "nccl"
     assert r0["peer_equals_private"] and r0["nccl_equals_peer"] and r0["noise_equal"]
+    assert r0["blocks_vs_interleaved"] <= TOL
     assert r0["sharded_vs_unsharded"] <= TOL and r0["oracle_err"] <= TOL         # two fp32 results, each within tolerance of the truth

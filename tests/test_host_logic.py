@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), "symbol {0} declared in the header is not exported".format(name)
         assert name in _lib.SYMBOLS, "symbol {0} has no ctypes prototype".format(name)
     assert set(_lib.SYMBOLS) == declared
-    assert lib.pb200_version() == 100
+    assert lib.pb200_version() == 200          # round 2: pb200_skyvis gained nsrc_bright + vis_row_stride, pb200_noise bl_step
 
 
 def test_struct_layouts_match_header_sizes():

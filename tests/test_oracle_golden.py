@@ -260,6 +260,34 @@ def test_multi_window_delay_transform_matches_reference():
         O.multi_window_weights(g["chans"], 1e6, g["chans"][0])
 
 
+def test_subband_delay_transform_matches_reference():
+    """delay_spectrum.py:1842-2248 ('sim' branch) run by the reference's own DelaySpectrum (astroutils window helpers and the
+    FFT downsampler stubbed, [AU-memory])."""
+    m = _load("subband_hera.npz")
+    df = m["chans"][1] - m["chans"][0]
+    wts = O.subband_weights(m["chans"], m["bw_eff"], m["freq_center"], "bhw")
+    assert NP.abs(wts - m["bhw_freq_wts"]).max() <= 1e-13
+    out = {}
+    for name, x in (("skyvis_lag", m["skyvis_freq"]), ("vis_lag", m["vis_freq"]), ("vis_noise_lag", m["vis_noise_freq"]),
+                    ("lag_kernel", NP.ones_like(m["bp"]))):
+        out[name], lags, corr = O.subband_delay_transform(x, m["bp"], wts, df, pad=1.0)
+        ref = m["bhw_" + name]
+        assert out[name].shape == ref.shape and NP.abs(out[name] - ref).max() <= 1e-12 * NP.abs(ref).max(), name
+    assert NP.allclose(lags, m["bhw_lags"], rtol=0, atol=1e-18) and NP.allclose(corr, m["bhw_lag_corr_length"], rtol=1e-12)
+    rl, rk, rs, rc = O.subband_resample(lags, out["lag_kernel"], [out["skyvis_lag"], out["vis_lag"], out["vis_noise_lag"]], m["bw_eff"],
+                                        lags.size * df)
+    assert NP.allclose(rl, m["bhw_rs_lags"], rtol=0, atol=1e-18) and NP.allclose(rc, m["bhw_rs_lag_corr_length"], rtol=1e-12)
+    assert NP.allclose(rk, m["bhw_rs_lag_kernel"], rtol=1e-11, atol=1e-12 * NP.nanmax(NP.abs(rk)), equal_nan=True)
+    for got, name in zip(rs, ("skyvis_lag", "vis_lag", "vis_noise_lag")):
+        ref = m["bhw_rs_" + name]
+        assert got.shape == ref.shape and NP.abs(got - ref).max() <= 1e-11 * NP.abs(ref).max(), name
+    # rectangular window, no padding
+    wr = O.subband_weights(m["chans"], [1.3e6], [m["chans"][15]], "rect")
+    assert NP.abs(wr - m["rect_freq_wts"]).max() <= 1e-13
+    lag, lags0, _ = O.subband_delay_transform(m["skyvis_freq"], m["bp"], wr, df, pad=0.0)
+    assert NP.abs(lag - m["rect_skyvis_lag"]).max() <= 1e-12 * NP.abs(lag).max()
+
+
 ROI_CASES = [("zenith_achromatic", {"radius": None, "center": None, "center_coords": None}),
              ("zenith_r30_chromatic", {"radius": 30.0, "center": None, "center_coords": None, "pbeam_chromaticity": True}),
              ("offzenith_altaz_reffreq", {"radius": 25.0, "center": NP.asarray([60.0, 140.0]), "center_coords": "altaz", "pbeam_reffreq": 151.3e6}),
