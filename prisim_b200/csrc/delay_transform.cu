@@ -314,9 +314,24 @@ __global__ void __launch_bounds__(32 * W32_WARPS, 2) k_delay_fft_w32(const Delay
   double2* tile = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * 32 * W32_STRIDE;
   const int row = blockIdx.x * W32_WARPS + warp;
   if (row >= P.nrows) return;                  // warp-uniform; no CTA barrier below
+  // all 32 loads of the lane in flight together (the kernel is bound by memory latency: 8 warps per SM); the window is
+  // applied afterwards from the (L1-resident) weight row(s), zero padding by a zero weight
   double2 v[32];
+  if (HAS_X) {
+    const double2* xrow = P.x + (size_t)row * P.nchan + lane;
 #pragma unroll
-  for (int b = 0; b < 32; ++b) v[b] = load_in_nb<HAS_X>(P, row, lane + 32 * b);
+    for (int b = 0; b < 32; ++b) v[b] = lane + 32 * b < P.nchan ? xrow[32 * b] : make_double2(0.0, 0.0);
+  }
+  {
+    const double* brow = P.bp + (size_t)row * P.bp_stride + lane;
+    const double* wrow = P.wts ? P.wts + (size_t)row * P.wts_stride + lane : nullptr;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      double m = 0.0;
+      if (lane + 32 * b < P.nchan) { m = brow[32 * b]; if (wrow) m *= wrow[32 * b]; }
+      v[b] = HAS_X ? make_double2(v[b].x * m, v[b].y * m) : make_double2(m, 0.0);
+    }
+  }
   ifft32(v);                                   // v[c] = sum_b x[a + 32 b] W32^(b c)
   {
     // twiddles W^(a c), W = exp(2 pi i / 1024): four chains c = c0, c0 + 4, ... stepped by W^(4 a)

@@ -53,6 +53,10 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
                            // argument increment.  Measured on config 2, all 6e7 cells (tools/err_c2.py, profiles/err_variants_r02.txt), with
                            // brightest-first ordering: 0 -> 4.55 Tterms/s, max error 6.4e-6;  1 -> 4.50, 4.4e-6;  2 -> 4.64, 4.4e-6;
                            // 2 with PB_FLUSH_TILES = 8 -> 4.62, 3.0e-6 (the default);  re-anchoring every 16 channels bought nothing (4.31, 4.2e-6)
+#ifndef PB_L2_HINTS        // L2 cache policies.  1: the fp64 running sums are read and written evict-last, so that the amplitude stream (0.73 GB per
+#define PB_L2_HINTS 1      // wave) does not push the 39 MB of live running sums out to DRAM (measured per config-2 launch: 57 -> 1.5 GB written).
+#endif                     // 2: additionally the amplitude stream is loaded evict-first -- WORSE: the CTAs of a wave share every amplitude tile
+                           // through L2, and evict-first drops it before the last of them has read it (100 -> 296 GB read, 1.6 % slower).
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
 #define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
 #endif
@@ -200,15 +204,36 @@ struct SegmentIter {
 // (the [nbl][nchan] output layout would put the 32 lanes 16 KB apart); k_skyvis_finalize transposes the scratch into
 // the output once at the end.  `first`: the slot holds nothing yet -- store instead of read-modify-write (no memset
 // of the scratch, one read less).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double2 ld_keep(const double2* p, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_keep(double2* p, double2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void flush_acc(const SkyvisParams& P, size_t slot, bool first, float2 (&acc_re)[KT / 2],
                                           float2 (&acc_im)[KT / 2]) {
   double2* base = P.accum + ((slot * NWARPS + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
+  const uint64_t keep = PB_L2_HINTS ? l2_policy_evict_last() : 0;
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
-    double2 v = first ? make_double2(0.0, 0.0) : base[k * 32];
+    double2 v = first ? make_double2(0.0, 0.0) : (PB_L2_HINTS ? ld_keep(base + k * 32, keep) : base[k * 32]);
     v.x += (double)((k & 1) ? acc_re[k >> 1].y : acc_re[k >> 1].x);
     v.y += (double)((k & 1) ? acc_im[k >> 1].y : acc_im[k >> 1].x);
-    base[k * 32] = v;
+    if (PB_L2_HINTS) st_keep(base + k * 32, v, keep);
+    else base[k * 32] = v;
   }
 #pragma unroll
   for (int k = 0; k < KT / 2; ++k) { acc_re[k] = make_float2(0.f, 0.f); acc_im[k] = make_float2(0.f, 0.f); }
@@ -322,10 +347,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   auto issue = [&](int i, int stage) {                 // source tile sg.s0 + i of this segment
     const size_t row0 = (size_t)(sg.s0 + i) * T;
     mbar_expect_tx(&full[stage], (uint32_t)(nsl * sizeof(float) * T * PB200_SLAB + sizeof(double) * T * 4));
-    for (int j = 0; j < nsl; ++j)
-      tma_bulk_g2s(&tin[stage].amp[j][0][0],
-                   (const float*)P.amp + ((size_t)(tile_x * SPC + j) * P.nsrc_pad + row0) * PB200_SLAB,
-                   sizeof(float) * T * PB200_SLAB, &full[stage]);
+    const uint64_t stream_pol = PB_L2_HINTS == 2 ? l2_policy_evict_first() : 0;
+    for (int j = 0; j < nsl; ++j) {
+      const float* src = (const float*)P.amp + ((size_t)(tile_x * SPC + j) * P.nsrc_pad + row0) * PB200_SLAB;
+      if (PB_L2_HINTS == 2) tma_bulk_g2s_hint(&tin[stage].amp[j][0][0], src, sizeof(float) * T * PB200_SLAB, &full[stage], stream_pol);
+      else tma_bulk_g2s(&tin[stage].amp[j][0][0], src, sizeof(float) * T * PB200_SLAB, &full[stage]);
+    }
     tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T * 4, &full[stage]);
   };
   if (tid == 0) {
@@ -777,44 +804,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
       issue(0, fill & 1);
       if (ntiles > 1) issue(1, (fill + 1) & 1);
     }
-    // cooperative stage of sub-tile `sub` (sources sub*TS .. sub*TS+TS-1) of source tile `tile`: thread (wc, bcol) does source wc
+    // cooperative stage of sub-tile `sub` (sources sub*TS .. sub*TS+TS-1) of source tile `tile`.  Without the taper TS = 8 and
+    // thread (wc, bcol) does source wc; with it TS = 4 and the work of a (source, baseline) pair is split over two threads so
+    // that all 16 warps carry a similar load before the barrier: warps wc < 4 the phasor part of source wc, warps wc >= 4 the
+    // taper part of source wc - 4.
     auto stage_sub = [&](int tile, int sub) {
       const int st = (fill + tile) & 1;
       if (sub == 0) mbar_wait(&full[st], ((fill + tile) >> 1) & 1);
-      if (wc >= TS) return;
       const int buf = (tile * NSUB + sub) & 1;
-      const double4 g = *reinterpret_cast<const double4*>(&tin[st].geom[sub * TS + wc][0]);
+      const int ss = TAPER ? (wc & (TS - 1)) : wc;                           // source of the sub-tile this thread works on
+      const bool do_phasor = !TAPER || wc < TS, do_taper = TAPER && wc >= TS;
+      const double4 g = *reinterpret_cast<const double4*>(&tin[st].geom[sub * TS + ss][0]);
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
-      const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
-      double sn, cs;
-      sincospi(2.0 * frac_turns(tau * df), &sn, &cs);
-      const double2 r = make_double2(cs, -sn);
-      pre[buf].rot[wc][bcol] = r;
-      sincospi(2.0 * frac_turns(tau * fs0), &sn, &cs);
-      double2 a = make_double2(cs, -sn);
-      double2 r16 = r;
+      if (do_phasor) {
+        const double tau = tau_g - G.tau_pc;                                // interferometry.py:6332
+        double sn, cs;
+        sincospi(2.0 * frac_turns(tau * df), &sn, &cs);
+        const double2 r = make_double2(cs, -sn);
+        pre[buf].rot[ss][bcol] = r;
+        sincospi(2.0 * frac_turns(tau * fs0), &sn, &cs);
+        double2 a = make_double2(cs, -sn);
+        double2 r16 = r;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r16 = make_double2(fma(r16.x, r16.x, -r16.y * r16.y), 2.0 * r16.x * r16.y);
-      pre[buf].anc[wc][0][bcol] = a;
+        for (int i = 0; i < 4; ++i) r16 = make_double2(fma(r16.x, r16.x, -r16.y * r16.y), 2.0 * r16.x * r16.y);
+        pre[buf].anc[ss][0][bcol] = a;
 #pragma unroll
-      for (int j = 1; j < WC64; ++j) {
-        a = make_double2(fma(-a.y, r16.y, a.x * r16.x), fma(a.y, r16.x, a.x * r16.y));
-        pre[buf].anc[wc][j][bcol] = a;
+        for (int j = 1; j < WC64; ++j) {
+          a = make_double2(fma(-a.y, r16.y, a.x * r16.x), fma(a.y, r16.x, a.x * r16.y));
+          pre[buf].anc[ss][j][bcol] = a;
+        }
       }
-      if (TAPER) {
+      if (do_taper) {
         // w_k = exp2(-kap F_k^2), F_k = F0 + k dF in units of 1e8 Hz (interferometry.py:6262-6283; g.w folds ln2 d^2 1e16 log2 e,
         // sqrt argument clamped at 0).  Block starts k = 16 j by the chain  w <- w X, X <- X Y;  g <- g Z.
         const double kap = g.w * fmax(G.blen2 - tau_g * tau_g, 0.0);
         double w = exp2(-kap * tF0 * tF0);
-        double X = exp2(-kap * 16.0 * tdF * (2.0 * tF0 + 16.0 * tdF));
-        const double Y = exp2(-512.0 * kap * tdF * tdF);
         double gk = exp2(-kap * tdF * (2.0 * tF0 + tdF));
-        const double Z = exp2(-32.0 * kap * tdF * tdF);
-        pret[buf].hm1[wc][bcol] = expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
+        const double hm1 = expm1(-2.0 * kap * tdF * tdF * 0.69314718055994530942);
+        pret[buf].hm1[ss][bcol] = hm1;
+        // the block-level ratios from powers of h = g_{k+1} / g_k and g_0 instead of three more exp2:
+        //   Z = h^16 (g at the next block start), Y = h^256, X = g_0^16 h^120 (w at the next block start)
+        const double h = 1.0 + hm1;
+        const double h2 = h * h, h4 = h2 * h2, h8 = h4 * h4, Z = h8 * h8;
+        const double h32 = Z * Z, h64 = h32 * h32, h128 = h64 * h64, Y = h128 * h128;
+        const double g2 = gk * gk, g4 = g2 * g2, g8 = g4 * g4;
+        double X = (g8 * g8) * ((h64 * h32) * (Z * h8));
 #pragma unroll
         for (int j = 0; j < WC64; ++j) {
-          pret[buf].w[wc][j][bcol] = w;
-          pret[buf].g[wc][j][bcol] = gk;
+          pret[buf].w[ss][j][bcol] = w;
+          pret[buf].g[ss][j][bcol] = gk;
           w *= X; X *= Y; gk *= Z;
         }
       }

@@ -233,10 +233,12 @@ class ShardedObserver(object):
         so = ShardedObserver(InterferometerArray, labels, baselines, channels, device=local_rank, ...)
         full = so.observe(timeobj, Tsysinfo, bandpass, pointing, skymodel, t_acc)    # rank dst: [nbl_total, nchan] CUDA tensor
 
-    ``observe`` returns the gathered snapshot on `dst` (a view of the gather buffer, valid until the next call) and
-    None elsewhere; ``so.ia`` is the rank-local array (noise / delay transforms stay local: channels are unsplit)."""
+    ``observe`` returns the gathered snapshot on `dst` (a view of one of `nbuf` gather buffers used in turn, so it stays
+    valid for the next nbuf - 1 calls: with the default 2 the device->host copy of snapshot j can overlap the kernels of
+    snapshot j + 1) and None elsewhere; ``so.ia`` is the rank-local array (noise / delay transforms stay local: channels
+    are unsplit)."""
 
-    def __init__(self, cls, labels, baselines, channels, dst=0, group=None, force_nccl=False, interleave=True, **kwargs):
+    def __init__(self, cls, labels, baselines, channels, dst=0, group=None, force_nccl=False, interleave=True, nbuf=2, **kwargs):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.dst = dst
@@ -247,22 +249,30 @@ class ShardedObserver(object):
         self.rows = shard_rows(self.nbl_total, self.world, self.rank, self.interleave)
         self.ia = make_sharded_array(cls, labels, baselines, channels, rank=self.rank, world_size=self.world, interleave=self.interleave,
                                      **kwargs)
-        self.gbuf = None
+        self.gbufs, self._turn = [], 0
         if self.world > 1:
-            self.gbuf = PeerGatherBuffer((self.nbl_total, self.ia.channels.size), self.ia.device, dst=dst, group=group,
-                                         row_bounds=None if self.interleave else self.bounds, interleave=self.interleave,
-                                         force_nccl=force_nccl)
+            for _ in range(max(1, int(nbuf))):
+                self.gbufs.append(PeerGatherBuffer((self.nbl_total, self.ia.channels.size), self.ia.device, dst=dst, group=group,
+                                                   row_bounds=None if self.interleave else self.bounds, interleave=self.interleave,
+                                                   force_nccl=force_nccl))
+
+    @property
+    def gbuf(self):
+        """the gather buffer the next observe() will fill"""
+        return self.gbufs[self._turn % len(self.gbufs)] if self.gbufs else None
 
     def observe(self, *args, **kwargs):
-        if self.gbuf is None:
+        if not self.gbufs:
             self.ia.observe(*args, **kwargs)
             return self.ia.skyvis_freq_device(-1)
-        self.ia.next_skyvis_out = self.gbuf.local            # the kernel epilogue writes into the writing rank's buffer
+        g = self.gbuf
+        self._turn += 1
+        self.ia.next_skyvis_out = g.local                    # the kernel epilogue writes into the writing rank's buffer
         self.ia.observe(*args, **kwargs)
-        self.gbuf.wait()
-        return self.gbuf.full if self.rank == self.dst else None
+        g.wait()
+        return g.full if self.rank == self.dst else None
 
     def close(self):
-        if self.gbuf is not None:
-            self.gbuf.close()
-            self.gbuf = None
+        for g in self.gbufs:
+            g.close()
+        self.gbufs = []

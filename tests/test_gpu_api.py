@@ -365,7 +365,8 @@ def test_subband_delay_transform_against_reference_golden():
                                     action="return_resampled", verbose=False)["sim"]
     assert NP.abs(ds.subband_delay_spectra["sim"]["freq_wts"] - m["rect_freq_wts"]).max() <= 1e-13
     assert NP.abs(ds.subband_delay_spectra["sim"]["skyvis_lag"] - m["rect_skyvis_lag"]).max() <= 1e-11 * NP.abs(m["rect_skyvis_lag"]).max()
-    assert NP.abs(r2["skyvis_lag"] - m["rect_rs_skyvis_lag"]).max() <= 1e-10 * NP.abs(m["rect_rs_skyvis_lag"]).max()
+    # (this window sits mid-band, so its Fourier-resampled spectrum is numerically zero in the reference as well: absolute tolerance)
+    assert NP.abs(r2["skyvis_lag"] - m["rect_rs_skyvis_lag"]).max() <= 1e-12 * NP.abs(m["rect_skyvis_lag"]).max()
     assert NP.allclose(r2["lags"], m["rect_rs_lags"], rtol=0, atol=1e-18)
     with pytest.raises(TypeError):
         ds.subband_delay_transform(1e6)

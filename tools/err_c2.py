@@ -38,4 +38,11 @@ for mode in sys.argv[1:] or ["plain"]:
     print("%-28s %-12s bright=%6d  %.1f ms  %.3f Tterms/s   max %.3e  p99.9(bl) %.3e  median(bl) %.3e  rms %.3e" % (
         os.path.basename(os.environ.get("PB200_LIB", "default")), mode, nb, ms, nsrc * bl.shape[0] * 1024 / ms / 1e9,
         emax.max().item(), emax.quantile(0.999).item(), emax.median().item(), err.pow(2).mean().sqrt().item()), flush=True)
+    # absolute error in units of the incoherent norm A2 = sqrt(mean_f sum_s a^2): what the 'auto' cancellation threshold rests on
+    a2 = torch.sqrt(amp.double().square().sum() / 1024)
+    ratio = (rms_b.flatten() / a2)
+    abs_a2 = ((V - V64).abs().amax(dim=1) / a2)
+    print("    A2 = %.4g; max |dV|/A2 = %.3e (p99.9 %.3e); baselines with rms_b/A2 < 0.45 / 0.3 / 0.2 / 0.15 / 0.1: %d / %d / %d / %d / %d; worst err/rms_b among rms_b/A2 >= 0.2: %.3e" % (
+        a2.item(), abs_a2.max().item(), abs_a2.quantile(0.999).item(), (ratio < 0.45).sum().item(), (ratio < 0.3).sum().item(),
+        (ratio < 0.2).sum().item(), (ratio < 0.15).sum().item(), (ratio < 0.1).sum().item(), emax[ratio >= 0.2].max().item()), flush=True)
     del amp, V
