@@ -471,19 +471,18 @@ def run_config2(env, pipeline=False):
             dst.copy_(src, non_blocking=True)
 
         def e2e_step():
-            ia._skyvis, ia._bp, ia._Tsys, ia.timestamp, ia.t_acc, ia.lst = [], [], [], [], [], []     # keep one snapshot resident
-            ia.obs_catalog_indices, ia._drained, ia.n_acc = [], 0, 0
             k = turn[0] % 2
             turn[0] += 1
             if copy_done[k] is not None:
-                copy_done[k].synchronize()                    # the pinned set (and gather buffer) used two snapshots ago is free again
+                copy_done[k].synchronize()                    # pinned set / gather buffer / product ring slot k (used two snapshots ago) are free again
             hk = host2[k]
             targs = (SimpleTime(2451545.0, lst_deg), tsysinfo, NP.ones(nchan), cfg["pointing_hadec"], sky, cfg["t_acc"])
-            full = so.observe(*targs) if so is not None else (ia.observe(*targs), ia.skyvis_freq_device(0))[1]
+            full = so.observe(*targs) if so is not None else (ia.observe(*targs), ia.skyvis_freq_device(-1))[1]
             prods = []
-            if pipeline:        # noise + add + delay transforms on this rank's rows, streamed out
-                ia.drain(lambda j, prod: prods.extend(prod[key] for key in ("vis_freq", "vis_noise_freq", "skyvis_lag", "vis_lag", "vis_noise_lag")),
-                         noise=True, delay_transform={"pad": 1.0, "freq_wts": win_host})
+            # stream the snapshot out of the array (bounded memory); pipeline: noise + add + three delay transforms on this rank's
+            # rows into the array's preallocated product ring (slot = snapshot number % 2 = k)
+            ia.drain(lambda j, prod: prods.extend(prod[key] for key in ("vis_freq", "vis_noise_freq", "skyvis_lag", "vis_lag", "vis_noise_lag") if key in prod),
+                     noise=pipeline, delay_transform={"pad": 1.0, "freq_wts": win_host} if pipeline else None, ring=2)
             ready = torch.cuda.Event()
             ready.record()
             copy_stream.wait_event(ready)
@@ -491,7 +490,7 @@ def run_config2(env, pipeline=False):
                 if full is not None and hk[0].numel():
                     copy_out(hk[0], full, torch_owned=so is None or world == 1)   # ONE device->host copy of the snapshot, from the writing rank
                 for i, t in enumerate(prods):
-                    copy_out(hk[1 + i], t)
+                    copy_out(hk[1 + i], t, torch_owned=False)
                 copy_done[k] = torch.cuda.Event()
                 copy_done[k].record()
 
@@ -671,7 +670,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per k_skyvis launch at the headline size (1 GPU), from the
 # committed ncu capture (profiles/); None until that capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = None
+TRAFFIC_BYTES_PER_LAUNCH = 86.0e9      # profiles/skyvis_dram_r02.txt: 64.9 GB read + 21.1 GB written (0.5 % of HBM bandwidth over 2.46 s)
 
 if __name__ == "__main__":
     main()

@@ -223,10 +223,12 @@ __device__ __forceinline__ void st_keep(double2* p, double2 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
 }
 
+// `last`: the segment is complete -- its sums are only read again by k_skyvis_finalize, so they are written evict-first
+// (a line that stayed tagged evict-last after its tile was done would squat in L2 for the rest of the launch).
 __device__ __forceinline__ void flush_acc(const SkyvisParams& P, size_t slot, bool first, float2 (&acc_re)[KT / 2],
-                                          float2 (&acc_im)[KT / 2]) {
+                                          float2 (&acc_im)[KT / 2], bool last = false) {
   double2* base = P.accum + ((slot * NWARPS + (threadIdx.x >> 5)) * KT) * 32 + (threadIdx.x & 31);
-  const uint64_t keep = PB_L2_HINTS ? l2_policy_evict_last() : 0;
+  const uint64_t keep = PB_L2_HINTS ? (last ? l2_policy_evict_first() : l2_policy_evict_last()) : 0;
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
     double2 v = first ? make_double2(0.0, 0.0) : (PB_L2_HINTS ? ld_keep(base + k * 32, keep) : base[k * 32]);
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       fresh = false;
     }
   }
-  if (live) flush_acc(P, sg.slot, fresh, acc_re, acc_im);
+  if (live) flush_acc(P, sg.slot, fresh, acc_re, acc_im, true);
   fill += (uint32_t)ntiles;
   }   // segments
 }
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
       if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
       if (sg.s0 + tile < P.bright_tiles || ((tile + 1) % FLUSH_TILES) == 0) { flush_acc(P, sg.slot, fresh, acc_re, acc_im); fresh = false; }
     }
-    flush_acc(P, sg.slot, fresh, acc_re, acc_im);
+    flush_acc(P, sg.slot, fresh, acc_re, acc_im, true);
     fill += (uint32_t)ntiles;
   }
 }

@@ -203,7 +203,7 @@ def _bcast_strides(t, nbl, nchan):
 
 
 def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, bl_offset=0, nbl_total=None, gains=None,
-          flux_unit_k=False, want=("rms", "noise", "vis"), device=None, bl_step=1):
+          flux_unit_k=False, want=("rms", "noise", "vis"), device=None, bl_step=1, out=None):
     """``pb200_noise`` for one snapshot.  tsys / aeff / effq are contiguous fp64 CUDA tensors of
     shape [nbl,nchan], [nchan], [nbl] or scalar (broadcast through strides).
     Replaces interferometry.py:6676-6693 and :6707-6722."""
@@ -211,9 +211,10 @@ def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, b
     ctx = get_context(device)
     nbl_total = nbl if nbl_total is None else int(nbl_total)
     dev = "cuda:{0}".format(device)
-    rms = torch.empty((nbl, nchan), dtype=torch.float64, device=dev) if "rms" in want else None
-    nz = torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "noise" in want else None
-    vis = torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "vis" in want else None
+    out = out or {}                                  # optional preallocated outputs {'rms', 'noise', 'vis'} (contiguous, right shape)
+    rms = out.get("rms", torch.empty((nbl, nchan), dtype=torch.float64, device=dev) if "rms" not in out else None) if "rms" in want else None
+    nz = out.get("noise", torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "noise" not in out else None) if "noise" in want else None
+    vis = out.get("vis", torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "vis" not in out else None) if "vis" in want else None
     st = []
     for t in (tsys, aeff, effq):
         st.extend(_bcast_strides(t, nbl, nchan))
@@ -225,12 +226,12 @@ def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, b
     return rms, nz, vis
 
 
-def add_noise(skyvis_t, noise_t, gains=None):
+def add_noise(skyvis_t, noise_t, gains=None, out=None):
     """``pb200_noise`` in add-only mode: vis = gains*skyvis + noise (interferometry.py:6722)."""
     device = skyvis_t.device.index
     ctx = get_context(device)
     nbl, nchan = skyvis_t.shape
-    vis = torch.empty_like(skyvis_t)
+    vis = torch.empty_like(skyvis_t) if out is None else out
     ctx.check(ctx.lib.pb200_noise(ctx.handle, _ptr(skyvis_t), None, None, None, None, _ptr(gains), int(nbl), int(nchan),
                                   1.0, 1.0, 0, 0, 0, 0, 1, nbl, 1, None, _ptr(noise_t), _ptr(vis), ctx.stream()))
     return vis
@@ -240,7 +241,7 @@ def delay_nout(nchan, pad=1.0, downsample=True):
     return int(_lib.load().pb200_delay_nout(int(nchan), float(pad), int(bool(downsample))))
 
 
-def delay_transform(x, bp, wts, df, pad=1.0, downsample=True, nrows=None, nchan=None, device=None):
+def delay_transform(x, bp, wts, df, pad=1.0, downsample=True, nrows=None, nchan=None, device=None, out=None):
     """``pb200_delay_transform``: x [nrows,nchan] complex128 or None; bp / wts [nrows,nchan] or
     [nchan] (broadcast) float64 or None.  Returns [nrows, nout] complex128.
     Replaces interferometry.py:8114-8134."""
@@ -256,7 +257,10 @@ def delay_transform(x, bp, wts, df, pad=1.0, downsample=True, nrows=None, nchan=
         return 0 if t.ndim == 1 or t.shape[0] == 1 else nchan
 
     nout = delay_nout(nchan, pad, downsample)
-    out = torch.empty((nrows, nout), dtype=torch.complex128, device="cuda:{0}".format(device))
+    if out is None:
+        out = torch.empty((nrows, nout), dtype=torch.complex128, device="cuda:{0}".format(device))
+    elif tuple(out.shape) != (nrows, nout) or out.dtype != torch.complex128 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous [nrows, nout] complex128 CUDA tensor")
     ctx.check(ctx.lib.pb200_delay_transform(ctx.handle, _ptr(x), _ptr(bp), stride(bp), _ptr(wts), stride(wts),
                                             int(nrows), int(nchan), float(df), float(pad), int(bool(downsample)),
                                             _ptr(out), ctx.stream()))

@@ -1350,7 +1350,7 @@ class InterferometerArray(object):
         self.add_noise()
 
     # ------------------------------------------------------------------ bounded-memory streaming
-    def drain(self, sink, noise=True, delay_transform=None):
+    def drain(self, sink, noise=True, delay_transform=None, ring=0):
         """Stream the resident snapshots out and free their device memory (a 1000-snapshot HERA-350 run is
         ~7.5 GB per snapshot with all products and cannot stay resident; the reference keeps growing numpy
         arrays, interferometry.py:6390).  For every resident snapshot: optionally generate noise + add it
@@ -1358,33 +1358,50 @@ class InterferometerArray(object):
         (``delay_transform=dict(pad=..., freq_wts=...)``), then call ``sink(j, products)`` with a dict of
         [nbl, n] CUDA tensors ('skyvis_freq', 'vis_freq', 'vis_noise_freq', 'vis_rms_freq', 'skyvis_lag', ...),
         and drop them.  Bookkeeping (timestamp, lst, t_acc, pointing centres, indices) is kept; snapshot numbering
-        continues."""
+        continues.
+
+        ``ring=n`` (n >= 1): the noise / delay-transform products are written into n preallocated buffer sets owned by
+        this object and used in turn (global snapshot j uses set j % n) instead of being allocated per snapshot: what
+        the sink receives stays valid until n more snapshots have been drained -- long enough for an asynchronous
+        device->host copy that overlaps the next snapshot -- and a long run makes no allocator calls at all."""
         base = getattr(self, "_drained", 0)
         nres = len(self._skyvis)
         if nres == 0:
             return 0
         if noise:
             aeff, effq = self._aeff_effq()
-            nbl, nchan = self.baselines.shape[0], self.channels.size
+        nbl, nchan = self.baselines.shape[0], self.channels.size
         getter = None
         if delay_transform is not None and delay_transform.get("freq_wts", None) is not None:
             getter = self._freq_wts_getter(delay_transform["freq_wts"])
+        pad = 1.0 if delay_transform is None else delay_transform.get("pad", 1.0)
+        nout = engine.delay_nout(nchan, pad, True) if delay_transform is not None else 0
+
+        def pooled(slot, name, shape, dtype):
+            pool = self.__dict__.setdefault("_drain_pool", {})
+            t = pool.get((slot, name))
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = pool[(slot, name)] = torch.empty(shape, dtype=dtype, device=self._dev_str())
+            return t
+
         for t in range(nres):
+            slot = (base + t) % ring if ring else None
+            buf = (lambda name, shape, dtype=torch.complex128: pooled(slot, name, shape, dtype)) if ring else (lambda *a, **k: None)
             prod = {"skyvis_freq": self._skyvis[t]}
             if self._gradient:
                 prod["gradient_" + self.gradient_mode] = self._gradient[t]
             if noise:
+                outs = {"rms": buf("rms", (nbl, nchan), torch.float64), "noise": buf("noise", (nbl, nchan))} if ring else None
                 rms, nz, _ = engine.noise(None, self._Tsys[t], aeff, effq, self.freq_resolution, self.t_acc[base + t],
                                           self.noise_seed, nbl, nchan, snapshot=base + t, bl_offset=self.bl_offset, bl_step=self.bl_step,
                                           nbl_total=self.nbl_total, flux_unit_k=(self.flux_unit.upper() == "K"),
-                                          want=("rms", "noise"), device=self.device)
-                prod.update(vis_rms_freq=rms, vis_noise_freq=nz, vis_freq=engine.add_noise(self._skyvis[t], nz))
+                                          want=("rms", "noise"), device=self.device, out=outs)
+                prod.update(vis_rms_freq=rms, vis_noise_freq=nz, vis_freq=engine.add_noise(self._skyvis[t], nz, out=buf("vis", (nbl, nchan))))
             if delay_transform is not None:
-                pad = delay_transform.get("pad", 1.0)
                 wts = None if getter is None else getter(base + t)          # per-snapshot weights are indexed by the global snapshot
                 for key in [k for k in ("skyvis_freq", "vis_freq", "vis_noise_freq") if k in prod]:
                     prod[key.replace("_freq", "_lag")] = engine.delay_transform(prod[key], self._bp[t], wts, self.freq_resolution,
-                                                                               pad=pad, downsample=True)
+                                                                               pad=pad, downsample=True, out=buf(key + "_lag", (nbl, nout)))
             sink(base + t, prod)
         self._skyvis, self._vis, self._noise, self._rms, self._bp, self._Tsys, self._gradient = [], [], [], [], [], [], []
         self._lag = {}
