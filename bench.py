@@ -2,7 +2,7 @@
 """Benchmark of the visibility hot path on BASELINE.json's configurations.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
-    python bench.py --config 3|5 ...                         (configs 3 and 5; default 2 = the headline)
+    python bench.py --config 3|4|5 ...                       (configs 3, 4 and 5; default 2 = the headline)
     python bench.py --impl reference ...                     (CPU arm: the reference's numpy path)
 
 Metric everywhere: Gterms/s, one term = one (source above horizon, baseline, channel) triple of one
@@ -18,6 +18,8 @@ snapshot.  One "step":
   config 3: one snapshot of the nside-256 diffuse sky (393k pixels above the horizon, extended sources ->
       taper) x HERA-331 x 256 channels through the fp64 kernel with the gridded-HEALPix beam; snapshots are
       dealt round-robin to the ranks (one snapshot per rank and step).
+  config 4: one snapshot of 128 MWA-like tiles (8,128 baselines) x 768 channels with the phased 4x4 tile beam (quantised delays,
+      ground plane) evaluated per source and channel inside the amplitude-table kernel; snapshots round-robin over ranks.
   config 5: observe + Tsys noise + add + three windowed delay transforms of one HERA-350 snapshot, streamed
       through InterferometerArray.drain; baseline-sharded over N ranks like config 2.
 
@@ -56,6 +58,8 @@ WORKLOADS = {
     2: "config2: HERA-350 (61,075 bl) x 1024 ch x 97.65625 kHz x 300k-src GLEAM-shaped catalogue, Airy 14 m, 1 snapshot",
     3: "config3: nside-256 diffuse sky (786,432 pixels, horizon-culled, extended sources) x HERA-331 (54,615 bl) x 256 ch x 390.625 kHz, "
        "gridded HEALPix beam (nside 128), fp64 kernel, 1 snapshot per GPU and step",
+    4: "config4: MWA Phase-II-like 128 tiles (8,128 bl) x 768 ch x 40 kHz x 50k-src catalogue, phased 4x4 dipole tile beam (quantised delays) "
+       "+ ground plane evaluated per source / channel / snapshot, 1 snapshot per GPU and step",
     5: "config5: HERA-350 x 1024 ch x 300k-src catalogue: visibilities + Tsys noise + three windowed delay transforms per snapshot",
 }
 NOMINAL_LANES = 148 * 128          # FP32 FMA lanes per clock on the whole chip
@@ -643,13 +647,100 @@ def run_config3(env):
         env.emit(line)
 
 
+# --------------------------------------------------------------------------------------------
+# config 4: MWA-like tiles, phased-array tile beam fused into the amplitude table
+# --------------------------------------------------------------------------------------------
+def run_config4(env):
+    torch, args = env.torch, env.args
+    from prisim_b200 import engine
+    from prisim_b200 import geometry as GEOM
+    from prisim_b200 import primary_beams as PB
+    from prisim_b200 import synthetic as S
+    from prisim_b200.interferometry import InterferometerArray, SimpleTime
+    world, rank, lr, dev = env.world, env.rank, env.local_rank, env.dev
+    cfg = S.config4()
+    sky, sp = cfg["skymodel"], cfg["skymodel"].spec_parms
+    nbl, nchan = cfg["baselines"].shape[0], cfg["channels"].size
+    lst_deg = 50.0 + 2.0 * rank                                # snapshots dealt round-robin: every rank its own LST
+    d_hadec = engine._f64(NP.stack((lst_deg - sky.location[:, 0], sky.location[:, 1]), axis=1), lr)
+    spec = {"flux_scale": engine._f64(sp["flux-scale"], lr), "index": engine._f64(sp["power-law-index"], lr),
+            "freq_ref": engine._f64(sp["freq-ref"], lr)}
+    d_bl = engine._f64(cfg["baselines"], lr)
+    pc_altaz = cfg["pointing_altaz"]
+    pc_dircos = GEOM.altaz2dircos(pc_altaz, "degrees")[0]
+    beam = PB.beam_desc_from_telescope(cfg["telescope"], pointing_info=cfg["pb_info"], pointing_center=pc_altaz, skyunits="altaz", device=lr)
+    vis = torch.empty((nbl, nchan), dtype=torch.complex128, device=dev)
+    ev = {"k1": [], "amp": []}
+
+    def step(timed):
+        dircos, index = engine.sky_cull(d_hadec, "hadec", latitude_deg=cfg["latitude"], device=lr)
+        nsrc = int(index.shape[0])
+        perm, nbright = engine.brightness_order(dircos, index, nsrc, spec, beam, cfg["channels"], device=lr)
+        dircos, index = dircos.index_select(0, perm).contiguous(), index.index_select(0, perm).contiguous()
+        e0, e1, e2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e0.record()
+        amp = engine.amp_table(dircos, index, nsrc, spec, beam, cfg["channels"], device=lr)
+        e1.record()
+        engine.skyvis(dircos, amp, nsrc, d_bl, pc_dircos, cfg["channels"], out=vis, device=lr, nsrc_bright=nbright)
+        e2.record()
+        if timed:
+            ev["amp"].append((e0, e1)); ev["k1"].append((e1, e2))
+        return nsrc
+
+    nsrc = step(False)
+    elapsed_ms, launches, clocks = env.timed_loop(step, args.steps)
+    k1_ms = statistics.mean(a.elapsed_time(b) for a, b in ev["k1"])
+    amp_ms = statistics.mean(a.elapsed_time(b) for a, b in ev["amp"])
+    terms_local = float(nsrc) * nbl * nchan
+    terms_step, = env.reduce([terms_local], "SUM")
+    ms_per_step = elapsed_ms / args.steps
+    value = terms_step / (ms_per_step * 1e-3) / 1e9
+    e2e = None
+    if not args.no_e2e:
+        sky.location = pinned(sky.location)
+        for key in ("flux-scale", "power-law-index", "freq-ref", "flux-offset"):
+            sp[key] = pinned(sp[key])
+        ia = InterferometerArray(cfg["labels"], cfg["baselines"], cfg["channels"], telescope=cfg["telescope"], latitude=cfg["latitude"],
+                                 skycoords="radec", pointing_coords="altaz", device=lr, noise_seed=5)
+        ia.cache_sky = False
+        host_vis = torch.empty((nbl, nchan), dtype=torch.complex128, pin_memory=True)
+        h2d = sky.location.nbytes + sum(sp[k].nbytes for k in ("flux-scale", "power-law-index", "freq-ref"))
+
+        def e2e_step():
+            ia.observe(SimpleTime(2451545.0, lst_deg), {"Tnet": 200.0}, NP.ones(nchan), pc_altaz, sky, cfg["t_acc"], pb_info=cfg["pb_info"])
+            ia.drain(lambda j, prod: host_vis.copy_(prod["skyvis_freq"], non_blocking=True), noise=False)
+            torch.cuda.synchronize()
+
+        e2e_ms = env.wall_loop(e2e_step, args.steps)
+        e2e = {"value": terms_step / (e2e_ms * 1e-3) / 1e9, "unit": "Gterms/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(host_vis.numel() * 16),
+               "ms_per_step": e2e_ms, "api": "InterferometerArray.observe(pb_info={delays, ...}) + device->host copy of skyvis_freq (pinned); precision='auto'",
+               "precision_report": ia.precision_report[-1] if ia.precision_report else None}
+    if rank == 0:
+        roofline = fma_roofline(env, "k_skyvis", terms_local, k1_ms, ms_per_step, clocks, 6, "fp32",
+                                float(nsrc) * nchan * 4 + nbl * nchan * 16.0, None)
+        n_el = 16
+        roofline["tile_beam"] = {"kernel": "k_amp_table<float> (dipole x 16-element phased array x ground plane, fp64 evaluation)", "ms": amp_ms,
+                                 "source_channel_elements_per_s": float(nsrc) * nchan / (amp_ms * 1e-3),
+                                 "element_phasors_per_s": float(nsrc) * nchan * n_el / (amp_ms * 1e-3),
+                                 "share_of_step": amp_ms / ms_per_step}
+        line = {"metric": "Gterms/s (src x bl x chan), config 4", "value": value, "unit": "Gterms/s", "n_gpus": world, "steps": args.steps,
+                "warmup": env.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOADS[4], "nsrc_above_horizon": nsrc, "nbl": nbl, "nchan": nchan, "terms_per_step": terms_step,
+                           "sharding": "snapshots round-robin over ranks",
+                           "l2": "L2 flushed between steps by the step's own streams: amplitude table {0:.2f} GB + {1:.2f} GB running sums".format(
+                               nsrc * nchan * 4 / 1e9, nbl * nchan * 16 / 1e9)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None}
+        env.emit(line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
                     help="configs 2/5 at N>1: strong (default) = baseline blocks of one snapshot; weak = one snapshot per rank")
     ap.add_argument("--nsrc", type=int, default=300000, help="catalogue size (default = the headline 300k)")
@@ -663,6 +754,8 @@ def main():
     env = Env(args)
     if args.config == 3:
         run_config3(env)
+    elif args.config == 4:
+        run_config4(env)
     else:
         run_config2(env, pipeline=(args.config == 5))
     env.finish()
