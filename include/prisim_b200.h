@@ -45,6 +45,9 @@ int pb200_version(void);
 int pb200_ctx_create(pb200_ctx** out, int device);
 void pb200_ctx_destroy(pb200_ctx* ctx);
 const char* pb200_last_error(const pb200_ctx* ctx);
+/* developer / test knobs: "skyvis_spc" = 0 (automatic) | 1 | 2 | 4 slabs of 128 channels per CTA of the phase-sum kernel;
+ * "dt_force_r8" != 0: 1024-point delay transforms through the radix-8 kernel instead of the warp-per-row one (A/B).        */
+int pb200_ctx_set_option(pb200_ctx* ctx, const char* name, long long value);
 /* number of kernels this ctx has launched since creation (bench.py's "gpu_launches") */
 long long pb200_launch_count(const pb200_ctx* ctx);
 
@@ -174,7 +177,7 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
  *   d_vis      [nbl,nchan] complex128, overwritten; consecutive baseline rows are vis_row_stride complex elements
  *              apart (0 = nchan, i.e. dense).  A multiple of nchan addresses every n-th row of a larger array: the
  *              interleaved baseline shard of one rank inside the writing rank's buffer (sharding.py).
- *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM
+ *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM | _RECURRENCE_QUARTER
  */
 #define PB200_SKYVIS_AUTO       0
 #define PB200_SKYVIS_RECURRENCE 1
@@ -186,6 +189,9 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
                                               register-file operand bandwidth, not by the FMA pipe) */
 #define PB200_SKYVIS_RECURRENCE_3TERM 6    /* packed three-term recurrence Z_{j+1} = 2cos(2phi) Z_j - Z_{j-1} in 16-channel half blocks (A/B) */
 #define PB200_SKYVIS_RECURRENCE_3TERM_SCALAR 7   /* the same with scalar FFMA (A/B) */
+#define PB200_SKYVIS_RECURRENCE_QUARTER 8   /* packed "quarter blocks": one MUFU anchor pair per source, the other three 8-channel quarters anchored by
+                                              exact r^8 rotations, inside a quarter one r^2 rotation + two three-term steps: 76 instead of 92 packed
+                                              instructions per source (the taper keeps the plain rotation) */
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                  const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, long long vis_row_stride, int method,

@@ -19,6 +19,7 @@ BEAM_DELTA, BEAM_AIRY, BEAM_GAUSSIAN, BEAM_DIPOLE, BEAM_TABLE, BEAM_LOGTABLE = 0
 ARRAY_NONE, ARRAY_ANALYTIC, ARRAY_ELEMENTS = 0, 1, 2
 DIPOLE_GENERAL, DIPOLE_SHORT, DIPOLE_HALFWAVE = 0, 1, 2
 SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR, SKYVIS_FP64, SKYVIS_RECURRENCE_LIFT, SKYVIS_RECURRENCE_3TERM, SKYVIS_RECURRENCE_3TERM_SCALAR = 0, 1, 2, 3, 4, 5, 6, 7
+SKYVIS_RECURRENCE_QUARTER = 8
 SLAB, SRC_TILE = 128, 32
 AMP_F32, AMP_F64 = 0, 1
 
@@ -51,6 +52,7 @@ SYMBOLS = {
     "pb200_ctx_create": (_i, [C.POINTER(_vp), _i]),
     "pb200_ctx_destroy": (None, [_vp]),
     "pb200_last_error": (C.c_char_p, [_vp]),
+    "pb200_ctx_set_option": (_i, [_vp, C.c_char_p, _ll]),
     "pb200_launch_count": (_ll, [_vp]),
     "pb200_sky_cull": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp, _vp, C.POINTER(_i), _vp]),
     "pb200_amp_bytes": (C.c_size_t, [_i, _i]),
@@ -139,6 +141,10 @@ class Context:
         if rc != PB200_OK:
             msg = self.lib.pb200_last_error(self.handle)
             raise PB200Error("prisim_b200 error {0}: {1}".format(rc, msg.decode() if msg else ""))
+
+    def set_option(self, name, value):
+        """``pb200_ctx_set_option``: developer / test knobs ('skyvis_spc', 'dt_force_r8')."""
+        self.check(self.lib.pb200_ctx_set_option(self.handle, name.encode(), int(value)))
 
     @property
     def launches(self):

@@ -42,6 +42,20 @@ void pb200_ctx_destroy(pb200_ctx* ctx) {
   delete ctx;
 }
 
+// developer / test knobs (the environment variables PB200_SKYVIS_SPC and PB200_DT_R8 set the same fields once, at ctx creation)
+int pb200_ctx_set_option(pb200_ctx* ctx, const char* name, long long value) {
+  if (!ctx || !name) return PB200_EINVAL;
+  if (!strcmp(name, "skyvis_spc")) {
+    if (value != 0 && value != 1 && value != 2 && value != 4) return pb_fail(ctx, PB200_EINVAL, "skyvis_spc must be 0 (automatic), 1, 2 or 4");
+    ctx->skyvis_spc_env = (int)value;
+  } else if (!strcmp(name, "dt_force_r8")) {
+    ctx->dt_force_r8 = value != 0;
+  } else {
+    return pb_fail(ctx, PB200_EINVAL, "pb200_ctx_set_option: unknown option %s", name);
+  }
+  return PB200_OK;
+}
+
 const char* pb200_last_error(const pb200_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 
 long long pb200_launch_count(const pb200_ctx* ctx) { return ctx ? ctx->launches : 0; }

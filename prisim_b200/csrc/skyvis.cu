@@ -57,6 +57,9 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
 #define PB_L2_HINTS 1      // wave) does not push the 39 MB of live running sums out to DRAM (measured per config-2 launch: 57 -> 1.5 GB written).
 #endif                     // 2: additionally the amplitude stream is loaded evict-first -- WORSE: the CTAs of a wave share every amplitude tile
                            // through L2, and evict-first drops it before the last of them has read it (100 -> 296 GB read, 1.6 % slower).
+#ifndef PB_ACC_SCALAR      // 1: the accumulates of the packed rotation loop as scalar FFMA (3 x 32-bit operands) instead of FFMA2 (3 x 64-bit)
+#define PB_ACC_SCALAR 0
+#endif
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
 #define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
 #endif
@@ -124,6 +127,7 @@ template <int SPC> struct __align__(16) TilePre {  // produced by the CTA once p
   float2 rot[T][Shape<SPC>::BL];
   float xd[T][Shape<SPC>::BL];                     // MUFU argument increment of one channel step (PB_TWO_ANCHOR == 2)
 };
+template <int SPC> struct __align__(16) TileRot8 { float2 rot8[T][Shape<SPC>::BL]; };   // eight-channel rotation r^8 (MODE 3)
 template <int SPC> struct __align__(16) TileKap { float kap[T][Shape<SPC>::BL]; };   // taper exponent coefficient
 
 // fraction of x in [-0.5, 0.5] (round-to-nearest-even magic number; |x| < 2^51)
@@ -134,6 +138,14 @@ __device__ __forceinline__ double frac_turns(double x) {
 }
 
 // exp(-2 pi i u) for an fp64 phase u in turns: fp64 range reduction, MUFU evaluation
+// acc += p * a on a channel pair: packed, or as two scalar FFMA (PB_ACC_SCALAR)
+__device__ __forceinline__ float2 acc_pair(float2 p, float2 a, float2 acc) {
+#if PB_ACC_SCALAR
+  return make_float2(fmaf(p.x, a.x, acc.x), fmaf(p.y, a.y, acc.y));
+#else
+  return __ffma2_rn(p, a, acc);
+#endif
+}
 __device__ __forceinline__ float anchor_arg(double u) { return (float)(frac_turns(u) * PB_INV_RCP2PI_F32); }
 __device__ __forceinline__ float2 mufu_phasor(float x) { return make_float2(__cosf(x), -__sinf(x)); }
 __device__ __forceinline__ float2 anchor_phasor(double u) { return mufu_phasor(anchor_arg(u)); }
@@ -292,7 +304,9 @@ __global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
 // Recurrence kernel (uniform channel grid)
 // =================================================================================================
 // MODE: phasor stepping of the channel loop -- 0 complex rotation by r^2 (4 ops per two channels), 1 lifted rotation
-// (3 shears) on CTA rows of short baselines, 2 three-term recurrence in 16-channel half blocks.  TAPER implies MODE 0.
+// (3 shears) on CTA rows of short baselines, 2 three-term recurrence in 16-channel half blocks, 3 "quarter blocks": one MUFU
+// anchor pair per source, the anchors of the other three 8-channel quarters by exact rotations r^8, and inside a quarter one
+// rotation by r^2 plus two three-term steps (76 instead of 92 packed instructions per source).  TAPER implies MODE 0.
 template <int SPC, bool PACKED, bool TAPER, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   static_assert(!TAPER || MODE == 0, "the taper folds into the complex rotation only");
@@ -306,6 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   float* sfreq2 = reinterpret_cast<float*>(tail + 64);                     // [SPC*SLAB] (f/1e8)^2, taper only
   TileKap<SPC>* tkap = reinterpret_cast<TileKap<SPC>*>(tail + 64 + SPC * PB200_SLAB * sizeof(float));   // [NSTAGE], taper only
+  TileRot8<SPC>* trot8 = reinterpret_cast<TileRot8<SPC>*>(tail + 64 + SPC * PB200_SLAB * sizeof(float));  // [NSTAGE], MODE 3 only (never with the taper)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wb = warp % WB, wc = warp / WB;           // tid % BL == wb*32 + lane: producer and consumer baseline coincide
@@ -394,6 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       if (lift_row) rp = two_anchor ? make_float2(-__fdiv_rn(rp.y, 1.0f + rp.x), rp.y) : make_float2(-__fdiv_rn(rp.y, rp.x), 2.0f * rp.x * rp.y);
       tpre[stage].rot[s][bcol] = rp;
       if (PB_TWO_ANCHOR == 2 && two_anchor) tpre[stage].xd[s][bcol] = anchor_arg(tau * df);
+      if (MODE == 3) trot8[stage].rot8[s][bcol] = rotation_phasor(8.0 * tau * df);
       if (TAPER) {
         // w = exp(-1/2 (u_proj/sigma)^2), u_proj^2 = (|b|^2 - (c tau_g)^2) f^2/c^2 (interferometry.py:6262-6283);
         // g.w = ln2 d^2 1e16 log2(e)  so that  w = exp2(-g.w (|b/c|^2 - tau_g^2) (f/1e8)^2); sqrt argument clamped at 0
@@ -493,8 +509,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
           // most two fresh 64-bit operands (PR / PI / A stay in the same operand slot across
           // consecutive instructions), which keeps FFMA2 at its 2-cycle pipe rate
           float2 t1 = __fmul2_rn(PR, RR), t2 = __fmul2_rn(PR, RI);
-          acc_re[2 * k4] = __ffma2_rn(PR, A0, acc_re[2 * k4]);
-          acc_im[2 * k4] = __ffma2_rn(PI, A0, acc_im[2 * k4]);
+          acc_re[2 * k4] = acc_pair(PR, A0, acc_re[2 * k4]);
+          acc_im[2 * k4] = acc_pair(PI, A0, acc_im[2 * k4]);
           float2 nr = __ffma2_rn(PI, NRI, t1);
           float2 ni = __ffma2_rn(PI, RR, t2);
           PR = nr; PI = ni;
@@ -502,8 +518,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
           if (k4 + 1 < KT / 4) {
             t1 = __fmul2_rn(PR, RR); t2 = __fmul2_rn(PR, RI);
           }
-          acc_re[2 * k4 + 1] = __ffma2_rn(PR, A1, acc_re[2 * k4 + 1]);
-          acc_im[2 * k4 + 1] = __ffma2_rn(PI, A1, acc_im[2 * k4 + 1]);
+          acc_re[2 * k4 + 1] = acc_pair(PR, A1, acc_re[2 * k4 + 1]);
+          acc_im[2 * k4 + 1] = acc_pair(PI, A1, acc_im[2 * k4 + 1]);
           if (k4 + 1 < KT / 4) {
             nr = __ffma2_rn(PI, NRI, t1);
             ni = __ffma2_rn(PI, RR, t2);
@@ -606,11 +622,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     }
   };
 
+  // MODE 3: quarter blocks.  Per source ONE pair of MUFU anchors (channels k0, k0 + 1; as in mode 0), the anchor pairs of the
+  // other three 8-channel quarters by rotating with the accurately rounded r^8 of the stage, and inside a quarter
+  //   P1 = P0 r^2 (complex, 4 packed instructions),  P2 = 2 cos(2 phi) P1 - P0,  P3 = 2 cos(2 phi) P2 - P1  (2 each):
+  // 8 + 8 accumulate = 16 packed instructions per quarter + 4 for the next quarter's anchor = 76 per source instead of the 92 of
+  // the pure rotation, with recurrence runs of two steps (error growth of the three-term form is steps^2 / 2 ulp).
+  auto run_tile4 = [&](int tile) {
+    const int stage = (fill + tile) & 1;
+    const TileIn<SPC>& ti = tin[stage];
+    const TilePre<SPC>& tp = tpre[stage];
+    const TileRot8<SPC>& t8 = trot8[stage];
+    auto anchors2 = [&](int s, float2& p, float2& q) {
+      const float x = anchor_arg(tp.tau[s][bcol] * fk0);
+      p = mufu_phasor(x);
+      q = mufu_phasor(x + tp.xd[s][bcol]);
+    };
+    float2 p_next, q_next;
+    anchors2(0, p_next, q_next);
+    float2 r_next = tp.rot[0][bcol], r8_next = t8.rot8[0][bcol];
+#pragma unroll 1
+    for (int chunk = 0; chunk < STAGGER; ++chunk) {
+    if (chunk == (warp >> 2) % STAGGER && tile + 1 < ntiles) precompute(tile + 1);
+#pragma unroll SRC_UNROLL
+    for (int s = chunk * (T / STAGGER); s < (chunk + 1) * (T / STAGGER); ++s) {
+      const float2 p0 = p_next, q0 = q_next, r = r_next, r8 = r8_next;
+      const int sn = (s + 1 < T) ? s + 1 : s;
+      anchors2(sn, p_next, q_next);
+      r_next = tp.rot[sn][bcol];
+      r8_next = t8.rot8[sn][bcol];
+      const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KT]);
+      const float2 RR = make_float2(r.x, r.x), RI = make_float2(r.y, r.y), NRI = make_float2(-r.y, -r.y);
+      const float2 CC = make_float2(2.0f * r.x, 2.0f * r.x);
+      const float2 ER = make_float2(r8.x, r8.x), EI = make_float2(r8.y, r8.y), NEI = make_float2(-r8.y, -r8.y);
+      float2 PR = make_float2(p0.x, q0.x), PI = make_float2(p0.y, q0.y);          // pair 0 of quarter 0
+#pragma unroll
+      for (int qd = 0; qd < KT / 8; ++qd) {
+        const float4 a4 = arow[2 * qd], b4 = arow[2 * qd + 1];
+        const float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w), A2 = make_float2(b4.x, b4.y), A3 = make_float2(b4.z, b4.w);
+        const int j = 4 * qd;
+        float2 QR = PR, QI = PI;
+        if (qd + 1 < KT / 8) {                               // anchor pair of the next quarter: this one rotated by r^8
+          const float2 u1 = __fmul2_rn(PR, ER), u2 = __fmul2_rn(PR, EI);
+          QR = __ffma2_rn(PI, NEI, u1);
+          QI = __ffma2_rn(PI, ER, u2);
+        }
+        const float2 t1 = __fmul2_rn(PR, RR), t2 = __fmul2_rn(PR, RI);
+        acc_re[j] = __ffma2_rn(PR, A0, acc_re[j]);
+        acc_im[j] = __ffma2_rn(PI, A0, acc_im[j]);
+        const float2 P1R = __ffma2_rn(PI, NRI, t1), P1I = __ffma2_rn(PI, RR, t2);      // pair 1 = pair 0 x r^2
+        acc_re[j + 1] = __ffma2_rn(P1R, A1, acc_re[j + 1]);
+        acc_im[j + 1] = __ffma2_rn(P1I, A1, acc_im[j + 1]);
+        const float2 P2R = __ffma2_rn(CC, P1R, make_float2(-PR.x, -PR.y)), P2I = __ffma2_rn(CC, P1I, make_float2(-PI.x, -PI.y));
+        acc_re[j + 2] = __ffma2_rn(P2R, A2, acc_re[j + 2]);
+        acc_im[j + 2] = __ffma2_rn(P2I, A2, acc_im[j + 2]);
+        const float2 P3R = __ffma2_rn(CC, P2R, make_float2(-P1R.x, -P1R.y)), P3I = __ffma2_rn(CC, P2I, make_float2(-P1I.x, -P1I.y));
+        acc_re[j + 3] = __ffma2_rn(P3R, A3, acc_re[j + 3]);
+        acc_im[j + 3] = __ffma2_rn(P3I, A3, acc_im[j + 3]);
+        PR = QR; PI = QI;
+      }
+    }
+    }
+  };
+
   bool fresh = true;                                   // nothing of this segment is in its slot yet
   for (int tile = 0; tile < ntiles; ++tile) {
     if (!live && tile + 1 < ntiles) precompute(tile + 1);
     if (live) {
-      if constexpr (MODE == 2) run_tile3(tile);
+      if constexpr (MODE == 3) run_tile4(tile);
+      else if constexpr (MODE == 2) run_tile3(tile);
       else if constexpr (MODE == 1) { if (lift_row) run_tile(tile, std::true_type()); else run_tile(tile, std::false_type()); }
       else run_tile(tile, std::false_type());
     }
@@ -958,7 +1037,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   if (nsrc > 0 && (!d_dircos || !d_amp)) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: null source arrays");
   if (amp_dtype != PB200_AMP_F32 && !(amp_dtype == PB200_AMP_F64 && method == PB200_SKYVIS_FP64))
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: an fp64 amplitude table needs method PB200_SKYVIS_FP64");
-  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_3TERM_SCALAR)
+  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_QUARTER)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PbDeviceGuard guard(ctx->device);
@@ -973,7 +1052,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   const double df = nchan > 1 ? (h_freqs[nchan - 1] - h_freqs[0]) / (double)(nchan - 1) : 0.0;
   const bool uniform = pb200_channels_uniform(h_freqs, nchan) != 0;
   const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64 ||
-                         method == PB200_SKYVIS_RECURRENCE_LIFT || method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR);
+                         method == PB200_SKYVIS_RECURRENCE_LIFT || method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ||
+                         method == PB200_SKYVIS_RECURRENCE_QUARTER);
   const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
   if (want_rec && !uniform)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: recurrence kernel needs uniformly spaced channels");
@@ -1000,7 +1080,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
   P.smax2_bits = smax2_bits;
   P.bright_tiles = nsrc_bright > 0 ? (nsrc_bright + T - 1) / T : 0;
-  const int mode = method == PB200_SKYVIS_RECURRENCE_LIFT ? 1 : (method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ? 2 : 0);
+  int mode = method == PB200_SKYVIS_RECURRENCE_LIFT ? 1 : (method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ? 2 :
+                   (method == PB200_SKYVIS_RECURRENCE_QUARTER ? 3 : 0));
   const bool taper = d_src_fwhm_deg != nullptr;
 
   // CTA shape: fp64 kernel 1 slab x 64 baselines; direct kernel 1 slab x 128 baselines; recurrence kernel wide-channel
@@ -1008,6 +1089,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   const bool fp64 = method == PB200_SKYVIS_FP64;
   int spc = (direct || fp64) ? 1 : (nslab % 2 == 0 ? 2 : 1);
   if (!direct && !fp64 && (ctx->skyvis_spc_env == 1 || ctx->skyvis_spc_env == 2 || ctx->skyvis_spc_env == 4)) spc = ctx->skyvis_spc_env;
+  if (mode == 3 && spc == 1) mode = 0;       // the r^8 table of the quarter form does not fit beside 128-baseline tiles (258 KB): plain rotation
   P.kt = fp64 ? KT64 : KT;
   P.wc = fp64 ? WC64 : spc * WCS;
   P.wb = NWARPS / P.wc;
@@ -1049,7 +1131,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   }
   const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR && method != PB200_SKYVIS_RECURRENCE_3TERM_SCALAR;
 #define SMEM_REC(SPC) (NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) + \
-                       (taper ? NSTAGE * sizeof(TileKap<SPC>) : 0))
+                       (taper ? NSTAGE * sizeof(TileKap<SPC>) : 0) + (mode == 3 && !taper ? NSTAGE * sizeof(TileRot8<SPC>) : 0))
 #define LAUNCH_REC(SPC)                                                                   \
   do {                                                                                    \
     if (taper) {                                                                          \
@@ -1058,6 +1140,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
     } else if (mode == 2) {                                                               \
       if (packed) LAUNCH((k_skyvis<SPC, true, false, 2>), SMEM_REC(SPC));                 \
       else LAUNCH((k_skyvis<SPC, false, false, 2>), SMEM_REC(SPC));                       \
+    } else if (mode == 3) {                                                               \
+      LAUNCH((k_skyvis<SPC, true, false, 3>), SMEM_REC(SPC));                             \
     } else if (mode == 1) {                                                               \
       LAUNCH((k_skyvis<SPC, true, false, 1>), SMEM_REC(SPC));                             \
     } else {                                                                              \

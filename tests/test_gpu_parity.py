@@ -443,7 +443,7 @@ def test_skyvis_random_shapes_property(eng):
 
     @settings(max_examples=14, deadline=None, suppress_health_check=list(HealthCheck))
     @given(nsrc=st.integers(1, 200), nbl=st.integers(1, 150), nchan=st.integers(2, 300), seed=st.integers(0, 10 ** 6),
-           method=st.sampled_from(["auto", "recurrence_lift", "recurrence_3term", "recurrence_3term_scalar", "recurrence_scalar", "direct", "fp64"]), spc=st.sampled_from(["1", "2", "4"]))
+           method=st.sampled_from(["auto", "recurrence_lift", "recurrence_3term", "recurrence_3term_scalar", "recurrence_quarter", "recurrence_scalar", "direct", "fp64"]), spc=st.sampled_from(["1", "2", "4"]))
     def check(nsrc, nbl, nchan, seed, method, spc):
         rng = NP.random.default_rng(seed)
         bl = rng.normal(0, 80.0, (nbl, 3)); bl[:, 2] *= 0.05
@@ -453,11 +453,13 @@ def test_skyvis_random_shapes_property(eng):
         dircos, _ = eng.sky_cull(altaz, "altaz")
         amp = eng.dense_to_amp_table(torch.as_tensor(dense).cuda(), dtype=torch.float64 if method == "fp64" else torch.float32)
         amp_used = eng.amp_table_to_dense(amp, nsrc, nchan).double().cpu().numpy()
-        os.environ["PB200_SKYVIS_SPC"] = spc
+        from prisim_b200 import _lib
+        ctx = _lib.get_context(0)
+        ctx.set_option("skyvis_spc", int(spc))
         try:
             V = eng.skyvis(dircos, amp, nsrc, bl, (0.0, 0.0, 1.0), freqs, method=method).cpu().numpy()
         finally:
-            os.environ.pop("PB200_SKYVIS_SPC", None)
+            ctx.set_option("skyvis_spc", 0)
         Vo = O.skyvis_snapshot(bl, altaz, amp_used, freqs, NP.asarray([90.0, 270.0]))
         assert V.shape == (nbl, nchan)
         assert rel_err_per_baseline(V, Vo) <= (1e-11 if method == "fp64" else TOL)

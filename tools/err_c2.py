@@ -28,7 +28,8 @@ for mode in sys.argv[1:] or ["plain"]:
         perm, nb = engine.brightness_order(dircos, index, nsrc, spec, beam, cfg["channels"], power_fraction=frac)
         dc, ix = dircos.index_select(0, perm).contiguous(), index.index_select(0, perm).contiguous()
     amp = engine.amp_table(dc, ix, nsrc, spec, beam, cfg["channels"])
-    run = lambda: engine.skyvis(dc, amp, nsrc, bl, pc, cfg["channels"], nsrc_bright=nb)
+    method = os.environ.get("PB200_METHOD", "auto")
+    run = lambda: engine.skyvis(dc, amp, nsrc, bl, pc, cfg["channels"], nsrc_bright=nb, method=method)
     V = run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); run(); e1.record(); torch.cuda.synchronize()
