@@ -1080,14 +1080,18 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   P.nsrc_pad = nsrc_pad; P.nbl = nbl; P.nchan = nchan; P.nslab = nslab;
   P.smax2_bits = smax2_bits;
   P.bright_tiles = nsrc_bright > 0 ? (nsrc_bright + T - 1) / T : 0;
+  // AUTO on a uniform grid without taper takes the quarter-block form (measured on config 2, same process, two A/B rounds:
+  // 4.71 vs 4.65 Tterms/s at 4 slabs per CTA, 4.56 vs 4.54 at 2; max error 3.3e-6 vs 3.0e-6, rms 2.7e-7 vs 3.1e-7);
+  // PB200_SKYVIS_RECURRENCE asks for the plain rotation explicitly
   int mode = method == PB200_SKYVIS_RECURRENCE_LIFT ? 1 : (method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ? 2 :
-                   (method == PB200_SKYVIS_RECURRENCE_QUARTER ? 3 : 0));
+                   ((method == PB200_SKYVIS_RECURRENCE_QUARTER || (method == PB200_SKYVIS_AUTO && !d_src_fwhm_deg)) ? 3 : 0));
   const bool taper = d_src_fwhm_deg != nullptr;
 
-  // CTA shape: fp64 kernel 1 slab x 64 baselines; direct kernel 1 slab x 128 baselines; recurrence kernel wide-channel
-  // CTAs when the slab count allows it (measured on B200: 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4 slabs)
+  // CTA shape: fp64 kernel 1 slab x 64 baselines; direct kernel 1 slab x 128 baselines; recurrence kernel the widest channel
+  // extent the slab count allows: the (source, baseline) delay / rotation stage is shared by all channel-block warps of a CTA
+  // (round 1 measured 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4 slabs, the round-2 kernel 4.46 / 4.54 / 4.65)
   const bool fp64 = method == PB200_SKYVIS_FP64;
-  int spc = (direct || fp64) ? 1 : (nslab % 2 == 0 ? 2 : 1);
+  int spc = (direct || fp64) ? 1 : (nslab % 4 == 0 ? 4 : (nslab % 2 == 0 ? 2 : 1));
   if (!direct && !fp64 && (ctx->skyvis_spc_env == 1 || ctx->skyvis_spc_env == 2 || ctx->skyvis_spc_env == 4)) spc = ctx->skyvis_spc_env;
   if (mode == 3 && spc == 1) mode = 0;       // the r^8 table of the quarter form does not fit beside 128-baseline tiles (258 KB): plain rotation
   P.kt = fp64 ? KT64 : KT;
