@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import os
 import warnings
+from collections import OrderedDict
 
 import numpy as NP
 import scipy.constants as FCNST
@@ -303,11 +304,15 @@ class ROI_parameters(object):
     """Drop-in for ``prisim.interferometry.ROI_parameters`` (interferometry.py:3905-4617) in memory: per snapshot the
     catalogue indices inside the region of interest and the primary-beam table [n_roi, nchan] that
     ``InterferometerArray.observe(roi_info={'ind', 'pbeam'})`` consumes.  The beam is evaluated on the GPU
-    (``primary_beam_generator`` -> ``pb200_amp_table``); FITS save / init_file are out of scope."""
+    (``primary_beam_generator`` -> ``pb200_amp_table``).  ``save`` / ``init_file`` exchange the tables through the same
+    FITS layout as the reference (:4621-4723 / :4080-4205) using the plain-numpy writer in ``fits_min`` (astropy is not
+    available here); on the GPU path the tables normally stay in memory and this file is only an interchange format."""
 
     def __init__(self, init_file=None, device=None):
+        self.device = device
         if init_file is not None:
-            raise NotImplementedError("FITS interchange of ROI parameters is outside the hot-path scope (SURVEY.md section 8f)")
+            self._load(init_file)
+            return
         self.skymodel = None
         self.freq = None
         self.freq_scale = None
@@ -315,6 +320,111 @@ class ROI_parameters(object):
         self.info = {"radius": [], "center": [], "ind": [], "pbeam": [], "center_coords": None}     # :4170-4176
         self.pinfo = []
         self.device = device
+
+    def _load(self, init_file):
+        """interferometry.py:4080-4205: rebuild the object from a file written by ``save`` (or by the reference)."""
+        from . import fits_min as F
+        try:
+            hdus = F.read(init_file)
+        except IOError:
+            raise IOError("init_file provided but could not open the initialization file.")
+        h0 = hdus[0][0]
+        ext = OrderedDict((str(F.header_get(h, "EXTNAME", "")).upper(), (h, d)) for h, d in hdus[1:])
+        n_obs = int(F.header_get(h0, "n_obs"))
+        self.skymodel, self.freq_scale = None, "Hz"
+        self.info = {"radius": [], "center": [], "ind": [], "pbeam": [], "center_coords": None}
+        tel = {}
+        if F.header_get(h0, "telescope") is not None:
+            tel["id"] = F.header_get(h0, "telescope")
+        tel["latitude"] = F.header_get(h0, "latitude", None)
+        tel["longitude"] = F.header_get(h0, "longitude", 0.0)
+        tel["altitude"] = F.header_get(h0, "altitude", 0.0)
+        for key, name in (("shape", "element_shape"), ("size", "element_size"), ("ocoords", "element_ocoords")):
+            if F.header_get(h0, name) is None:
+                raise KeyError("Antenna {0} not found in the init_file header".format(name.replace("_", " ")))
+            tel[key] = F.header_get(h0, name)
+        if "ANTENNA ELEMENT ORIENTATION" not in ext:
+            raise KeyError('Extension named "orientation" not found in init_file.')
+        tel["orientation"] = ext["ANTENNA ELEMENT ORIENTATION"][1].reshape(1, -1)
+        if "ANTENNA ELEMENT LOCATIONS" in ext:
+            tel["element_locs"] = ext["ANTENNA ELEMENT LOCATIONS"][1]
+        tel["groundplane"] = F.header_get(h0, "ground_plane", None)
+        for key in ("scale", "max"):
+            v = F.header_get(h0, "ground_modify_" + key)
+            if tel["groundplane"] is not None and v is not None:
+                tel.setdefault("ground_modify", {})[key] = v
+        self.telescope = tel
+        if "FREQ" not in ext:
+            raise KeyError('Extension named "FREQ" not found in init_file.')
+        self.freq = ext["FREQ"][1]
+        empty = NP.asarray([])
+        self.info["ind"] = [ext["IND_{0:0d}".format(i)][1] if "IND_{0:0d}".format(i) in ext else empty for i in range(n_obs)]
+        self.info["pbeam"] = [ext["PB_{0:0d}".format(i)][1] if "PB_{0:0d}".format(i) in ext else empty for i in range(n_obs)]
+        self.pinfo = []
+        if any(k.startswith("DELAYS_") or k.startswith("POINTING_CENTER_") for k in ext):
+            for i in range(n_obs):
+                p = {}
+                if "DELAYS_{0:0d}".format(i) in ext:
+                    h, d = ext["DELAYS_{0:0d}".format(i)]
+                    p["delays"] = d
+                    err = F.header_get(h, "delayerr")
+                    if err is not None:
+                        p["delayerr"] = None if err <= 0.0 else err
+                if "POINTING_CENTER_{0:0d}".format(i) in ext:
+                    h, d = ext["POINTING_CENTER_{0:0d}".format(i)]
+                    p["pointing_center"] = d
+                    if F.header_get(h, "pointing_coords") is None:
+                        raise KeyError('Header of extension POINTING_CENTER_{0:0d} not found to contain key "pointing_coords" in init_file'.format(i))
+                    p["pointing_coords"] = F.header_get(h, "pointing_coords")
+                self.pinfo.append(p)
+
+    def save(self, infile, tabtype="BinTableHDU", overwrite=False, verbose=True):
+        """Same call and file layout as interferometry.py:4621-4723: ``infile + '.fits'`` with the telescope keywords in
+        the primary header and one image extension per array (element orientation / locations, FREQ, IND_j, PB_j, DELAYS_j,
+        POINTING_CENTER_j).  ``fits_min.getdata(file, 'IND_3')`` reads a table back like ``fits.getdata`` in run_prisim."""
+        from . import fits_min as F
+        if not isinstance(infile, str):
+            raise TypeError("Output filename must be a string")
+        tel = self.telescope
+        hdr = OrderedDict()
+        hdr["n_obs"] = (len(self.info["ind"]), "Number of observations")
+        if "id" in tel:
+            hdr["telescope"] = (tel["id"], "Telescope Name")
+        hdr["element_shape"] = (tel["shape"], "Antenna element shape")
+        hdr["element_size"] = (float(tel["size"]), "Antenna element size [m]")
+        hdr["element_ocoords"] = (tel["ocoords"], "Antenna element orientation coordinates")
+        if tel.get("latitude", None) is not None:
+            hdr["latitude"] = (float(tel["latitude"]), "Latitude (in degrees)")
+        hdr["longitude"] = (float(tel.get("longitude", 0.0) or 0.0), "Longitude (in degrees)")
+        if tel.get("altitude", None) is not None:
+            hdr["altitude"] = (float(tel["altitude"]), "Altitude (in m)")
+        if tel.get("groundplane", None) is not None:
+            hdr["ground_plane"] = (float(tel["groundplane"]), "Antenna element height above ground plane [m]")
+            for key, text in (("scale", "Ground plane modification scale factor"), ("max", "Maximum ground plane modification")):
+                if key in tel.get("ground_modify", {}):
+                    hdr["ground_modify_" + key] = (float(tel["ground_modify"][key]), text)
+        ext = [("ANTENNA ELEMENT ORIENTATION", NP.asarray(tel["orientation"], dtype=NP.float64), None)]
+        if "element_locs" in tel:
+            ext.append(("ANTENNA ELEMENT LOCATIONS", NP.asarray(tel["element_locs"], dtype=NP.float64), None))
+        ext.append(("FREQ", NP.asarray(self.freq, dtype=NP.float64), None))
+        for i in range(len(self.info["ind"])):
+            if NP.asarray(self.info["ind"][i]).size > 0:
+                ext.append(("IND_{0:0d}".format(i), NP.asarray(self.info["ind"][i]), None))
+                ext.append(("PB_{0:0d}".format(i), NP.asarray(self.info["pbeam"][i]), None))
+            if self.pinfo and i < len(self.pinfo) and self.pinfo[i] is not None:
+                p = self.pinfo[i]
+                if "delays" in p:
+                    err = p.get("delayerr", None)
+                    ext.append(("DELAYS_{0:0d}".format(i), NP.asarray(p["delays"], dtype=NP.float64),
+                                {"delayerr": (0.0 if err is None else float(err), "Jitter in delays [s]")}))
+                if "pointing_center" in p:
+                    if "pointing_coords" not in p:
+                        raise KeyError('Key "pointing_coords" not found in attribute pinfo.')
+                    ext.append(("POINTING_CENTER_{0:0d}".format(i), NP.asarray(p["pointing_center"], dtype=NP.float64),
+                                {"pointing_coords": (p["pointing_coords"], "Pointing coordinate system")}))
+        F.write(infile + ".fits", hdr, ext, overwrite=overwrite)
+        if verbose:
+            print("\tRegions of interest information written successfully to FITS file on disk:\n\t\t{0}\n".format(infile + ".fits"))
 
     def _altaz(self, skymodel, lst):
         coords = getattr(skymodel, "coords", None)

@@ -216,8 +216,8 @@ def test_roi_parameters_host_paths_without_gpu():
         roi.append_settings(sky, freq, pinfo=None, roi_info={"radius": 30.0, "center": None})
     with pytest.raises(TypeError):
         ROI_parameters().append_settings(sky, freq, roi_info={"radius": 10.0}, telescope=None)
-    with pytest.raises(NotImplementedError):
-        ROI_parameters(init_file="roi.fits")
+    with pytest.raises(IOError):                                                 # a missing file (FITS interchange itself: test below)
+        ROI_parameters(init_file="no_such_roi.fits")
 
 
 def test_gradient_and_duplicate_argument_errors_without_gpu():
@@ -325,3 +325,77 @@ def test_baseline_group_lookups_match_reference_golden():
         getBaselineGroupKeys(query, [("1", "0")])
     with pytest.raises(TypeError):
         getBaselinesInGroups(query, info["reversemap"], None)
+
+
+def test_fits_min_roundtrip_and_card_format(tmp_path):
+    """prisim_b200.fits_min: the fixed-format FITS subset ROI_parameters.save needs (primary header + IMAGE extensions)."""
+    from prisim_b200 import fits_min as F
+    rng = NP.random.default_rng(0)
+    arrays = {"F8": rng.normal(size=(5, 7)), "I8": rng.integers(-5, 10 ** 12, 13), "F4": rng.normal(size=(3, 4, 2)).astype(NP.float32),
+              "I4": rng.integers(0, 1000, (2, 3)).astype(NP.int32), "U1": rng.integers(0, 255, 9).astype(NP.uint8), "EMPTYDIM": NP.zeros((0, 4))}
+    fn = str(tmp_path / "t.fits")
+    hdr = {"n_obs": (2, "Number of observations"), "element_shape": ("dish", "Antenna element shape"), "element_size": (14.0, "m"),
+           "latitude": -30.7224, "flag": True, "quote": "it's", "tiny": 1.5e-300}
+    F.write(fn, hdr, [(k, v, {"delayerr": (0.0, "Jitter in delays [s]")} if k == "I8" else None) for k, v in arrays.items()])
+    raw = open(fn, "rb").read()
+    assert len(raw) % 2880 == 0 and raw[:30] == b"SIMPLE  =                    T"
+    first = raw[:2880].decode("ascii")
+    cards = [first[i:i + 80] for i in range(0, 2880, 80)]
+    assert any(c.startswith("HIERARCH element_shape = 'dish    '") for c in cards) and any(c.startswith("END") for c in cards)
+    hdus = F.read(fn)
+    h0 = hdus[0][0]
+    assert F.header_get(h0, "N_OBS") == 2 and F.header_get(h0, "element_size") == 14.0 and F.header_get(h0, "LATITUDE") == -30.7224
+    assert F.header_get(h0, "flag") is True and F.header_get(h0, "quote") == "it's" and F.header_get(h0, "tiny") == 1.5e-300
+    for k, v in arrays.items():
+        got = F.getdata(fn, k.lower())
+        assert got.dtype == v.dtype and got.shape == v.shape and NP.array_equal(got, v), k
+    assert F.header_get(hdus[2][0], "delayerr") == 0.0
+    with pytest.raises(KeyError):
+        F.getdata(fn, "nope")
+    with pytest.raises(IOError):
+        F.write(fn, {}, [])
+    with pytest.raises(TypeError):
+        F.write(str(tmp_path / "c.fits"), {}, [("C", NP.zeros(3, dtype=NP.complex128), None)])
+
+
+def test_roi_parameters_save_and_init_file_roundtrip(tmp_path):
+    """ROI_parameters.save / ROI_parameters(init_file=...) with the reference's FITS layout (interferometry.py:4621-4723, :4080-4205)."""
+    from prisim_b200 import fits_min as F
+    from prisim_b200.interferometry import ROI_parameters
+    from prisim_b200.skymodel import SkyModel
+    rng = NP.random.default_rng(1)
+    nsrc, nchan = 40, 6
+    parms = {"location": NP.stack((rng.uniform(0, 360, nsrc), rng.uniform(-90, 90, nsrc)), 1), "coords": "hadec", "spec_type": "func", "frequency": [150e6],
+             "spec_parms": {"name": NP.repeat("power-law", nsrc), "power-law-index": NP.zeros(nsrc), "freq-ref": NP.full(nsrc, 150e6), "flux-scale": NP.ones(nsrc)}}
+    sky = SkyModel(init_parms=parms)
+    tel = {"id": "mwa", "shape": "dipole", "size": 0.74, "orientation": NP.asarray([1.0, 0.0, 0.0]), "ocoords": "dircos", "groundplane": 0.3,
+           "ground_modify": {"scale": 1.5, "max": 4.0}, "latitude": -26.701, "longitude": 116.67, "altitude": 377.8,
+           "element_locs": rng.normal(size=(16, 3))}
+    freq = 0.15 + 1e-4 * NP.arange(nchan)
+    roi = ROI_parameters()
+    inds = [NP.asarray([3, 17, 25]), NP.asarray([], dtype=int), NP.asarray([0, 1, 2, 39])]
+    for j, ind in enumerate(inds):
+        pb = rng.uniform(0, 1, (ind.size, nchan))
+        roi.append_settings(sky, freq, pinfo={}, roi_info={"ind": ind, "pbeam": pb if ind.size else None}, telescope=tel, freq_scale="GHz")
+    roi.pinfo = [{"delays": rng.uniform(0, 1e-8, 16), "delayerr": None, "pointing_center": NP.asarray([[60.0, 120.0]]), "pointing_coords": "altaz"},
+                 {"delays": rng.uniform(0, 1e-8, 16), "delayerr": 2e-10}, {"pointing_center": NP.asarray([[0.1, 0.2, 0.97]]), "pointing_coords": "dircos"}]
+    base = str(tmp_path / "roiinfo")
+    roi.save(base, verbose=False)
+    with pytest.raises(IOError):
+        roi.save(base, verbose=False)
+    roi.save(base, overwrite=True, verbose=False)
+    # what scripts/run_prisim.py:1959-1961 reads per (chunk, snapshot)
+    assert NP.array_equal(F.getdata(base + ".fits", "IND_2"), inds[2])
+    assert NP.array_equal(F.getdata(base + ".fits", "PB_0"), roi.info["pbeam"][0])
+    back = ROI_parameters(init_file=base + ".fits")
+    assert NP.allclose(back.freq, freq * 1e9) and len(back.info["ind"]) == 3
+    for j in range(3):
+        assert NP.array_equal(back.info["ind"][j], inds[j]) and NP.array_equal(back.info["pbeam"][j], roi.info["pbeam"][j])
+    t = back.telescope
+    assert t["id"] == "mwa" and t["shape"] == "dipole" and t["size"] == 0.74 and t["ocoords"] == "dircos" and t["groundplane"] == 0.3
+    assert t["ground_modify"] == {"scale": 1.5, "max": 4.0} and t["latitude"] == -26.701 and t["longitude"] == 116.67 and t["altitude"] == 377.8
+    assert NP.array_equal(t["orientation"], NP.asarray([[1.0, 0.0, 0.0]])) and NP.array_equal(t["element_locs"], tel["element_locs"])
+    assert NP.array_equal(back.pinfo[0]["delays"], roi.pinfo[0]["delays"]) and back.pinfo[0]["delayerr"] is None
+    assert back.pinfo[0]["pointing_coords"] == "altaz" and NP.array_equal(back.pinfo[0]["pointing_center"], roi.pinfo[0]["pointing_center"])
+    assert back.pinfo[1]["delayerr"] == 2e-10 and "pointing_center" not in back.pinfo[1]
+    assert back.pinfo[2]["pointing_coords"] == "dircos" and "delays" not in back.pinfo[2]
