@@ -763,7 +763,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per k_skyvis launch at the headline size (1 GPU), from the
 # committed ncu capture (profiles/); None until that capture exists for the current kernel.
-TRAFFIC_BYTES_PER_LAUNCH = 86.0e9      # profiles/skyvis_dram_r02.txt: 64.9 GB read + 21.1 GB written (0.5 % of HBM bandwidth over 2.46 s)
+TRAFFIC_BYTES_PER_LAUNCH = 142.8e9     # profiles/skyvis_dram_r02.txt: 128.8 GB read + 14.0 GB written (0.9 % of HBM bandwidth over 2.37 s; final kernel)
 
 if __name__ == "__main__":
     main()

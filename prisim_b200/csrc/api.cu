@@ -21,6 +21,19 @@ int pb200_ctx_create(pb200_ctx** out, int device) {
   memset(ctx, 0, sizeof(*ctx));
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  // L2 set-aside for lines accessed with an evict-last policy (the fp64 running sums of the phase-sum kernel, 39 MB live per launch);
+  // without it evict-last degrades to normal replacement.  Device-wide and harmless to other users of the device.
+  {
+    int prev = -1;
+    const char* l2 = getenv("PB200_L2_PERSIST_MB");
+    const size_t want = (size_t)(l2 ? atoi(l2) : 64) << 20;
+    if (want > 0 && cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(device) == cudaSuccess) {
+      const size_t cap = (size_t)prop.persistingL2CacheMaxSize;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want < cap ? want : cap);
+      cudaGetLastError();
+      if (prev != device) cudaSetDevice(prev);
+    }
+  }
   const char* spc = getenv("PB200_SKYVIS_SPC");          // developer override of the phase-sum CTA shape (tools/variants.sh)
   ctx->skyvis_spc_env = spc ? atoi(spc) : 0;
   const char* r8 = getenv("PB200_DT_R8");
