@@ -213,9 +213,18 @@ def noise(skyvis_t, tsys, aeff, effq, df, t_acc, seed, nbl, nchan, snapshot=0, b
     nbl_total = nbl if nbl_total is None else int(nbl_total)
     dev = "cuda:{0}".format(device)
     out = out or {}                                  # optional preallocated outputs {'rms', 'noise', 'vis'} (contiguous, right shape)
-    rms = out.get("rms", torch.empty((nbl, nchan), dtype=torch.float64, device=dev) if "rms" not in out else None) if "rms" in want else None
-    nz = out.get("noise", torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "noise" not in out else None) if "noise" in want else None
-    vis = out.get("vis", torch.empty((nbl, nchan), dtype=torch.complex128, device=dev) if "vis" not in out else None) if "vis" in want else None
+
+    def product(name, dtype):
+        if name not in want:
+            return None
+        t = out.get(name, None)
+        if t is None:
+            return torch.empty((nbl, nchan), dtype=dtype, device=dev)
+        if tuple(t.shape) != (nbl, nchan) or t.dtype != dtype or not t.is_contiguous():
+            raise ValueError("preallocated '{0}' must be a contiguous [nbl, nchan] {1} CUDA tensor".format(name, dtype))
+        return t
+
+    rms, nz, vis = product("rms", torch.float64), product("noise", torch.complex128), product("vis", torch.complex128)
     st = []
     for t in (tsys, aeff, effq):
         st.extend(_bcast_strides(t, nbl, nchan))
