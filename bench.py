@@ -526,7 +526,7 @@ def run_config2(env, pipeline=False):
             roofline["tail"] = {"kernels": "k_noise + 3 x k_delay_fft_w32", "ms": tail_ms, "algorithmic_bytes": tail_bytes,
                                 "achieved_gbs": tail_bytes / (tail_ms * 1e-3) / 1e9, "peak_gbs": roofline["hbm_gbs_measured"],
                                 "frac": tail_bytes / (tail_ms * 1e-3) / 1e9 / roofline["hbm_gbs_measured"] if roofline["hbm_gbs_measured"] else None}
-        cpu = None if args.no_cpu_baseline else cpu_baseline(cfg, terms_step)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(cfg, terms_step)     # the CPU arm is timed at N=1 only
         mode = ("single GPU" if world == 1 else
                 ("interleaved baseline shards of ONE snapshot, " if strong else "one snapshot per GPU, ") +
                 ("kernel epilogue stores over NVLink peer memory into rank 0's buffer" if gbuf.mode == "peer" else "NCCL point-to-point gather to rank 0"))
