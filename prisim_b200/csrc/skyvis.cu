@@ -60,6 +60,9 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
 #ifndef PB_ACC_SCALAR      // 1: the accumulates of the packed rotation loop as scalar FFMA (3 x 32-bit operands) instead of FFMA2 (3 x 64-bit)
 #define PB_ACC_SCALAR 0
 #endif
+#ifndef PB_STAGE_FP64      // 1: the stage's rotations r^2 (and r^8) from ONE fp64 sincospi + two fp64 complex squarings (FP64 pipe, idle otherwise)
+#define PB_STAGE_FP64 0    // instead of one fp32 sincospif + first-order correction each (~25 FMA-pipe instructions each)
+#endif
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
 #define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
 #endif
@@ -404,12 +407,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
       const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
       tpre[stage].tau[s][bcol] = tau;
-      float2 rp = rotation_phasor((three_term || two_anchor) ? 2.0 * tau * df : tau * df);   // packed rows: the two-channel rotation r^2
+      float2 rp;
+      if (PB_STAGE_FP64 && MODE == 3) {
+        double sn, cs;
+        sincospi(2.0 * frac_turns(2.0 * tau * df) , &sn, &cs);                       // exp(-2 pi i 2 tau df) = (cs, -sn)
+        rp = make_float2((float)cs, (float)(-sn));
+        double ar = cs, ai = -sn;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { const double t = fma(ar, ar, -ai * ai); ai = 2.0 * ar * ai; ar = t; }
+        trot8[stage].rot8[s][bcol] = make_float2((float)ar, (float)ai);
+      } else {
+        rp = rotation_phasor((three_term || two_anchor) ? 2.0 * tau * df : tau * df);   // packed rows: the two-channel rotation r^2
+        if (MODE == 3) trot8[stage].rot8[s][bcol] = rotation_phasor(8.0 * tau * df);
+      }
       // lifted rows: shear coefficients of the two-channel step, t = -tan(phi) and s = sin(2 phi) for r = e^{i phi}
       if (lift_row) rp = two_anchor ? make_float2(-__fdiv_rn(rp.y, 1.0f + rp.x), rp.y) : make_float2(-__fdiv_rn(rp.y, rp.x), 2.0f * rp.x * rp.y);
       tpre[stage].rot[s][bcol] = rp;
       if (PB_TWO_ANCHOR == 2 && two_anchor) tpre[stage].xd[s][bcol] = anchor_arg(tau * df);
-      if (MODE == 3) trot8[stage].rot8[s][bcol] = rotation_phasor(8.0 * tau * df);
       if (TAPER) {
         // w = exp(-1/2 (u_proj/sigma)^2), u_proj^2 = (|b|^2 - (c tau_g)^2) f^2/c^2 (interferometry.py:6262-6283);
         // g.w = ln2 d^2 1e16 log2(e)  so that  w = exp2(-g.w (|b/c|^2 - tau_g^2) (f/1e8)^2); sqrt argument clamped at 0
