@@ -1107,7 +1107,7 @@ class InterferometerArray(object):
             # (1) cancellation test.  The fp32 kernel's absolute error on incoherent (point-source) skies is
             # ~1-3.5e-6 of the incoherent norm sqrt(mean_f sum_s a^2) (measured), the tolerance 1e-5 of each
             # baseline's rms: baselines whose spectrum cancels below cancel_ratio x that norm go to fp64.
-            a2 = torch.sqrt(amp32.double().square().sum() / nchan)
+            a2 = torch.linalg.vector_norm(amp32, dtype=torch.float64) / (nchan ** 0.5)       # one pass, no fp64 copy of the table
             rms_b = torch.sqrt(skyvis.real.square().mean(dim=1) + skyvis.imag.square().mean(dim=1))
             low = rms_b < self.cancel_ratio * a2
             flagged = torch.nonzero(low).flatten()

@@ -249,6 +249,9 @@ class ShardedObserver(object):
         self.rows = shard_rows(self.nbl_total, self.world, self.rank, self.interleave)
         self.ia = make_sharded_array(cls, labels, baselines, channels, rank=self.rank, world_size=self.world, interleave=self.interleave,
                                      **kwargs)
+        # the sampled fp64 audit of the precision control is a property of the snapshot, not of a shard: spread its baselines over the ranks
+        if self.world > 1 and hasattr(self.ia, "audit_baselines"):
+            self.ia.audit_baselines = max(4, -(-self.ia.audit_baselines // self.world))
         self.gbufs, self._turn = [], 0
         if self.world > 1:
             for _ in range(max(1, int(nbuf))):

@@ -184,6 +184,7 @@ def _two_gpu_worker(rank, port, q):
         res["mode"] = so.gbuf.mode
         # (2) every rank's block computed into private memory, gathered over NCCL: must be the same bits
         ia = make_sharded_array(InterferometerArray, labels, bl, chans, interleave=True, **kw)
+        ia.audit_baselines = so.ia.audit_baselines                            # audited rows are stored in fp64: same audit set, same bits
         ia.observe(*args)
         priv = gather_baseline_shards(ia.skyvis_freq_device(0), bl.shape[0], dst=0, interleave=True)
         # (3) the NCCL fallback of the gather buffer
