@@ -262,9 +262,10 @@ template <int KTV>
 __global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
   __shared__ double2 tile[KTV][33];
   const Sched sc = P.sc;
-  const size_t t = blockIdx.x;                          // (output tile * 16 + warp)
-  const int warp = (int)(t % NWARPS);
-  const int ot = (int)(t / NWARPS);
+  const int nw = P.wb * P.wc;                           // warps per output tile
+  const size_t t = blockIdx.x;                          // (output tile * nw + warp)
+  const int warp = (int)(t % nw);
+  const int ot = (int)(t / nw);
   const int gx = ot % sc.gx, gy = ot / sc.gx;
   const int wb = warp % P.wb, wc = warp / P.wb;
   const size_t wtile = (size_t)KTV * 32;                // double2 per warp tile
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(256) k_skyvis_finalize(const SkyvisParams P) {
     double2 v = P.accum[t * wtile + k * 32 + tx];
     for (int c = c_lo; c < c_hi; ++c) {
       if (U * (c + 1) / sc.ncta == U * c / sc.ncta) continue;      // empty range: no head partial was written
-      const double2 h = P.accum[((size_t)(sc.ntile + c) * NWARPS + warp) * wtile + k * 32 + tx];
+      const double2 h = P.accum[((size_t)(sc.ntile + c) * nw + warp) * wtile + k * 32 + tx];
       v.x += h.x; v.y += h.y;
     }
     tile[k][tx] = v;
@@ -835,10 +836,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_direct(const SkyvisParam
 //     w_{k+1} = w_k g_k, g_{k+1} = g_k + g_k (h - 1) and a w first: 7 DFMA per term (was 8 with the taper folded
 //     into a complex rotation).
 // =================================================================================================
+#ifndef PB_F64_WB
+#define PB_F64_WB 2                           // baseline warps per CTA: 2 = one 512-thread CTA per SM; 1 = 256-thread CTAs, two per SM (measured: no gain)
+#endif
+#ifndef PB_F64_ABLATE
+#define PB_F64_ABLATE 0                       // timing experiments only (wrong results): 1 = no stage after the first, 2 = no channel loop
+#endif
 constexpr int KT64 = 16;
-constexpr int WC64 = PB200_SLAB / KT64;       // 8
-constexpr int WB64 = NWARPS / WC64;           // 2
-constexpr int BL64 = 32 * WB64;               // 64
+constexpr int WC64 = PB200_SLAB / KT64;       // 8 channel blocks = one slab
+constexpr int WB64 = PB_F64_WB;
+constexpr int NW64 = WC64 * WB64;             // warps per CTA
+constexpr int NT64 = 32 * NW64;
+constexpr int BL64 = 32 * WB64;               // baselines per CTA
+constexpr int T64 = 16 * WB64;                // source rows per TMA tile (half the shared memory of T = 32 for the two-CTA shape)
+constexpr int CTAS64 = 2 / WB64;              // resident CTAs per SM
+static_assert(WB64 == 1 || WB64 == 2, "fp64 CTA shape");
 template <bool TAPER> struct Sub64 { static constexpr int TS = TAPER ? 4 : 8; };   // sources per cooperative sub-tile
 template <int TS> struct __align__(16) Pre64 {
   double2 anc[TS][WC64][BL64];                // exp(-2 pi i tau f) at the first channel of every 16-channel block
@@ -850,14 +862,14 @@ template <int TS> struct __align__(16) Pre64Taper {
   double hm1[TS][BL64];                       // g_{k+1} / g_k - 1 (the same for every channel)
 };
 template <typename AMP> struct __align__(16) TileIn64 {
-  AMP amp[T][PB200_SLAB];
-  double geom[T][4];
+  AMP amp[T64][PB200_SLAB];
+  double geom[T64][4];
 };
 
 template <typename AMP, bool TAPER>
-__global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams P) {
+__global__ void __launch_bounds__(NT64, CTAS64) k_skyvis_fp64(const SkyvisParams P) {
   constexpr int TS = Sub64<TAPER>::TS;
-  constexpr int NSUB = T / TS;
+  constexpr int NSUB = T64 / TS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileIn64<AMP>* tin = reinterpret_cast<TileIn64<AMP>*>(smem_raw);
   Pre64<TS>* pre = reinterpret_cast<Pre64<TS>*>(smem_raw + NSTAGE * sizeof(TileIn64<AMP>));
@@ -890,10 +902,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
     const double tF0 = fs0 * 1e-8, tdF = df * 1e-8;
     const AMP* amp_slab = (const AMP*)P.amp + (size_t)slab * P.nsrc_pad * PB200_SLAB;
     auto issue = [&](int i, int stage) {
-      const size_t row0 = (size_t)(sg.s0 + i) * T;
+      const size_t row0 = (size_t)(sg.s0 + i) * T64;
       mbar_expect_tx(&full[stage], (uint32_t)sizeof(TileIn64<AMP>));
-      tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + row0 * PB200_SLAB, sizeof(AMP) * T * PB200_SLAB, &full[stage]);
-      tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T * 4, &full[stage]);
+      tma_bulk_g2s(&tin[stage].amp[0][0], amp_slab + row0 * PB200_SLAB, sizeof(AMP) * T64 * PB200_SLAB, &full[stage]);
+      tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T64 * 4, &full[stage]);
     };
     if (tid == 0) {
       issue(0, fill & 1);
@@ -906,6 +918,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
     auto stage_sub = [&](int tile, int sub) {
       const int st = (fill + tile) & 1;
       if (sub == 0) mbar_wait(&full[st], ((fill + tile) >> 1) & 1);
+      if (PB_F64_ABLATE == 1 && (tile | sub) != 0) return;
       const int buf = (tile * NSUB + sub) & 1;
       const int ss = TAPER ? (wc & (TS - 1)) : wc;                           // source of the sub-tile this thread works on
       const bool do_phasor = !TAPER || wc < TS, do_taper = TAPER && wc >= TS;
@@ -967,7 +980,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
         else if (tile + 1 < ntiles) stage_sub(tile + 1, 0);
         const int buf = (tile * NSUB + sub) & 1;
 #pragma unroll 1
-        for (int ss = 0; ss < TS; ++ss) {
+        for (int ss = 0; ss < (PB_F64_ABLATE == 2 ? 0 : TS); ++ss) {
           const double2 z0 = pre[buf].anc[ss][wc][bcol];
           const double2 r = pre[buf].rot[ss][bcol];
           const AMP* arow = &ti.amp[sub * TS + ss][wc * KT64];
@@ -1009,7 +1022,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_fp64(const SkyvisParams 
       if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, st);
     }
     // partial sums of this segment -> scratch slot (k_skyvis_finalize adds head partials and transposes)
-    double2* base = P.accum + ((sg.slot * NWARPS + warp) * KT64) * 32 + lane;
+    double2* base = P.accum + ((sg.slot * NW64 + warp) * KT64) * 32 + lane;
 #pragma unroll
     for (int k = 0; k < KT64; ++k) base[k * 32] = make_double2(acc_re[k], acc_im[k]);
     fill += (uint32_t)ntiles;
@@ -1110,40 +1123,45 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   if (mode == 3 && spc == 1) mode = 0;       // the r^8 table of the quarter form does not fit beside 128-baseline tiles (258 KB): plain rotation
   P.kt = fp64 ? KT64 : KT;
   P.wc = fp64 ? WC64 : spc * WCS;
-  P.wb = NWARPS / P.wc;
+  P.wb = fp64 ? WB64 : NWARPS / P.wc;
+  const int nw = P.wb * P.wc;                 // warps per CTA
   const int bl_per_cta = 32 * P.wb;
   // persistent schedule (struct Sched): one CTA per SM (every variant needs > half of an SM's shared memory or registers)
   Sched& sc = P.sc;
   sc.gx = pb_div_up(nslab, spc);
   sc.ntile = sc.gx * pb_div_up(nbl, bl_per_cta);
-  sc.S = nsrc_pad / T;
+  sc.S = nsrc_pad / (fp64 ? T64 : T);
   const long long units = (long long)sc.ntile * sc.S;
-  sc.ncta = (int)(units < ctx->sm_count ? units : ctx->sm_count);
+  const int resident = ctx->sm_count * (fp64 ? CTAS64 : 1);
+  sc.ncta = (int)(units < resident ? units : resident);
   sc.nwave = sc.ntile / sc.ncta;
   sc.ntail = sc.ntile % sc.ncta;
-  const size_t slot_bytes = (size_t)NWARPS * P.kt * 32 * sizeof(double2);
+  const size_t slot_bytes = (size_t)nw * P.kt * 32 * sizeof(double2);
   void* accum;
   rc = pb_scratch(ctx, 4, ((size_t)sc.ntile + sc.ncta) * slot_bytes, &accum);
   if (rc) return rc;
   P.accum = (double2*)accum;
   const dim3 grid(sc.ncta);
-#define LAUNCH(KERNEL, SMEM)                                                                              \
+#define LAUNCH_N(KERNEL, SMEM, NT)                                                                        \
   do {                                                                                                    \
     PB_CUDA(ctx, cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM))); \
-    KERNEL<<<grid, NTHREADS, (SMEM), stream>>>(P);                                                        \
+    if ((NT) != NTHREADS) /* two CTAs per SM need the full shared-memory carve-out */                    \
+      PB_CUDA(ctx, cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); \
+    KERNEL<<<grid, (NT), (SMEM), stream>>>(P);                                                            \
   } while (0)
+#define LAUNCH(KERNEL, SMEM) LAUNCH_N(KERNEL, SMEM, NTHREADS)
   if (fp64) {
 #define SMEM64(AMP, TP) (NSTAGE * sizeof(TileIn64<AMP>) + 2 * sizeof(Pre64<Sub64<TP>::TS>) + (TP ? 2 * sizeof(Pre64Taper<Sub64<TP>::TS>) : 0) + 64)
     if (amp_dtype == PB200_AMP_F64) {
-      if (taper) LAUNCH((k_skyvis_fp64<double, true>), SMEM64(double, true));
-      else LAUNCH((k_skyvis_fp64<double, false>), SMEM64(double, false));
+      if (taper) LAUNCH_N((k_skyvis_fp64<double, true>), SMEM64(double, true), NT64);
+      else LAUNCH_N((k_skyvis_fp64<double, false>), SMEM64(double, false), NT64);
     } else {
-      if (taper) LAUNCH((k_skyvis_fp64<float, true>), SMEM64(float, true));
-      else LAUNCH((k_skyvis_fp64<float, false>), SMEM64(float, false));
+      if (taper) LAUNCH_N((k_skyvis_fp64<float, true>), SMEM64(float, true), NT64);
+      else LAUNCH_N((k_skyvis_fp64<float, false>), SMEM64(float, false), NT64);
     }
 #undef SMEM64
     PB_CHECK_LAUNCH(ctx, "k_skyvis_fp64");
-    k_skyvis_finalize<KT64><<<(unsigned)sc.ntile * NWARPS, 256, 0, stream>>>(P);
+    k_skyvis_finalize<KT64><<<(unsigned)sc.ntile * nw, 256, 0, stream>>>(P);
     PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
     return PB200_OK;
   }
@@ -1181,6 +1199,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
 #undef LAUNCH_REC
 #undef SMEM_REC
 #undef LAUNCH
+#undef LAUNCH_N
   PB_CHECK_LAUNCH(ctx, "k_skyvis");
   k_skyvis_finalize<KT><<<(unsigned)sc.ntile * NWARPS, 256, 0, stream>>>(P);
   PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
