@@ -177,7 +177,7 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
  *   d_vis      [nbl,nchan] complex128, overwritten; consecutive baseline rows are vis_row_stride complex elements
  *              apart (0 = nchan, i.e. dense).  A multiple of nchan addresses every n-th row of a larger array: the
  *              interleaved baseline shard of one rank inside the writing rank's buffer (sharding.py).
- *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM | _RECURRENCE_QUARTER
+ *   method     PB200_SKYVIS_AUTO | _RECURRENCE | _DIRECT | _RECURRENCE_SCALAR | _FP64 | _RECURRENCE_LIFT | _RECURRENCE_3TERM | _RECURRENCE_QUARTER | _RECURRENCE_PAIR
  */
 #define PB200_SKYVIS_AUTO       0
 #define PB200_SKYVIS_RECURRENCE 1
@@ -192,6 +192,8 @@ int pb200_amp_scale(pb200_ctx* ctx, const void* d_amp_in, int amp_dtype, int nsr
 #define PB200_SKYVIS_RECURRENCE_QUARTER 8   /* packed "quarter blocks": one MUFU anchor pair per source, the other three 8-channel quarters anchored by
                                               exact r^8 rotations, inside a quarter one r^2 rotation + two three-term steps: 76 instead of 92 packed
                                               instructions per source (the taper keeps the plain rotation) */
+#define PB200_SKYVIS_RECURRENCE_PAIR 9      /* the quarter-block arithmetic with one thread owning two baselines x 16 channels, so that every amplitude
+                                              load feeds two baselines (A/B; point sources, nchan a multiple of 256) */
 int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* d_amp, int amp_dtype, int nsrc,
                  const double* d_bl, int nbl, const double* h_pc, const double* h_freqs, int nchan,
                  const double* d_src_fwhm_deg, int nsrc_bright, void* d_vis, long long vis_row_stride, int method,

@@ -20,6 +20,7 @@ ARRAY_NONE, ARRAY_ANALYTIC, ARRAY_ELEMENTS = 0, 1, 2
 DIPOLE_GENERAL, DIPOLE_SHORT, DIPOLE_HALFWAVE = 0, 1, 2
 SKYVIS_AUTO, SKYVIS_RECURRENCE, SKYVIS_DIRECT, SKYVIS_RECURRENCE_SCALAR, SKYVIS_FP64, SKYVIS_RECURRENCE_LIFT, SKYVIS_RECURRENCE_3TERM, SKYVIS_RECURRENCE_3TERM_SCALAR = 0, 1, 2, 3, 4, 5, 6, 7
 SKYVIS_RECURRENCE_QUARTER = 8
+SKYVIS_RECURRENCE_PAIR = 9
 SLAB, SRC_TILE = 128, 32
 AMP_F32, AMP_F64 = 0, 1
 

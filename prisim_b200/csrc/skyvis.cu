@@ -726,6 +726,188 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
 }
 
 // =================================================================================================
+// Pair form of the quarter-block recurrence: one thread = TWO baselines x 16 channels
+// =================================================================================================
+// Same arithmetic per (baseline, channel) as MODE 3 of k_skyvis, other ownership: a lane owns baselines `lane` and `lane + 32`
+// of a 64-baseline CTA row and 16 consecutive channels (two 8-channel quarters), so that every broadcast LDS.128 of four
+// amplitudes feeds two baselines (4 instead of 8 amplitude loads per 32 terms; the round-1 ablation priced the amplitude
+// loads at 15 % of the loop).  The price is one anchor (fp64 range reduction + 4 MUFU) per 16 instead of per 32 terms, on pipes
+// that are otherwise idle.  CTA = 16 warps = 16 channel blocks (2 slabs, 256 channels) x 64 baselines; the cooperative stage
+// is shared by 16 channel-block warps as in the 4-slab shape of k_skyvis.  Scratch layout: each thread writes its two
+// baselines as two "virtual warps" (2 * warp + half) of 16 channels x 32 lanes, so k_skyvis_finalize<16> with wc = 16,
+// wb = 2 transposes it like any other launch.
+#ifndef PB_PAIR_UNROLL
+#define PB_PAIR_UNROLL 1
+#endif
+#ifndef PB_PAIR_UNROLL
+#define PB_PAIR_UNROLL 1
+#endif
+constexpr int PAIR_UNROLL = PB_PAIR_UNROLL;
+constexpr int KTP = 16;                       // channels per thread
+constexpr int SPCP = 2;                       // slabs per CTA
+constexpr int WCP = SPCP * PB200_SLAB / KTP;  // 16 channel blocks = warps
+constexpr int BLP = 64;                       // baselines per CTA
+static_assert(WCP == NWARPS, "pair form: one warp per channel block");
+struct __align__(16) TilePreP {
+  double tau[T][BLP];
+  float2 rot[T][BLP];                         // r^2
+  float2 rot8[T][BLP];                        // r^8
+  float xd[T][BLP];                           // MUFU argument increment of one channel
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_skyvis_pair(const SkyvisParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TileIn<SPCP>* tin = reinterpret_cast<TileIn<SPCP>*>(smem_raw);
+  TilePreP* tpre = reinterpret_cast<TilePreP*>(smem_raw + NSTAGE * sizeof(TileIn<SPCP>));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NSTAGE * (sizeof(TileIn<SPCP>) + sizeof(TilePreP)));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sl = warp / (WCP / SPCP), wcs = warp % (WCP / SPCP);   // slab within the CTA, 16-channel block within the slab
+  const int scol = tid & (BLP - 1), sgrp = tid / BLP;              // stage: baseline column and source group (8 groups x 4 sources)
+  const double df = P.df;
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  float2 acc_re[2][KTP / 2], acc_im[2][KTP / 2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < KTP / 2; ++k) { acc_re[h][k] = make_float2(0.f, 0.f); acc_im[h][k] = make_float2(0.f, 0.f); }
+
+  // fp32 partial sums -> fp64 running sums of the segment's slot (see flush_acc), one virtual warp per baseline half
+  auto flush = [&](size_t slot, bool first, bool last) {
+    const uint64_t keep = PB_L2_HINTS ? (last ? l2_policy_evict_first() : l2_policy_evict_last()) : 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double2* base = P.accum + ((slot * (2 * NWARPS) + 2 * warp + h) * KTP) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < KTP; ++k) {
+        double2 v = first ? make_double2(0.0, 0.0) : (PB_L2_HINTS ? ld_keep(base + k * 32, keep) : base[k * 32]);
+        v.x += (double)((k & 1) ? acc_re[h][k >> 1].y : acc_re[h][k >> 1].x);
+        v.y += (double)((k & 1) ? acc_im[h][k >> 1].y : acc_im[h][k >> 1].x);
+        if (PB_L2_HINTS) st_keep(base + k * 32, v, keep);
+        else base[k * 32] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < KTP / 2; ++k) { acc_re[h][k] = make_float2(0.f, 0.f); acc_im[h][k] = make_float2(0.f, 0.f); }
+    }
+  };
+
+  uint32_t fill = 0;
+  SegmentIter seg_iter(P.sc, (int)blockIdx.x);
+  Segment sg;
+#pragma unroll 1
+  while (seg_iter.next(sg)) {
+    const int tile_x = sg.tile % P.sc.gx, tile_y = sg.tile / P.sc.gx;
+    const int kbase = (tile_x * SPCP + sl) * PB200_SLAB + wcs * KTP;     // first global channel of this thread
+    const int ntiles = sg.s1 - sg.s0;
+    const int bs = tile_y * BLP + scol;                                    // the baseline this thread stages
+    const Geometry G = load_baseline(P, bs, bs < P.nbl);
+    const double fk0 = P.f0 + (double)kbase * P.df;
+    auto issue = [&](int i, int stage) {
+      const size_t row0 = (size_t)(sg.s0 + i) * T;
+      mbar_expect_tx(&full[stage], (uint32_t)(SPCP * sizeof(float) * T * PB200_SLAB + sizeof(double) * T * 4));
+      for (int j = 0; j < SPCP; ++j)
+        tma_bulk_g2s(&tin[stage].amp[j][0][0], (const float*)P.amp + ((size_t)(tile_x * SPCP + j) * P.nsrc_pad + row0) * PB200_SLAB,
+                     sizeof(float) * T * PB200_SLAB, &full[stage]);
+      tma_bulk_g2s(&tin[stage].geom[0][0], P.geom + row0 * 4, sizeof(double) * T * 4, &full[stage]);
+    };
+    if (tid == 0) {
+      issue(0, fill & 1);
+      if (ntiles > 1) issue(1, (fill + 1) & 1);
+    }
+    // cooperative per-tile stage: tau, r^2, r^8 and the one-channel argument increment of 4 sources of this thread's column
+    auto precompute = [&](int tile) {
+      const int stage = (fill + tile) & 1;
+      mbar_wait(&full[stage], ((fill + tile) >> 1) & 1);
+#pragma unroll 2
+      for (int j = 0; j < T * BLP / NTHREADS; ++j) {
+        const int s = sgrp + (NTHREADS / BLP) * j;
+        const double4 g = *reinterpret_cast<const double4*>(&tin[stage].geom[s][0]);
+        const double tau = g.x * G.bx + g.y * G.by + g.z * G.bz - G.tau_pc;     // baseline_delay_horizon.py:240, interferometry.py:6332
+        tpre[stage].tau[s][scol] = tau;
+        tpre[stage].rot[s][scol] = rotation_phasor(2.0 * tau * df);
+        tpre[stage].rot8[s][scol] = rotation_phasor(8.0 * tau * df);
+        tpre[stage].xd[s][scol] = anchor_arg(tau * df);
+      }
+    };
+    precompute(0);
+    __syncthreads();
+
+    bool fresh = true;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int stage = (fill + tile) & 1;
+      const TileIn<SPCP>& ti = tin[stage];
+      const TilePreP& tp = tpre[stage];
+      // unit u = 2 s + h: (source s, baseline half h); the anchors / rotations of unit u + 1 are fetched while unit u runs
+      auto fetch = [&](int u, float& x, float& xd) {           // the fp64 part of the anchors of unit u
+        const int s = u >> 1, col = lane + 32 * (u & 1);
+        x = anchor_arg(tp.tau[s][col] * fk0);
+        xd = tp.xd[s][col];
+      };
+      float x_n, xd_n;
+      fetch(0, x_n, xd_n);
+#pragma unroll 1
+      for (int chunk = 0; chunk < STAGGER; ++chunk) {
+        if (chunk == (warp >> 2) % STAGGER && tile + 1 < ntiles) precompute(tile + 1);
+#pragma unroll PAIR_UNROLL
+        for (int s = chunk * (T / STAGGER); s < (chunk + 1) * (T / STAGGER); ++s) {
+          const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KTP]);
+          const float4 a0 = arow[0], a1 = arow[1], a2 = arow[2], a3 = arow[3];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float2 p0 = mufu_phasor(x_n), q0 = mufu_phasor(x_n + xd_n);
+            const float2 r = tp.rot[s][lane + 32 * h], r8 = tp.rot8[s][lane + 32 * h];
+            fetch(min(2 * s + h + 1, 2 * T - 1), x_n, xd_n);
+            const float2 RR = make_float2(r.x, r.x), RI = make_float2(r.y, r.y), NRI = make_float2(-r.y, -r.y);
+            const float2 CC = make_float2(2.0f * r.x, 2.0f * r.x);
+            const float2 ER = make_float2(r8.x, r8.x), EI = make_float2(r8.y, r8.y), NEI = make_float2(-r8.y, -r8.y);
+            float2 PR = make_float2(p0.x, q0.x), PI = make_float2(p0.y, q0.y);          // pair 0 of quarter 0
+#pragma unroll
+            for (int qd = 0; qd < KTP / 8; ++qd) {
+              const float4 a4 = qd == 0 ? a0 : a2, b4 = qd == 0 ? a1 : a3;
+              const float2 A0 = make_float2(a4.x, a4.y), A1 = make_float2(a4.z, a4.w), A2 = make_float2(b4.x, b4.y), A3 = make_float2(b4.z, b4.w);
+              const int j = 4 * qd;
+              float2 QR = PR, QI = PI;
+              if (qd + 1 < KTP / 8) {                            // anchor pair of the next quarter: this one rotated by r^8
+                const float2 u1 = __fmul2_rn(PR, ER), u2 = __fmul2_rn(PR, EI);
+                QR = __ffma2_rn(PI, NEI, u1);
+                QI = __ffma2_rn(PI, ER, u2);
+              }
+              const float2 t1 = __fmul2_rn(PR, RR), t2 = __fmul2_rn(PR, RI);
+              acc_re[h][j] = __ffma2_rn(PR, A0, acc_re[h][j]);
+              acc_im[h][j] = __ffma2_rn(PI, A0, acc_im[h][j]);
+              const float2 P1R = __ffma2_rn(PI, NRI, t1), P1I = __ffma2_rn(PI, RR, t2);      // pair 1 = pair 0 x r^2
+              acc_re[h][j + 1] = __ffma2_rn(P1R, A1, acc_re[h][j + 1]);
+              acc_im[h][j + 1] = __ffma2_rn(P1I, A1, acc_im[h][j + 1]);
+              const float2 P2R = __ffma2_rn(CC, P1R, make_float2(-PR.x, -PR.y)), P2I = __ffma2_rn(CC, P1I, make_float2(-PI.x, -PI.y));
+              acc_re[h][j + 2] = __ffma2_rn(P2R, A2, acc_re[h][j + 2]);
+              acc_im[h][j + 2] = __ffma2_rn(P2I, A2, acc_im[h][j + 2]);
+              const float2 P3R = __ffma2_rn(CC, P2R, make_float2(-P1R.x, -P1R.y)), P3I = __ffma2_rn(CC, P2I, make_float2(-P1I.x, -P1I.y));
+              acc_re[h][j + 3] = __ffma2_rn(P3R, A3, acc_re[h][j + 3]);
+              acc_im[h][j + 3] = __ffma2_rn(P3I, A3, acc_im[h][j + 3]);
+              PR = QR; PI = QI;
+            }
+          }
+        }
+      }
+      __syncthreads();                                   // tile consumed, next tile's stage visible
+      if (tid == 0 && tile + NSTAGE < ntiles) issue(tile + NSTAGE, stage);
+      const bool bright = sg.s0 + tile < P.bright_tiles;
+      if (bright || ((tile + 1 + (warp >> 2) * (FLUSH_TILES / 4)) % FLUSH_TILES) == 0) {
+        flush(sg.slot, fresh, false);
+        fresh = false;
+      }
+    }
+    flush(sg.slot, fresh, true);
+    fill += (uint32_t)ntiles;
+  }
+}
+
+// =================================================================================================
 // Direct kernel: arbitrary channel frequencies, one accurate sincospi per term (no recurrence)
 // =================================================================================================
 template <bool TAPER>
@@ -1064,7 +1246,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   if (nsrc > 0 && (!d_dircos || !d_amp)) return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: null source arrays");
   if (amp_dtype != PB200_AMP_F32 && !(amp_dtype == PB200_AMP_F64 && method == PB200_SKYVIS_FP64))
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: an fp64 amplitude table needs method PB200_SKYVIS_FP64");
-  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_QUARTER)
+  if (method < PB200_SKYVIS_AUTO || method > PB200_SKYVIS_RECURRENCE_PAIR)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: unknown method");
   cudaStream_t stream = (cudaStream_t)stream_;
   PbDeviceGuard guard(ctx->device);
@@ -1080,7 +1262,7 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   const bool uniform = pb200_channels_uniform(h_freqs, nchan) != 0;
   const bool want_rec = (method == PB200_SKYVIS_RECURRENCE || method == PB200_SKYVIS_RECURRENCE_SCALAR || method == PB200_SKYVIS_FP64 ||
                          method == PB200_SKYVIS_RECURRENCE_LIFT || method == PB200_SKYVIS_RECURRENCE_3TERM || method == PB200_SKYVIS_RECURRENCE_3TERM_SCALAR ||
-                         method == PB200_SKYVIS_RECURRENCE_QUARTER);
+                         method == PB200_SKYVIS_RECURRENCE_QUARTER || method == PB200_SKYVIS_RECURRENCE_PAIR);
   const bool direct = (method == PB200_SKYVIS_DIRECT) || (method == PB200_SKYVIS_AUTO && !uniform);
   if (want_rec && !uniform)
     return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: recurrence kernel needs uniformly spaced channels");
@@ -1118,12 +1300,15 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
   // extent the slab count allows: the (source, baseline) delay / rotation stage is shared by all channel-block warps of a CTA
   // (round 1 measured 4.10 / 4.34 / 4.31 Tterms/s for 1 / 2 / 4 slabs, the round-2 kernel 4.46 / 4.54 / 4.65)
   const bool fp64 = method == PB200_SKYVIS_FP64;
-  int spc = (direct || fp64) ? 1 : (nslab % 4 == 0 ? 4 : (nslab % 2 == 0 ? 2 : 1));
-  if (!direct && !fp64 && (ctx->skyvis_spc_env == 1 || ctx->skyvis_spc_env == 2 || ctx->skyvis_spc_env == 4)) spc = ctx->skyvis_spc_env;
+  const bool pair = method == PB200_SKYVIS_RECURRENCE_PAIR;
+  if (pair && (taper || nslab % SPCP != 0))
+    return pb_fail(ctx, PB200_EINVAL, "pb200_skyvis: the pair form needs point sources and a multiple of 256 channels");
+  int spc = (direct || fp64) ? 1 : (pair ? SPCP : (nslab % 4 == 0 ? 4 : (nslab % 2 == 0 ? 2 : 1)));
+  if (!direct && !fp64 && !pair && (ctx->skyvis_spc_env == 1 || ctx->skyvis_spc_env == 2 || ctx->skyvis_spc_env == 4)) spc = ctx->skyvis_spc_env;
   if (mode == 3 && spc == 1) mode = 0;       // the r^8 table of the quarter form does not fit beside 128-baseline tiles (258 KB): plain rotation
-  P.kt = fp64 ? KT64 : KT;
-  P.wc = fp64 ? WC64 : spc * WCS;
-  P.wb = fp64 ? WB64 : NWARPS / P.wc;
+  P.kt = fp64 ? KT64 : (pair ? KTP : KT);
+  P.wc = fp64 ? WC64 : (pair ? WCP : spc * WCS);
+  P.wb = fp64 ? WB64 : (pair ? 2 : NWARPS / P.wc);       // pair form: the two baseline halves of a thread are two virtual warps
   const int nw = P.wb * P.wc;                 // warps per CTA
   const int bl_per_cta = 32 * P.wb;
   // persistent schedule (struct Sched): one CTA per SM (every variant needs > half of an SM's shared memory or registers)
@@ -1162,6 +1347,13 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
 #undef SMEM64
     PB_CHECK_LAUNCH(ctx, "k_skyvis_fp64");
     k_skyvis_finalize<KT64><<<(unsigned)sc.ntile * nw, 256, 0, stream>>>(P);
+    PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
+    return PB200_OK;
+  }
+  if (pair) {
+    LAUNCH(k_skyvis_pair, NSTAGE * (sizeof(TileIn<SPCP>) + sizeof(TilePreP)) + 64);
+    PB_CHECK_LAUNCH(ctx, "k_skyvis_pair");
+    k_skyvis_finalize<KTP><<<(unsigned)sc.ntile * nw, 256, 0, stream>>>(P);
     PB_CHECK_LAUNCH(ctx, "k_skyvis_finalize");
     return PB200_OK;
   }

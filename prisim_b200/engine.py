@@ -158,7 +158,7 @@ def skyvis(dircos, amp, nsrc, baselines_enu, pc_dircos, freqs_hz, src_fwhm_deg=N
     code = {"auto": _lib.SKYVIS_AUTO, "recurrence": _lib.SKYVIS_RECURRENCE, "direct": _lib.SKYVIS_DIRECT,
             "recurrence_scalar": _lib.SKYVIS_RECURRENCE_SCALAR, "fp64": _lib.SKYVIS_FP64,
             "recurrence_lift": _lib.SKYVIS_RECURRENCE_LIFT, "recurrence_3term": _lib.SKYVIS_RECURRENCE_3TERM, "recurrence_3term_scalar": _lib.SKYVIS_RECURRENCE_3TERM_SCALAR,
-            "recurrence_quarter": _lib.SKYVIS_RECURRENCE_QUARTER}[method]
+            "recurrence_quarter": _lib.SKYVIS_RECURRENCE_QUARTER, "recurrence_pair": _lib.SKYVIS_RECURRENCE_PAIR}[method]
     amp_dtype = _lib.AMP_F64 if (amp is not None and amp.dtype == torch.float64) else _lib.AMP_F32
     ctx.check(ctx.lib.pb200_skyvis(ctx.handle, _ptr(dircos), _ptr(amp), amp_dtype, int(nsrc), _ptr(bl), int(nbl), _ptr(pc),
                                    _ptr(freqs), int(nchan), _ptr(src_fwhm_deg), int(nsrc_bright), _ptr(out), int(row_stride), code, ctx.stream()))

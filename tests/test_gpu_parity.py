@@ -282,9 +282,12 @@ def test_skyvis_persistent_schedule_waves_and_tail(eng, nbl, nchan, nsrc):
     pc = (0.0, 0.0, 1.0)
     V64 = eng.skyvis(dircos, amp64, nsrc, bl, pc, freqs, method="fp64")
     rms_b = V64.abs().pow(2).mean(dim=1, keepdim=True).sqrt()
-    for method in ("recurrence", "direct"):
+    for method in ("recurrence", "direct") + (("recurrence_pair",) if nchan % 256 == 0 else ()):
         V = eng.skyvis(dircos, amp, nsrc, bl, pc, freqs, method=method)
         assert ((V - V64).abs() / rms_b).max().item() <= TOL, method
+    if nchan % 256:                                    # the pair form (two baselines x 16 channels per thread) says so when it does not apply
+        with pytest.raises(Exception, match="pair form"):
+            eng.skyvis(dircos, amp, nsrc, bl, pc, freqs, method="recurrence_pair")
     rows = NP.unique(NP.concatenate(([0, nbl - 1], rng.choice(nbl, 40, replace=False))))
     amp32 = eng.amp_table_to_dense(amp, nsrc, nchan).double().cpu().numpy()
     Vo = O.skyvis_snapshot(bl[rows], altaz, amp32, freqs, NP.asarray([90.0, 270.0]))
