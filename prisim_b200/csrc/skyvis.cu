@@ -63,6 +63,11 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
 #ifndef PB_STAGE_FP64      // 1: the stage's rotations r^2 (and r^8) from ONE fp64 sincospi + two fp64 complex squarings (FP64 pipe, idle otherwise)
 #define PB_STAGE_FP64 0    // instead of one fp32 sincospif + first-order correction each (~25 FMA-pipe instructions each)
 #endif
+#ifndef PB_Q3_INT          // quarter-block form: 1 = the per-source anchor argument from 32-bit fixed-point turn fractions staged per (source,
+#define PB_Q3_INT 1        // baseline) -- X0 + block * D in one IMAD, then I2F.F64, DMUL, F2F instead of DMUL, 3 DADD, DMUL, F2F -- and the stage
+#endif                     // products packed into two 16-byte records (2 LDS.128 instead of 3 LDS.64 + 1 LDS.32 per source): 94 instead of 124
+                           // non-FMA instructions per 4 sources.  Config 2, two A/B rounds in one session: 4.84 / 4.85 vs 4.70 / 4.67 Tterms/s,
+                           // max error 3.29e-6 vs 3.30e-6 (an fp32 scale constant instead of the fp64 product: 4.90 but 6.5e-6)
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
 #define PB_ABLATE 0        // precompute after tile 0, 2 = skip the anchors, 4 = skip the flushes, 8 = constant amplitudes
 #endif
@@ -131,6 +136,10 @@ template <int SPC> struct __align__(16) TilePre {  // produced by the CTA once p
   float xd[T][Shape<SPC>::BL];                     // MUFU argument increment of one channel step (PB_TWO_ANCHOR == 2)
 };
 template <int SPC> struct __align__(16) TileRot8 { float2 rot8[T][Shape<SPC>::BL]; };   // eight-channel rotation r^8 (MODE 3)
+template <int SPC> struct __align__(16) TileQ3 {    // PB_Q3_INT: stage products of the quarter-block form, two 16-byte records per pair
+  uint4 xa[T][Shape<SPC>::BL];                       // anchor phase at the CTA's first channel and its step per 32-channel block (2^-32 turn), argument increment (float bits), 0
+  float4 rr[T][Shape<SPC>::BL];                      // r^2 (x, y), r^8 (z, w)
+};
 template <int SPC> struct __align__(16) TileKap { float kap[T][Shape<SPC>::BL]; };   // taper exponent coefficient
 
 // fraction of x in [-0.5, 0.5] (round-to-nearest-even magic number; |x| < 2^51)
@@ -319,8 +328,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   constexpr int WB = S::WB, WC = S::WC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileIn<SPC>* tin = reinterpret_cast<TileIn<SPC>*>(smem_raw);
+  constexpr bool Q3I = MODE == 3 && PB_Q3_INT;
   TilePre<SPC>* tpre = reinterpret_cast<TilePre<SPC>*>(smem_raw + NSTAGE * sizeof(TileIn<SPC>));
-  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>));
+  TileQ3<SPC>* tq3 = reinterpret_cast<TileQ3<SPC>*>(smem_raw + NSTAGE * sizeof(TileIn<SPC>));      // Q3I: instead of tpre / trot8
+  unsigned char* tail = smem_raw + NSTAGE * (sizeof(TileIn<SPC>) + (Q3I ? sizeof(TileQ3<SPC>) : sizeof(TilePre<SPC>)));
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);
   float* sfreq2 = reinterpret_cast<float*>(tail + 64);                     // [SPC*SLAB] (f/1e8)^2, taper only
   TileKap<SPC>* tkap = reinterpret_cast<TileKap<SPC>*>(tail + 64 + SPC * PB200_SLAB * sizeof(float));   // [NSTAGE], taper only
@@ -354,6 +365,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
   const int ntiles = sg.s1 - sg.s0;
   const Geometry G = load_baseline(P, b, valid);
   const double fk0 = P.f0 + (double)kbase * P.df;
+  const double fcta0 = P.f0 + (double)(tile_x * SPC * PB200_SLAB) * P.df;   // first channel of the CTA tile (Q3I)
 
   if (TAPER && tid < SPC * PB200_SLAB) {
     const int ch = tile_x * SPC * PB200_SLAB + tid;
@@ -407,6 +419,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const double4 g = *reinterpret_cast<const double4*>(&tin[stage].geom[s][0]);
       const double tau_g = g.x * G.bx + g.y * G.by + g.z * G.bz;            // baseline_delay_horizon.py:240
       const double tau = tau_g - G.tau_pc;                                  // interferometry.py:6332
+      if constexpr (Q3I) {
+        const int X0 = (int)__double2ll_rn(frac_turns(tau * fcta0) * 4294967296.0);           // wraps at +-1/2 turn, as the phase does
+        const int D = (int)__double2ll_rn(frac_turns(tau * (32.0 * df)) * 4294967296.0);
+        tq3[stage].xa[s][bcol] = make_uint4((unsigned)X0, (unsigned)D, __float_as_uint(anchor_arg(tau * df)), 0u);
+        const float2 r2 = rotation_phasor(2.0 * tau * df), r8 = rotation_phasor(8.0 * tau * df);
+        tq3[stage].rr[s][bcol] = make_float4(r2.x, r2.y, r8.x, r8.y);
+        continue;
+      }
       tpre[stage].tau[s][bcol] = tau;
       float2 rp;
       if (PB_STAGE_FP64 && MODE == 3) {
@@ -647,14 +667,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
     const TileIn<SPC>& ti = tin[stage];
     const TilePre<SPC>& tp = tpre[stage];
     const TileRot8<SPC>& t8 = trot8[stage];
+    const TileQ3<SPC>& tq = tq3[stage];
     auto anchors2 = [&](int s, float2& p, float2& q) {
-      const float x = anchor_arg(tp.tau[s][bcol] * fk0);
-      p = mufu_phasor(x);
-      q = mufu_phasor(x + tp.xd[s][bcol]);
+      if constexpr (Q3I) {
+        const uint4 a = tq.xa[s][bcol];
+        // the scale to MUFU units stays an fp64 product rounded once (an fp32 constant would bias every phase by its rounding error;
+        // measured: max error 6.5e-6 instead of 3.3e-6 on config 2)
+        const float x = (float)((double)(int)(a.x + (unsigned)wc * a.y) * (PB_INV_RCP2PI_F32 / 4294967296.0));
+        p = mufu_phasor(x);
+        q = mufu_phasor(x + __uint_as_float(a.z));
+      } else {
+        const float x = anchor_arg(tp.tau[s][bcol] * fk0);
+        p = mufu_phasor(x);
+        q = mufu_phasor(x + tp.xd[s][bcol]);
+      }
+    };
+    auto rotations = [&](int s, float2& r, float2& r8) {
+      if constexpr (Q3I) {
+        const float4 v = tq.rr[s][bcol];
+        r = make_float2(v.x, v.y); r8 = make_float2(v.z, v.w);
+      } else {
+        r = tp.rot[s][bcol]; r8 = t8.rot8[s][bcol];
+      }
     };
     float2 p_next, q_next;
     anchors2(0, p_next, q_next);
-    float2 r_next = tp.rot[0][bcol], r8_next = t8.rot8[0][bcol];
+    float2 r_next, r8_next;
+    rotations(0, r_next, r8_next);
 #pragma unroll 1
     for (int chunk = 0; chunk < STAGGER; ++chunk) {
     if (chunk == (warp >> 2) % STAGGER && tile + 1 < ntiles) precompute(tile + 1);
@@ -663,8 +702,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_skyvis(const SkyvisParams P) {
       const float2 p0 = p_next, q0 = q_next, r = r_next, r8 = r8_next;
       const int sn = (s + 1 < T) ? s + 1 : s;
       anchors2(sn, p_next, q_next);
-      r_next = tp.rot[sn][bcol];
-      r8_next = t8.rot8[sn][bcol];
+      rotations(sn, r_next, r8_next);
       const float4* arow = reinterpret_cast<const float4*>(&ti.amp[sl][s][wcs * KT]);
       const float2 RR = make_float2(r.x, r.x), RI = make_float2(r.y, r.y), NRI = make_float2(-r.y, -r.y);
       const float2 CC = make_float2(2.0f * r.x, 2.0f * r.x);
@@ -1358,7 +1396,8 @@ extern "C" int pb200_skyvis(pb200_ctx* ctx, const double* d_dircos, const void* 
     return PB200_OK;
   }
   const bool packed = method != PB200_SKYVIS_RECURRENCE_SCALAR && method != PB200_SKYVIS_RECURRENCE_3TERM_SCALAR;
-#define SMEM_REC(SPC) (NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) + \
+#define SMEM_REC(SPC) ((PB_Q3_INT && mode == 3 && !taper) ? NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TileQ3<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) : \
+                       NSTAGE * (sizeof(TileIn<SPC>) + sizeof(TilePre<SPC>)) + 64 + SPC * PB200_SLAB * sizeof(float) +                   \
                        (taper ? NSTAGE * sizeof(TileKap<SPC>) : 0) + (mode == 3 && !taper ? NSTAGE * sizeof(TileRot8<SPC>) : 0))
 #define LAUNCH_REC(SPC)                                                                   \
   do {                                                                                    \
