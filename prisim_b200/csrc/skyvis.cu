@@ -65,7 +65,7 @@ constexpr int T = PB200_SRC_TILE;              // sources per tile
 #endif
 #ifndef PB_Q3_INT          // quarter-block form: 1 = the per-source anchor argument from 32-bit fixed-point turn fractions staged per (source,
 #define PB_Q3_INT 1        // baseline) -- X0 + block * D in one IMAD, then I2F.F64, DMUL, F2F instead of DMUL, 3 DADD, DMUL, F2F -- and the stage
-#endif                     // products packed into two 16-byte records (2 LDS.128 instead of 3 LDS.64 + 1 LDS.32 per source): 94 instead of 124
+#endif                     // products packed into two 16-byte records (2 LDS.128 instead of 3 LDS.64 + 1 LDS.32 per source): 100 instead of 124
                            // non-FMA instructions per 4 sources.  Config 2, two A/B rounds in one session: 4.84 / 4.85 vs 4.70 / 4.67 Tterms/s,
                            // max error 3.29e-6 vs 3.30e-6 (an fp32 scale constant instead of the fp64 product: 4.90 but 6.5e-6)
 #ifndef PB_ABLATE          // developer ablation switches for tools/variants.sh (0 in the product): 1 = skip the per-tile
