@@ -4,26 +4,27 @@
 // and call numpy exp/sum on them.
 //
 // Design (DESIGN.md section "K1"):
-//   * FP32-FMA-issue bound, not HBM and not tensor cores: 6 FMA-pipe lane-issues per term (complex
-//     rotation 2 FMUL + 2 FFMA, accumulate 2 FFMA) is the algorithmic cost.
-//   * one thread owns one baseline x KT=32 consecutive channels, accumulators in registers; a
-//     warp's 32 lanes are 32 baselines of the same channel block, so amplitude reads are
-//     shared-memory broadcasts (one LDS.128 = 4 channels for the whole warp).
-//   * a CTA = 4 channel blocks (one PB200_SLAB-channel slab) x 4 baseline groups = 512 threads,
-//     128 baselines; it streams source tiles (32 rows of the slab + fp64 geometry, 17 KB) through
-//     a double-buffered shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier).
-//   * per tile the CTA first computes, cooperatively and once per (source, baseline), the delay
-//     tau = s.b/c - tau_pc in fp64 and the per-channel rotation r = exp(-2 pi i tau df) to full fp32
-//     accuracy (fp64 range reduction + first-order correction of the fp32 argument), and parks
-//     them in shared memory; the four channel-block warps that share a baseline reuse them.
-//   * each thread then anchors its channel block with exp(-2 pi i tau f_k0): the product is formed
-//     and range-reduced in fp64, pre-scaled in fp64 so that the MUFU's own 1/(2 pi) multiply lands
-//     on the reduced turn fraction without a systematic bias, and fed to MUFU.SIN/COS.
-//   * channels advance by the fp32 rotation, two channels per packed FFMA2 (sm_100 f32x2), which
-//     halves the issue slots of the 6-per-term core and leaves room for the anchor/LDS work.
-//   * fp32 accumulators are flushed into the fp64 output every FLUSH_TILES source tiles
-//     (<= 1024 sources); the output buffer itself is the fp64 accumulator (one owner thread per
-//     (b,f): no atomics, deterministic order).
+//   * FP32-FMA-issue bound, not HBM and not tensor cores: the phasor depends on (source, baseline, channel) jointly, so the
+//     sum is no GEMM; the cost is the complex rotate + accumulate per term on the FMA pipe.
+//   * one thread owns one baseline x KT=32 consecutive channels, 64 fp32 accumulators in registers; a warp's 32 lanes are 32
+//     baselines of the same channel block, so amplitude reads are shared-memory broadcasts (one LDS.128 = 4 channels for
+//     the whole warp).
+//   * a CTA = 16 warps = SPC slabs of PB200_SLAB channels x 16/(4 SPC) baseline groups (default SPC = 4: 512 channels x 32
+//     baselines); it streams source tiles (32 rows per slab + fp64 geometry) through a double-buffered shared-memory ring
+//     filled by TMA bulk copies (cp.async.bulk + mbarrier).
+//   * persistent CTAs, one per SM: whole output tiles in waves, the remainder split along the source axis (stream-K) with
+//     deterministic head partials added by k_skyvis_finalize (struct Sched).
+//   * per tile the CTA first computes, cooperatively and once per (source, baseline), the delay tau = s.b/c - tau_pc in
+//     fp64 and from it the channel rotations r^2 (and r^8) to full fp32 accuracy, the MUFU argument increment of one
+//     channel and -- default quarter-block form -- the anchor phase and its per-block step as 32-bit fixed-point turn
+//     fractions, parked in shared memory for all channel-block warps of that baseline.
+//   * each thread anchors its channel block with exp(-2 pi i tau f_k0) on the MUFU (argument range-reduced in fp64 /
+//     fixed point and pre-scaled so that the MUFU's own 1/(2 pi) multiply lands on the reduced turn fraction without a
+//     systematic bias), both channels of the first pair directly.
+//   * channels advance two per packed FFMA2 (sm_100 f32x2): complex rotation by r^2 (MODE 0), or quarter blocks (MODE 3,
+//     default): anchors of the other 8-channel quarters by r^8, inside a quarter one rotation and two three-term steps.
+//   * fp32 accumulators are flushed into fp64 running sums (scratch in warp-tile layout, L2 evict-last) every
+//     FLUSH_TILES source tiles, after every tile for the brightest sources (sorted first by the caller); no atomics.
 #include "common.cuh"
 #include <cstdlib>
 #include <type_traits>
