@@ -399,3 +399,21 @@ def test_roi_parameters_save_and_init_file_roundtrip(tmp_path):
     assert back.pinfo[0]["pointing_coords"] == "altaz" and NP.array_equal(back.pinfo[0]["pointing_center"], roi.pinfo[0]["pointing_center"])
     assert back.pinfo[1]["delayerr"] == 2e-10 and "pointing_center" not in back.pinfo[1]
     assert back.pinfo[2]["pointing_coords"] == "dircos" and "delays" not in back.pinfo[2]
+
+
+def test_fixed_point_anchor_phase_identity():
+    """The quarter-block kernel (csrc/skyvis.cu, PB_Q3_INT) stages, per (source, baseline), the anchor phase at the CTA's
+    first channel and its step per 32-channel block as 32-bit fixed-point turn fractions; a thread's phase is the wrapping
+    integer sum X0 + block * D.  Numpy restatement of that arithmetic against the directly reduced phase: the difference
+    stays below (1 + 15) / 2 * 2^-32 turn (1.2e-8 rad, a tenth of an fp32 ulp of the MUFU argument)."""
+    rng = NP.random.default_rng(77)
+    tau = rng.uniform(-1.2e-6, 1.2e-6, 20000)                               # seconds: |b| <= 360 m
+    df = 97656.25
+    fcta0 = 100e6 + rng.integers(0, 8, tau.size) * 512 * df                  # first channel of a 4-slab CTA tile
+    block = rng.integers(0, 16, tau.size)
+    frac = lambda x: x - NP.rint(x)
+    to_fix = lambda x: NP.rint(frac(x) * 4294967296.0).astype(NP.int64) & 0xFFFFFFFF
+    X = (to_fix(tau * fcta0) + block * to_fix(tau * (32.0 * df))) & 0xFFFFFFFF
+    turns = NP.where(X >= 2 ** 31, X - 2 ** 32, X) / 4294967296.0
+    direct = frac(tau * (fcta0 + block * 32.0 * df))
+    assert NP.abs(frac(turns - direct)).max() <= 8.5 * 2.0 ** -32
